@@ -1,0 +1,259 @@
+"""ctypes mirror of include/hiphase_b200.h (the C ABI structs) plus numpy <-> struct packing helpers.
+
+The same struct layouts feed the product library (hiphase_b200/csrc/libhiphase_b200.so) and, in tests and the
+bench's CPU-baseline leg only, the oracle (oracle/libhp_oracle.so).
+"""
+import ctypes as C
+
+import numpy as np
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+u64p = C.POINTER(C.c_uint64)
+i64p = C.POINTER(C.c_int64)
+
+HP_OK = 0
+HP_ERR_INVALID_INPUT = -1
+HP_ERR_NO_DEVICE = -2
+HP_ERR_CUDA = -3
+HP_ERR_UNSUPPORTED = -4
+HP_ERR_OUT_OF_MEMORY = -5
+HP_ERR_INTERNAL = -6
+
+HP_BLOCK_OK = 0
+HP_BLOCK_IGNORED_NOT_NOOVERLAP = 1
+HP_BLOCK_COST_OVERFLOW = 2
+HP_BLOCK_QUEUE_OVERFLOW = 3
+HP_BLOCK_ASSERT = 4
+
+HP_WFA_OK = 0
+HP_WFA_MAX_EDIT_DISTANCE = 1
+HP_WFA_SKIPPED = 2
+
+# VariantType (src/data_types/variants.rs:8-31)
+VT_SNV, VT_INSERTION, VT_DELETION, VT_INDEL, VT_SV_INSERTION, VT_SV_DELETION = 0, 1, 2, 3, 4, 5
+VT_SV_DUPLICATION, VT_SV_INVERSION, VT_SV_BREAKEND, VT_TANDEM_REPEAT, VT_UNKNOWN = 6, 7, 8, 9, 10
+
+
+class hp_params(C.Structure):
+    _fields_ = [("min_queue_size", C.c_uint32), ("queue_increment", C.c_uint32),
+                ("wfa_prune_distance", C.c_uint32), ("wfa_max_edit_distance", C.c_uint32)]
+
+
+def default_params():
+    """Defaults of src/cli.rs:186-226."""
+    return hp_params(1000, 3, 500, 500)
+
+
+class hp_block_batch(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint32), ("var_off", u64p), ("read_off", u64p), ("read_start", u32p),
+                ("read_end", u32p), ("cell_off", u64p), ("alleles", u8p), ("quals", u8p),
+                ("ignored", u8p), ("is_snv", u8p)]
+
+
+class hp_phase_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("pruned_solutions", "estimated_cost", "actual_cost", "phased_variants",
+                                          "phased_snvs", "homozygous_variants", "skipped_variants")]
+
+
+class hp_astar_counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("evals", "cells", "sum_parent_len", "pops")]
+
+
+class hp_astar_out(C.Structure):
+    _fields_ = [("h1", u8p), ("h2", u8p), ("stats", C.POINTER(hp_phase_stats)), ("status", i32p),
+                ("heuristic", u64p), ("counters", C.POINTER(hp_astar_counters))]
+
+
+class hp_variant_table(C.Structure):
+    _fields_ = [("n_variants", C.c_uint32), ("position", i64p), ("ref_len", u32p), ("allele0_off", u64p),
+                ("allele0_len", u32p), ("allele1_off", u64p), ("allele1_len", u32p), ("index_allele0", u8p),
+                ("vtype", u8p), ("ignored", u8p), ("allele_bytes", u8p), ("n_allele_bytes", C.c_uint64)]
+
+
+class hp_wfa_batch(C.Structure):
+    _fields_ = [("n_jobs", C.c_uint32), ("variants", hp_variant_table), ("reference", u8p),
+                ("n_reference", C.c_uint64), ("ref_start", u64p), ("ref_end", u64p), ("het_lo", u32p),
+                ("het_hi", u32p), ("hom_lo", u32p), ("hom_hi", u32p), ("read_bytes", u8p), ("read_off", u64p),
+                ("row_off", u64p)]
+
+
+class hp_wfa_counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("bases_compared", "waves_processed", "set_ops", "n_nodes")]
+
+
+class hp_wfa_out(C.Structure):
+    _fields_ = [("status", i32p), ("score", u32p), ("alleles", u8p), ("quals", u8p), ("n_nodes", u32p),
+                ("traversed", u64p), ("trav_words", C.c_uint32), ("counters", C.POINTER(hp_wfa_counters))]
+
+
+STATS_DTYPE = np.dtype([(n, "<u8") for n, _ in hp_phase_stats._fields_])
+COUNTERS_DTYPE = np.dtype([(n, "<u8") for n, _ in hp_astar_counters._fields_])
+WFA_COUNTERS_DTYPE = np.dtype([(n, "<u8") for n, _ in hp_wfa_counters._fields_])
+
+
+def ptr(arr, ctype_ptr):
+    """Pointer to a C-contiguous numpy array (or NULL for None)."""
+    if arr is None:
+        return ctype_ptr()
+    assert arr.flags["C_CONTIGUOUS"]
+    return arr.ctypes.data_as(ctype_ptr)
+
+
+def _np(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class BlockBatch:
+    """A batch of phase blocks in the reference's u8 layout (numpy side of hp_block_batch)."""
+
+    FIELDS = ("var_off", "read_off", "read_start", "read_end", "cell_off", "alleles", "quals", "ignored", "is_snv")
+
+    def __init__(self, var_off, read_off, read_start, read_end, cell_off, alleles, quals, ignored, is_snv):
+        self.var_off = _np(var_off, np.uint64)
+        self.read_off = _np(read_off, np.uint64)
+        self.read_start = _np(read_start, np.uint32)
+        self.read_end = _np(read_end, np.uint32)
+        self.cell_off = _np(cell_off, np.uint64)
+        self.alleles = _np(alleles, np.uint8)
+        self.quals = _np(quals, np.uint8)
+        self.ignored = _np(ignored, np.uint8)
+        self.is_snv = _np(is_snv, np.uint8)
+        self.n_blocks = len(self.var_off) - 1
+        assert len(self.read_off) == self.n_blocks + 1
+        assert len(self.cell_off) == len(self.read_start) + 1 == len(self.read_end) + 1
+
+    @property
+    def n_vars(self):
+        return int(self.var_off[-1])
+
+    @property
+    def n_reads(self):
+        return int(self.read_off[-1])
+
+    @property
+    def n_cells(self):
+        return int(self.cell_off[-1])
+
+    def as_struct(self):
+        return hp_block_batch(self.n_blocks, ptr(self.var_off, u64p), ptr(self.read_off, u64p),
+                              ptr(self.read_start, u32p), ptr(self.read_end, u32p), ptr(self.cell_off, u64p),
+                              ptr(self.alleles, u8p), ptr(self.quals, u8p), ptr(self.ignored, u8p),
+                              ptr(self.is_snv, u8p))
+
+    @staticmethod
+    def from_blocks(blocks):
+        """blocks: list of dicts {n_var, reads:[(start, alleles_u8, quals_u8)], ignored, is_snv} (clipped reads)."""
+        var_off, read_off, rs, re, cell_off = [0], [0], [], [], [0]
+        al, ql, ig, sn = [], [], [], []
+        for b in blocks:
+            n = int(b["n_var"])
+            var_off.append(var_off[-1] + n)
+            ig.append(_np(b.get("ignored", np.zeros(n)), np.uint8))
+            sn.append(_np(b.get("is_snv", np.ones(n)), np.uint8))
+            for (start, a, q) in b["reads"]:
+                a = _np(a, np.uint8)
+                q = _np(q, np.uint8)
+                assert len(a) == len(q)
+                rs.append(int(start))
+                re.append(int(start) + len(a))
+                cell_off.append(cell_off[-1] + len(a))
+                al.append(a)
+                ql.append(q)
+            read_off.append(len(rs))
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+        return BlockBatch(var_off, read_off, rs, re, cell_off, cat(al), cat(ql), cat(ig), cat(sn))
+
+    def block(self, b):
+        """Block b back as a dict (for the slow python restatement and brute-force checks)."""
+        v0, v1 = int(self.var_off[b]), int(self.var_off[b + 1])
+        reads = []
+        for r in range(int(self.read_off[b]), int(self.read_off[b + 1])):
+            c0, c1 = int(self.cell_off[r]), int(self.cell_off[r + 1])
+            reads.append((int(self.read_start[r]), self.alleles[c0:c1].copy(), self.quals[c0:c1].copy()))
+        return {"n_var": v1 - v0, "reads": reads, "ignored": self.ignored[v0:v1].copy(), "is_snv": self.is_snv[v0:v1].copy()}
+
+    def select(self, idx):
+        return BlockBatch.from_blocks([self.block(int(i)) for i in idx])
+
+
+class AstarOut:
+    """Host-side result buffers of hp_astar_solve_batch."""
+
+    def __init__(self, batch, want_heuristic=False, want_counters=False):
+        self.h1 = np.full(batch.n_vars, 255, np.uint8)
+        self.h2 = np.full(batch.n_vars, 255, np.uint8)
+        self.stats = np.zeros(batch.n_blocks, STATS_DTYPE)
+        self.status = np.full(batch.n_blocks, -1, np.int32)
+        self.heuristic = np.zeros(batch.n_vars + batch.n_blocks, np.uint64) if want_heuristic else None
+        self.counters = np.zeros(batch.n_blocks, COUNTERS_DTYPE) if want_counters else None
+
+    def as_struct(self):
+        return hp_astar_out(ptr(self.h1, u8p), ptr(self.h2, u8p),
+                            self.stats.ctypes.data_as(C.POINTER(hp_phase_stats)), ptr(self.status, i32p),
+                            ptr(self.heuristic, u64p),
+                            self.counters.ctypes.data_as(C.POINTER(hp_astar_counters)) if self.counters is not None
+                            else C.POINTER(hp_astar_counters)())
+
+
+class WfaBatch:
+    """numpy side of hp_wfa_batch.  variants: dict of arrays (see hp_variant_table)."""
+
+    def __init__(self, variants, reference, ref_start, ref_end, het_lo, het_hi, hom_lo, hom_hi, read_bytes, read_off):
+        v = variants
+        self.position = _np(v["position"], np.int64)
+        self.ref_len = _np(v["ref_len"], np.uint32)
+        self.allele0_off = _np(v["allele0_off"], np.uint64)
+        self.allele0_len = _np(v["allele0_len"], np.uint32)
+        self.allele1_off = _np(v["allele1_off"], np.uint64)
+        self.allele1_len = _np(v["allele1_len"], np.uint32)
+        self.index_allele0 = _np(v["index_allele0"], np.uint8)
+        self.vtype = _np(v["vtype"], np.uint8)
+        self.ignored = _np(v["ignored"], np.uint8)
+        self.allele_bytes = _np(v["allele_bytes"], np.uint8)
+        self.reference = _np(reference, np.uint8)
+        self.ref_start = _np(ref_start, np.uint64)
+        self.ref_end = _np(ref_end, np.uint64)
+        self.het_lo = _np(het_lo, np.uint32)
+        self.het_hi = _np(het_hi, np.uint32)
+        self.hom_lo = _np(hom_lo, np.uint32)
+        self.hom_hi = _np(hom_hi, np.uint32)
+        self.read_bytes = _np(read_bytes, np.uint8)
+        self.read_off = _np(read_off, np.uint64)
+        self.n_jobs = len(self.ref_start)
+        row_len = (self.het_hi.astype(np.int64) - self.het_lo.astype(np.int64))
+        self.row_off = np.concatenate([[0], np.cumsum(row_len)]).astype(np.uint64)
+
+    @property
+    def n_variants(self):
+        return len(self.position)
+
+    def as_struct(self):
+        vt = hp_variant_table(self.n_variants, ptr(self.position, i64p), ptr(self.ref_len, u32p),
+                              ptr(self.allele0_off, u64p), ptr(self.allele0_len, u32p), ptr(self.allele1_off, u64p),
+                              ptr(self.allele1_len, u32p), ptr(self.index_allele0, u8p), ptr(self.vtype, u8p),
+                              ptr(self.ignored, u8p), ptr(self.allele_bytes, u8p), len(self.allele_bytes))
+        return hp_wfa_batch(self.n_jobs, vt, ptr(self.reference, u8p), len(self.reference), ptr(self.ref_start, u64p),
+                            ptr(self.ref_end, u64p), ptr(self.het_lo, u32p), ptr(self.het_hi, u32p),
+                            ptr(self.hom_lo, u32p), ptr(self.hom_hi, u32p), ptr(self.read_bytes, u8p),
+                            ptr(self.read_off, u64p), ptr(self.row_off, u64p))
+
+
+class WfaOut:
+    def __init__(self, batch, trav_words=0, want_counters=False):
+        n = batch.n_jobs
+        self.status = np.full(n, -1, np.int32)
+        self.score = np.zeros(n, np.uint32)
+        self.alleles = np.full(int(batch.row_off[-1]), 255, np.uint8)
+        self.quals = np.full(int(batch.row_off[-1]), 255, np.uint8)
+        self.n_nodes = np.zeros(n, np.uint32)
+        self.trav_words = int(trav_words)
+        self.traversed = np.zeros(n * trav_words, np.uint64) if trav_words else None
+        self.counters = np.zeros(n, WFA_COUNTERS_DTYPE) if want_counters else None
+
+    def as_struct(self):
+        return hp_wfa_out(ptr(self.status, i32p), ptr(self.score, u32p), ptr(self.alleles, u8p), ptr(self.quals, u8p),
+                          ptr(self.n_nodes, u32p), ptr(self.traversed, u64p), self.trav_words,
+                          self.counters.ctypes.data_as(C.POINTER(hp_wfa_counters)) if self.counters is not None
+                          else C.POINTER(hp_wfa_counters)())

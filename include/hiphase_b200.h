@@ -1,0 +1,255 @@
+/*
+ * hiphase_b200.h -- C ABI of the B200-native per-block phasing hot path.
+ *
+ * This is the drop-in boundary.  The reference (PacificBiosciences/HiPhase v1.5.0) has no FFI of its own:
+ * the hot path sits behind two internal Rust call sites, and each entry point below names the one it replaces.
+ *
+ *   call site 1  src/phaser.rs:541-543       astar_phaser::astar_solver(block, variants, read_segments,
+ *                                            min_queue_size, queue_increment) -> AstarResult
+ *                                            (src/astar_phaser.rs:426-633)
+ *   call site 2  src/read_parsing.rs:769-780 WFAGraph::from_reference_variants_with_hom(...)   (src/wfa_graph.rs:119)
+ *                                            WFAGraph::edit_distance_with_pruning(read, prune) (src/wfa_graph.rs:350)
+ *                                            + traversed nodes -> allele/qual row              (src/read_parsing.rs:790-851)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer it passes in; the library never frees them.
+ *   - every function returns an int status: HP_OK (0) or a negative HP_ERR_* code.  Conditions the reference
+ *     answers with panic!/assert! (e.g. src/astar_phaser.rs:439, 631) come back as HP_ERR_INVALID_INPUT or as a
+ *     per-block / per-job status, never as a crash.
+ *   - "host" entry points take host pointers (pinned or pageable) and do the H2D/D2H copies themselves;
+ *     "_device" entry points take device pointers on the context's GPU and a cudaStream_t (passed as void*).
+ *   - there is NO CPU fallback: without a CUDA device hp_ctx_create fails with HP_ERR_NO_DEVICE.
+ *   - re-entrancy: one hp_ctx per thread (the reference runs one solve_block per worker, src/main.rs:385-408);
+ *     different contexts may be used concurrently.
+ */
+#ifndef HIPHASE_B200_H
+#define HIPHASE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------------------------- */
+#define HP_OK                      0
+#define HP_ERR_INVALID_INPUT      -1   /* malformed batch (reference would panic / bail!)                      */
+#define HP_ERR_NO_DEVICE          -2   /* no CUDA device / wrong architecture: the product never runs on CPU   */
+#define HP_ERR_CUDA               -3   /* a CUDA runtime call failed; see hp_last_error()                      */
+#define HP_ERR_UNSUPPORTED        -4   /* parameters outside what the kernels were built for                   */
+#define HP_ERR_OUT_OF_MEMORY      -5
+#define HP_ERR_INTERNAL           -6
+
+/* per-block status written to hp_astar_out.status */
+#define HP_BLOCK_OK                0
+#define HP_BLOCK_IGNORED_NOT_NOOVERLAP  1  /* an ignored variant is not NoOverlap(3) in some read: astar_phaser.rs:435-442 */
+#define HP_BLOCK_COST_OVERFLOW     2   /* sum of all quals in the block >= 2^31: 32-bit cost path refused       */
+#define HP_BLOCK_QUEUE_OVERFLOW    3   /* internal: main queue outgrew its slab (retried transparently)         */
+#define HP_BLOCK_ASSERT            4   /* a reference assert! would have fired (e.g. astar_phaser.rs:284, 529)  */
+
+/* per-job status written to hp_wfa_out.status */
+#define HP_WFA_OK                  0
+#define HP_WFA_MAX_EDIT_DISTANCE   1   /* WFAGraphError::MaxEditDistance, src/wfa_graph.rs:645-648              */
+#define HP_WFA_SKIPPED             2   /* job overlaps no het variant (read_parsing.rs:703-712)                 */
+#define HP_WFA_WORKSPACE_OVERFLOW  3   /* internal: wave/set pool outgrew its slab (retried transparently)      */
+
+/* AlleleType, src/data_types/read_segments.rs:5-16 */
+#define HP_ALLELE_REFERENCE  0
+#define HP_ALLELE_ALTERNATE  1
+#define HP_ALLELE_AMBIGUOUS  2
+#define HP_ALLELE_NOOVERLAP  3
+
+/* VariantType, src/data_types/variants.rs:8-31 (numeric order of the Rust enum) */
+#define HP_VT_SNV            0
+#define HP_VT_INSERTION      1
+#define HP_VT_DELETION       2
+#define HP_VT_INDEL          3
+#define HP_VT_SV_INSERTION   4
+#define HP_VT_SV_DELETION    5
+#define HP_VT_SV_DUPLICATION 6
+#define HP_VT_SV_INVERSION   7
+#define HP_VT_SV_BREAKEND    8
+#define HP_VT_TANDEM_REPEAT  9
+#define HP_VT_UNKNOWN       10
+
+/* ---- parameters (defaults = src/cli.rs:186-226) ------------------------------------------------------------ */
+typedef struct hp_params {
+    uint32_t min_queue_size;        /* --phase-min-queue-size, default 1000 (cli.rs:215-219)                    */
+    uint32_t queue_increment;       /* --phase-queue-increment, default 3   (cli.rs:222-226)                    */
+    uint32_t wfa_prune_distance;    /* --global-pruning-distance, default 500; 0 = disabled (cli.rs:194-198,352)*/
+    uint32_t wfa_max_edit_distance; /* --global-realignment-max-ed, default 500 (cli.rs:187-191)                */
+} hp_params;
+
+void hp_default_params(hp_params* p);
+
+typedef struct hp_ctx hp_ctx;
+
+int  hp_abi_version(void);
+/* device < 0 selects the current CUDA device. */
+int  hp_ctx_create(const hp_params* params, int device, hp_ctx** out_ctx);
+void hp_ctx_destroy(hp_ctx* ctx);
+/* last error text of this context (or of the failed hp_ctx_create when ctx == NULL); never NULL. */
+const char* hp_last_error(const hp_ctx* ctx);
+
+/* ---- A* phasing: replaces astar_phaser::astar_solver (src/astar_phaser.rs:426) ---------------------------- */
+/*
+ * A batch of independent phase blocks in the reference's own u8 layout.  Block b owns
+ *   variants   [var_off[b],  var_off[b+1])    -> ignored[], is_snv[], and the outputs h1[], h2[]
+ *   reads      [read_off[b], read_off[b+1])   -> read_start[], read_end[], cell_off[]
+ * Read r is one collapsed ReadSegment (src/data_types/read_segments.rs:19-62): region = [read_start[r], read_end[r])
+ * in block-relative variant indices, and its clipped alleles / quals are the read_end-read_start bytes at
+ * alleles[cell_off[r] ..], quals[cell_off[r] ..]   (cell_off[r+1]-cell_off[r] == read_end[r]-read_start[r]).
+ */
+typedef struct hp_block_batch {
+    uint32_t        n_blocks;
+    const uint64_t* var_off;     /* [n_blocks+1]                                                           */
+    const uint64_t* read_off;    /* [n_blocks+1]                                                           */
+    const uint32_t* read_start;  /* [n_reads]                                                              */
+    const uint32_t* read_end;    /* [n_reads]                                                              */
+    const uint64_t* cell_off;    /* [n_reads+1]                                                            */
+    const uint8_t*  alleles;     /* [n_cells]   HP_ALLELE_*                                                */
+    const uint8_t*  quals;       /* [n_cells]                                                              */
+    const uint8_t*  ignored;     /* [n_vars]    Variant::is_ignored() (astar_phaser.rs:445-447)            */
+    const uint8_t*  is_snv;      /* [n_vars]    Variant::get_type()==Snv (astar_phaser.rs:606)             */
+} hp_block_batch;
+
+/* PhaseStats as produced by astar_solver (astar_phaser.rs:599-621; writers/phase_stats.rs:159-173). */
+typedef struct hp_phase_stats {
+    uint64_t pruned_solutions;
+    uint64_t estimated_cost;      /* H[0]                                                                  */
+    uint64_t actual_cost;
+    uint64_t phased_variants;
+    uint64_t phased_snvs;
+    uint64_t homozygous_variants;
+    uint64_t skipped_variants;
+} hp_phase_stats;
+
+/* Exact work counters of the reference algorithm for one block (SURVEY.md section 8d "algorithmic bytes"). */
+typedef struct hp_astar_counters {
+    uint64_t evals;          /* AstarNode::new_extended_node calls (astar_phaser.rs:69), pre-pass + main     */
+    uint64_t cells;          /* sum over evals and active reads of the window w_r one score_partial scans    */
+    uint64_t sum_parent_len; /* sum over evals of the parent haplotype length                                */
+    uint64_t pops;           /* queue pops, pre-pass + main                                                  */
+} hp_astar_counters;
+
+typedef struct hp_astar_out {
+    uint8_t*           h1;         /* [n_vars]  haplotype_1, values 0/1, 2 for ignored variants               */
+    uint8_t*           h2;         /* [n_vars]  haplotype_2                                                   */
+    hp_phase_stats*    stats;      /* [n_blocks]                                                              */
+    int32_t*           status;     /* [n_blocks] HP_BLOCK_*                                                   */
+    uint64_t*          heuristic;  /* optional (may be NULL): [n_vars + n_blocks], block b at var_off[b]+b, N+1 entries */
+    hp_astar_counters* counters;   /* optional (may be NULL): [n_blocks]                                      */
+} hp_astar_out;
+
+/* Host buffers in, host buffers out: H2D + kernels + D2H (the end-to-end call). */
+int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* batch, hp_astar_out* out);
+
+/*
+ * Device-resident variant: every pointer inside *batch and *out is a device pointer on the context's GPU; the
+ * work is enqueued on `stream` (a cudaStream_t) and the call returns without synchronising unless the internal
+ * queue slab has to be grown (then it synchronises and retries).  n_vars/n_reads/n_cells are the array lengths.
+ */
+int hp_astar_solve_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads,
+                          uint64_t n_cells, hp_astar_out* out, void* stream);
+
+/* Single-block convenience with the shape of call site 1 (host buffers). */
+int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads,
+                       const uint32_t* read_start, const uint32_t* read_end, const uint64_t* cell_off,
+                       const uint8_t* alleles, const uint8_t* quals,
+                       const uint8_t* ignored, const uint8_t* is_snv,
+                       uint8_t* h1, uint8_t* h2, hp_phase_stats* stats);
+
+/* Number of kernel launches this context has issued so far (for bench.py's gpu_launches). */
+uint64_t hp_launch_count(const hp_ctx* ctx);
+/* Device time (ms, CUDA events on the launching stream) of the dominant kernel in the last _device / _batch call. */
+float hp_last_kernel_ms(const hp_ctx* ctx);
+
+/* ---- graph-WFA realignment: replaces WFAGraph::{from_reference_variants_with_hom, edit_distance_with_pruning}
+ *      and the traversed-nodes -> allele row glue (src/wfa_graph.rs:119, 350; src/read_parsing.rs:790-851) ---- */
+/*
+ * Variant table (shared by all jobs of the batch).  Variant k:
+ *   position[k], ref_len[k]              Variant::position(), get_ref_len()
+ *   allele bytes                         get_truncated_allele0/1 (variants.rs:581-591) at
+ *                                        allele_bytes[allele0_off[k] .. allele0_off[k]+allele0_len[k]) etc.
+ *   index_allele0[k]                     convert_index(Reference) (variants.rs:649); != 0 means allele0 is an ALT
+ *   vtype[k]                             HP_VT_*  (quality table, read_parsing.rs:815-835)
+ *   ignored[k]                           is_ignored()
+ * Job j aligns read bytes read_bytes[read_off[j] .. read_off[j+1]) against the graph of reference window
+ * [ref_start[j], ref_end[j]) (coordinates into `reference`), het variants [het_lo[j], het_hi[j]) and hom
+ * variants [hom_lo[j], hom_hi[j]) -- both are index ranges into the one variant table (hets and homs are
+ * separate, position-sorted runs of it, exactly the two slices of read_parsing.rs:772-773).
+ * Output row j has row_len[j] = het_hi-het_lo cells at alleles[row_off[j] ..] / quals[row_off[j] ..]: the
+ * alleles/quals of read_parsing.rs:790-835 restricted to [first_overlap,last_overlap) (everything outside is
+ * NoOverlap/0 by construction).
+ */
+typedef struct hp_variant_table {
+    uint32_t        n_variants;
+    const int64_t*  position;
+    const uint32_t* ref_len;
+    const uint64_t* allele0_off;
+    const uint32_t* allele0_len;
+    const uint64_t* allele1_off;
+    const uint32_t* allele1_len;
+    const uint8_t*  index_allele0;
+    const uint8_t*  vtype;
+    const uint8_t*  ignored;
+    const uint8_t*  allele_bytes;
+    uint64_t        n_allele_bytes;
+} hp_variant_table;
+
+typedef struct hp_wfa_batch {
+    uint32_t         n_jobs;
+    hp_variant_table variants;
+    const uint8_t*   reference;      /* chromosome (or concatenated windows) bytes                          */
+    uint64_t         n_reference;
+    const uint64_t*  ref_start;      /* [n_jobs]                                                            */
+    const uint64_t*  ref_end;        /* [n_jobs]  exclusive                                                 */
+    const uint32_t*  het_lo;         /* [n_jobs]                                                            */
+    const uint32_t*  het_hi;
+    const uint32_t*  hom_lo;
+    const uint32_t*  hom_hi;
+    const uint8_t*   read_bytes;
+    const uint64_t*  read_off;       /* [n_jobs+1]                                                          */
+    const uint64_t*  row_off;        /* [n_jobs+1] offsets into the output rows                             */
+} hp_wfa_batch;
+
+typedef struct hp_wfa_counters {
+    uint64_t bases_compared;   /* executions of the compare at wfa_graph.rs:454-456                            */
+    uint64_t waves_processed;  /* (offset,set) entries visited at wfa_graph.rs:448                             */
+    uint64_t set_ops;          /* set unions / inserts at wfa_graph.rs:491-505, 538-551, 599-613               */
+    uint64_t n_nodes;
+} hp_wfa_counters;
+
+typedef struct hp_wfa_out {
+    int32_t*         status;         /* [n_jobs] HP_WFA_*                                                    */
+    uint32_t*        score;          /* [n_jobs] edit distance (max_edit_distance when status==1)            */
+    uint8_t*         alleles;        /* [row_off[n_jobs]]                                                    */
+    uint8_t*         quals;          /* [row_off[n_jobs]]                                                    */
+    uint32_t*        n_nodes;        /* optional [n_jobs]: node count of the job's graph                     */
+    uint64_t*        traversed;      /* optional: [n_jobs * trav_words] bitset of traversed node ids         */
+    uint32_t         trav_words;     /* 64-bit words per job in `traversed` (0 if traversed == NULL)         */
+    hp_wfa_counters* counters;       /* optional [n_jobs]                                                    */
+} hp_wfa_out;
+
+/* Host buffers in / out. */
+int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* batch, hp_wfa_out* out);
+
+/*
+ * Pre-built graph variant (the shape of WFAGraph::add_node + edit_distance_with_pruning, wfa_graph.rs:298, 350):
+ * node i has bytes seq[seq_off[i] .. seq_off[i+1]) and parents parent_idx[parent_off[i] .. parent_off[i+1]);
+ * nodes must be in topological insertion order; the last node is the sink.  One read per call.
+ * traversed must hold ceil(n_nodes/64) words.  Returns HP_OK and writes *status = HP_WFA_OK / HP_WFA_MAX_EDIT_DISTANCE.
+ */
+int hp_wfa_graph_align(hp_ctx* ctx, uint32_t n_nodes, const uint8_t* seq, const uint64_t* seq_off,
+                       const uint32_t* parent_idx, const uint64_t* parent_off,
+                       const uint8_t* read, uint64_t read_len,
+                       uint64_t prune_distance /* UINT64_MAX = off */, uint32_t max_edit_distance,
+                       int32_t* status, uint32_t* score, uint64_t* traversed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPHASE_B200_H */

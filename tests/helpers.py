@@ -1,0 +1,45 @@
+"""Shared helpers for the tests: golden-fixture loading and variant-table construction."""
+import json
+import os
+
+import numpy as np
+
+from hiphase_b200 import _abi as A
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_VT = {"snv": A.VT_SNV, "insertion": A.VT_INSERTION, "deletion": A.VT_DELETION, "indel": A.VT_INDEL,
+       "sv_insertion": A.VT_SV_INSERTION, "sv_deletion": A.VT_SV_DELETION, "tr": A.VT_TANDEM_REPEAT}
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def variant_table(variants):
+    """variants: list of dicts {type,pos,ref_len,a0,a1,i0[,ignored]} with *truncated* allele strings."""
+    blob = bytearray()
+    t = {k: [] for k in ("position", "ref_len", "allele0_off", "allele0_len", "allele1_off", "allele1_len",
+                         "index_allele0", "vtype", "ignored")}
+    for v in variants:
+        a0 = v["a0"].encode() if isinstance(v["a0"], str) else bytes(v["a0"])
+        a1 = v["a1"].encode() if isinstance(v["a1"], str) else bytes(v["a1"])
+        t["position"].append(v["pos"]); t["ref_len"].append(v["ref_len"])
+        t["allele0_off"].append(len(blob)); t["allele0_len"].append(len(a0)); blob += a0
+        t["allele1_off"].append(len(blob)); t["allele1_len"].append(len(a1)); blob += a1
+        t["index_allele0"].append(v.get("i0", 0)); t["vtype"].append(_VT[v["type"]]); t["ignored"].append(v.get("ignored", 0))
+    t["allele_bytes"] = np.frombuffer(bytes(blob), np.uint8) if blob else np.zeros(0, np.uint8)
+    return t
+
+
+def wfa_batch_single(reference, hets, homs, ref_start, ref_end, reads):
+    """One variant table (hets then homs), one job per read."""
+    ref = np.frombuffer(reference.encode() if isinstance(reference, str) else bytes(reference), np.uint8)
+    vt = variant_table(list(hets) + list(homs))
+    n = len(reads)
+    rb = [np.frombuffer(r.encode() if isinstance(r, str) else bytes(r), np.uint8) for r in reads]
+    read_off = np.concatenate([[0], np.cumsum([len(x) for x in rb])]) if n else np.zeros(1)
+    return A.WfaBatch(vt, ref, [ref_start] * n, [ref_end] * n, [0] * n, [len(hets)] * n, [len(hets)] * n,
+                      [len(hets) + len(homs)] * n, np.concatenate(rb) if n and sum(len(x) for x in rb) else np.zeros(0, np.uint8),
+                      read_off)
