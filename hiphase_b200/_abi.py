@@ -1,7 +1,7 @@
 """ctypes mirror of include/hiphase_b200.h (the C ABI structs) plus numpy <-> struct packing helpers.
 
 The same struct layouts feed the product library (hiphase_b200/csrc/libhiphase_b200.so) and, in tests and the
-bench's CPU-baseline leg only, the oracle (oracle/libhp_oracle.so).
+bench CPU-baseline leg only, the CPU checker under oracle/.
 """
 import ctypes as C
 

@@ -1,0 +1,384 @@
+// hp_api.cu -- host side of the C ABI (include/hiphase_b200.h): context, workspaces, H2D/D2H, kernel launches.
+// There is deliberately no CPU code path for the algorithms in this file.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hiphase_b200.h"
+#include "hp_device.cuh"
+#include "hp_host.h"
+
+namespace hp {
+
+thread_local std::string g_create_error;
+
+bool DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&ptr, want) != cudaSuccess) { cudaGetLastError(); ptr = nullptr; return false; }
+    cap = want;
+    return true;
+}
+void DevBuf::release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+
+__global__ void iota_kernel(uint32_t* p, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// Largest-first processing order (LPT): blocks are binned by floor(log2(n_cells * min(n_var, 40))) so the
+// longest serial chains start first and the tail of the persistent kernel stays short.
+__global__ void order_count_kernel(const BlkMeta* meta, uint32_t n, uint32_t* bins) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t cost = (uint64_t)meta[i].n_cells * min(meta[i].n_var, 40u) + meta[i].n_var;
+    const int bin = 63 - __clzll((long long)(cost | 1ull));
+    atomicAdd(&bins[63 - bin], 1u);
+}
+__global__ void order_scan_kernel(uint32_t* bins) {
+    uint32_t run = 0;
+    for (int i = 0; i < 64; i++) { uint32_t x = bins[i]; bins[i] = run; run += x; }
+}
+__global__ void order_fill_kernel(const BlkMeta* meta, uint32_t n, uint32_t* bins, uint32_t* order) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t cost = (uint64_t)meta[i].n_cells * min(meta[i].n_var, 40u) + meta[i].n_var;
+    const int bin = 63 - __clzll((long long)(cost | 1ull));
+    order[atomicAdd(&bins[63 - bin], 1u)] = i;
+}
+
+static int fail(hp_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define HP_CUDA(ctx, call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            cudaGetLastError();                                                                        \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? HP_ERR_OUT_OF_MEMORY : HP_ERR_CUDA,     \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+        }                                                                                              \
+    } while (0)
+
+static uint32_t sub_capl_for(const hp_params& p) {
+    const uint64_t max_visits = (uint64_t)p.min_queue_size / 10 + (uint64_t)p.queue_increment * HP_MAX_SEGMENT;
+    const uint64_t live = 1 + 3 * max_visits;
+    return (uint32_t)((live + 31) / 32 + 1);
+}
+
+int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads, uint64_t n_cells,
+                 uint32_t max_block_vars, hp_astar_out* out, cudaStream_t stream, int max_ctas) {
+    const uint32_t nb = batch->n_blocks;
+    if (nb == 0) return HP_OK;
+    if (n_cells >= (1ull << 32) || n_reads >= (1ull << 32) || n_cells / 64 + n_reads >= (1ull << 32))
+        return fail(ctx, HP_ERR_UNSUPPORTED, "batch too large for 32-bit indices: split it");
+    if (max_block_vars == 0) return fail(ctx, HP_ERR_INVALID_INPUT, "max_block_vars must be > 0");
+
+    const uint64_t n_words = n_cells / 64 + n_reads + 1;
+    const uint64_t n_vb = n_vars + nb;
+    if (!ctx->meta.reserve(sizeof(BlkMeta) * (size_t)nb) || !ctx->rmeta.reserve(sizeof(ReadMeta) * (size_t)(n_reads + 1)) ||
+        !ctx->planes.reserve(8ull * HP_PLANE_STRIDE * n_words) || !ctx->act_off.reserve(4 * n_vb) ||
+        !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->order.reserve(4ull * nb) ||
+        !ctx->heur.reserve(4 * n_vb) || !ctx->ticket.reserve(256 + 4 * 64))
+        return fail(ctx, HP_ERR_OUT_OF_MEMORY, "workspace allocation failed");
+
+    int n_ctas = std::min<int>((nb + astar_solve_warps() - 1) / astar_solve_warps(), ctx->sm_count);
+    if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
+    const uint32_t hap_words = (max_block_vars + 63) / 64;
+    const uint64_t slab_bytes = astar_slab_bytes(ctx->qcap, hap_words);
+    if (!ctx->slabs.reserve(slab_bytes * (uint64_t)n_ctas * astar_solve_warps()))
+        return fail(ctx, HP_ERR_OUT_OF_MEMORY, "queue slab allocation failed");
+
+    HP_CUDA(ctx, cudaMemsetAsync(ctx->act_off.ptr, 0, 4 * n_vb, stream));
+    HP_CUDA(ctx, cudaMemsetAsync(ctx->act_cur.ptr, 0, 4 * n_vb, stream));
+    HP_CUDA(ctx, cudaMemsetAsync(ctx->ticket.ptr, 0, 256 + 4 * 64, stream));
+
+    PrepArgs pa;
+    pa.n_blocks = nb; pa.var_off = batch->var_off; pa.read_off = batch->read_off; pa.read_start = batch->read_start;
+    pa.read_end = batch->read_end; pa.cell_off = batch->cell_off; pa.alleles = batch->alleles; pa.quals = batch->quals;
+    pa.ignored = batch->ignored;
+    pa.meta = (BlkMeta*)ctx->meta.ptr; pa.rmeta = (ReadMeta*)ctx->rmeta.ptr; pa.planes = (uint64_t*)ctx->planes.ptr;
+    pa.act_off = (uint32_t*)ctx->act_off.ptr; pa.act_cur = (uint32_t*)ctx->act_cur.ptr; pa.act_idx = (uint32_t*)ctx->act_idx.ptr;
+    HP_CUDA(ctx, launch_astar_prep(pa, stream));
+    ctx->launches++;
+
+    uint32_t* bins = (uint32_t*)((uint8_t*)ctx->ticket.ptr + 256);
+    const int tb = 256, gb = (nb + tb - 1) / tb;
+    order_count_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins);
+    order_scan_kernel<<<1, 1, 0, stream>>>(bins);
+    order_fill_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins, (uint32_t*)ctx->order.ptr);
+    HP_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+
+    AstarArgs a;
+    a.n_blocks = nb;
+    a.alleles = batch->alleles; a.quals = batch->quals; a.ignored = batch->ignored; a.is_snv = batch->is_snv;
+    a.meta = pa.meta; a.rmeta = pa.rmeta; a.planes = pa.planes; a.act_off = pa.act_off; a.act_idx = pa.act_idx;
+    a.order = (uint32_t*)ctx->order.ptr;
+    a.heur = (uint32_t*)ctx->heur.ptr; a.ticket = (uint32_t*)ctx->ticket.ptr;
+    a.slabs = (uint8_t*)ctx->slabs.ptr; a.slab_bytes = slab_bytes; a.qcap = ctx->qcap; a.hap_words = hap_words;
+    a.min_queue_size = ctx->params.min_queue_size; a.queue_increment = ctx->params.queue_increment;
+    a.sub_capl = ctx->sub_capl;
+    a.out_h1 = out->h1; a.out_h2 = out->h2; a.out_stats = (uint64_t*)out->stats; a.out_status = out->status;
+    a.out_heur = out->heuristic; a.out_counters = (uint64_t*)out->counters;
+
+    HP_CUDA(ctx, cudaEventRecord(ctx->ev0, stream));
+    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, stream));
+    HP_CUDA(ctx, cudaEventRecord(ctx->ev1, stream));
+    ctx->launches++;
+    ctx->timing_pending = true;
+    return HP_OK;
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" {
+
+int hp_abi_version(void) { return HP_ABI_VERSION; }
+
+void hp_default_params(hp_params* p) {
+    p->min_queue_size = 1000; p->queue_increment = 3; p->wfa_prune_distance = 500; p->wfa_max_edit_distance = 500;
+}
+
+const char* hp_last_error(const hp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hp_ctx_create(const hp_params* params, int device, hp_ctx** out_ctx) {
+    if (!out_ctx) return HP_ERR_INVALID_INPUT;
+    *out_ctx = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, HP_ERR_NO_DEVICE, "no CUDA device: hiphase_b200 has no CPU fallback");
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n_dev) return fail(nullptr, HP_ERR_NO_DEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, HP_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, HP_ERR_NO_DEVICE, "kernels are built for sm_100a (Blackwell B200) only");
+    hp_params p;
+    if (params) p = *params; else hp_default_params(&p);
+    // astar_subsolver visits min_queue_size/10 + queue_increment*size nodes (astar_phaser.rs:333); zero visits
+    // underflows next_expected-1 in the reference.
+    if ((uint64_t)p.min_queue_size / 10 + p.queue_increment == 0)
+        return fail(nullptr, HP_ERR_UNSUPPORTED, "min_queue_size/10 + queue_increment must be > 0");
+    const uint64_t max_visits = (uint64_t)p.min_queue_size / 10 + (uint64_t)p.queue_increment * HP_MAX_SEGMENT;
+    if (4 * max_visits + 2 >= (1u << 20)) return fail(nullptr, HP_ERR_UNSUPPORTED, "sub-solver visit budget exceeds the 20-bit node index");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, HP_ERR_CUDA, "cudaSetDevice failed");
+    const uint32_t capl = sub_capl_for(p);
+    if (astar_smem_bytes(capl) > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(nullptr, HP_ERR_UNSUPPORTED, "sub-solver queue does not fit shared memory for these parameters");
+
+    hp_ctx* ctx = new hp_ctx();
+    ctx->params = p; ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->sub_capl = capl;
+    uint64_t q = std::max<uint64_t>(16ull * p.min_queue_size + 384, 4096);
+    ctx->qcap = (uint32_t)std::min<uint64_t>((q + 31) & ~31ull, 1u << 24);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, HP_ERR_CUDA, "stream/event creation failed");
+    }
+    *out_ctx = ctx;
+    return HP_OK;
+}
+
+void hp_ctx_destroy(hp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->meta, &ctx->rmeta, &ctx->planes, &ctx->act_off, &ctx->act_cur, &ctx->act_idx, &ctx->order,
+                      &ctx->heur, &ctx->ticket, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out})
+        b->release();
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+uint64_t hp_launch_count(const hp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+float hp_last_kernel_ms(const hp_ctx* cctx) {
+    hp_ctx* ctx = const_cast<hp_ctx*>(cctx);
+    if (!ctx) return 0.f;
+    if (ctx->timing_pending) {
+        if (cudaEventSynchronize(ctx->ev1) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+        }
+        cudaGetLastError();
+        ctx->timing_pending = false;
+    }
+    return ctx->last_ms;
+}
+
+int hp_astar_solve_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads, uint64_t n_cells,
+                          uint32_t max_block_vars, hp_astar_out* out, void* stream) {
+    if (!ctx || !batch || !out) return HP_ERR_INVALID_INPUT;
+    HP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return astar_device(ctx, batch, n_vars, n_reads, n_cells, max_block_vars, out, (cudaStream_t)stream, 0);
+}
+
+static int validate_host_batch(hp_ctx* ctx, const hp_block_batch* b, uint32_t* max_n) {
+    if (!b->var_off || !b->read_off || !b->cell_off) return fail(ctx, HP_ERR_INVALID_INPUT, "null offset array");
+    uint32_t mx = 0;
+    if (b->var_off[0] != 0 || b->read_off[0] != 0 || b->cell_off[0] != 0) return fail(ctx, HP_ERR_INVALID_INPUT, "offset arrays must start at 0");
+    for (uint32_t i = 0; i < b->n_blocks; i++) {
+        if (b->var_off[i + 1] < b->var_off[i] || b->read_off[i + 1] < b->read_off[i])
+            return fail(ctx, HP_ERR_INVALID_INPUT, "offset arrays must be non-decreasing");
+        const uint64_t n = b->var_off[i + 1] - b->var_off[i];
+        if (n == 0) return fail(ctx, HP_ERR_INVALID_INPUT, "empty phase block (astar_solver is never called with 0 variants, phaser.rs:415-434)");
+        if (n > (1u << 24)) return fail(ctx, HP_ERR_UNSUPPORTED, "phase block with more than 2^24 variants");
+        mx = std::max<uint32_t>(mx, (uint32_t)n);
+    }
+    const uint64_t nr = b->read_off[b->n_blocks];
+    for (uint64_t r = 0; r < nr; r++)
+        if (b->cell_off[r + 1] < b->cell_off[r]) return fail(ctx, HP_ERR_INVALID_INPUT, "cell_off must be non-decreasing");
+    *max_n = mx;
+    return HP_OK;
+}
+
+// Carves `bytes` (256-aligned) out of a staging buffer.
+static uint8_t* carve(uint8_t*& p, size_t bytes) { uint8_t* r = p; p += (bytes + 255) & ~(size_t)255; return r; }
+
+static int astar_host_once(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out, uint32_t max_n, int max_ctas) {
+    const uint32_t nb = b->n_blocks;
+    const uint64_t n_vars = b->var_off[nb], n_reads = b->read_off[nb], n_cells = b->cell_off[n_reads];
+    cudaStream_t st = ctx->stream;
+    // ---- H2D ----
+    const size_t in_bytes = 256 * 12 + 8 * (nb + 1) * 2 + 4 * n_reads * 2 + 8 * (n_reads + 1) + n_cells * 2 + n_vars * 2;
+    if (!ctx->stage_in.reserve(in_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "input staging allocation failed");
+    uint8_t* p = (uint8_t*)ctx->stage_in.ptr;
+    hp_block_batch d = *b;
+#define HP_UP(field, type, count)                                                                                  \
+    do {                                                                                                           \
+        uint8_t* dst = carve(p, sizeof(type) * (size_t)(count));                                                   \
+        if ((count) > 0) HP_CUDA(ctx, cudaMemcpyAsync(dst, b->field, sizeof(type) * (size_t)(count), cudaMemcpyHostToDevice, st)); \
+        d.field = (const type*)dst;                                                                                \
+    } while (0)
+    HP_UP(var_off, uint64_t, nb + 1); HP_UP(read_off, uint64_t, nb + 1);
+    HP_UP(read_start, uint32_t, n_reads); HP_UP(read_end, uint32_t, n_reads); HP_UP(cell_off, uint64_t, n_reads + 1);
+    HP_UP(alleles, uint8_t, n_cells); HP_UP(quals, uint8_t, n_cells);
+    HP_UP(ignored, uint8_t, n_vars); HP_UP(is_snv, uint8_t, n_vars);
+#undef HP_UP
+    // ---- device outputs ----
+    const size_t out_bytes = 256 * 8 + n_vars * 2 + sizeof(hp_phase_stats) * (size_t)nb + 4ull * nb +
+                             (out->heuristic ? 8 * (n_vars + nb) : 0) + (out->counters ? sizeof(hp_astar_counters) * (size_t)nb : 0);
+    if (!ctx->stage_out.reserve(out_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "output staging allocation failed");
+    uint8_t* q = (uint8_t*)ctx->stage_out.ptr;
+    hp_astar_out dout;
+    dout.h1 = carve(q, n_vars); dout.h2 = carve(q, n_vars);
+    dout.stats = (hp_phase_stats*)carve(q, sizeof(hp_phase_stats) * (size_t)nb);
+    dout.status = (int32_t*)carve(q, 4ull * nb);
+    dout.heuristic = out->heuristic ? (uint64_t*)carve(q, 8 * (n_vars + nb)) : nullptr;
+    dout.counters = out->counters ? (hp_astar_counters*)carve(q, sizeof(hp_astar_counters) * (size_t)nb) : nullptr;
+
+    int rc = astar_device(ctx, &d, n_vars, n_reads, n_cells, max_n, &dout, st, max_ctas);
+    if (rc != HP_OK) return rc;
+    // ---- D2H ----
+    HP_CUDA(ctx, cudaMemcpyAsync(out->h1, dout.h1, n_vars, cudaMemcpyDeviceToHost, st));
+    HP_CUDA(ctx, cudaMemcpyAsync(out->h2, dout.h2, n_vars, cudaMemcpyDeviceToHost, st));
+    HP_CUDA(ctx, cudaMemcpyAsync(out->stats, dout.stats, sizeof(hp_phase_stats) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    HP_CUDA(ctx, cudaMemcpyAsync(out->status, dout.status, 4ull * nb, cudaMemcpyDeviceToHost, st));
+    if (out->heuristic) HP_CUDA(ctx, cudaMemcpyAsync(out->heuristic, dout.heuristic, 8 * (n_vars + nb), cudaMemcpyDeviceToHost, st));
+    if (out->counters) HP_CUDA(ctx, cudaMemcpyAsync(out->counters, dout.counters, sizeof(hp_astar_counters) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    HP_CUDA(ctx, cudaStreamSynchronize(st));
+    return HP_OK;
+}
+
+int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out) {
+    if (!ctx || !b || !out || !out->h1 || !out->h2 || !out->stats || !out->status) return HP_ERR_INVALID_INPUT;
+    if (b->n_blocks == 0) return HP_OK;
+    HP_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t max_n = 0;
+    int rc = validate_host_batch(ctx, b, &max_n);
+    if (rc != HP_OK) return rc;
+    rc = astar_host_once(ctx, b, out, max_n, 0);
+    if (rc != HP_OK) return rc;
+
+    // Blocks whose main queue outgrew its slab are re-run with a 4x larger slab (and fewer resident warps).
+    const uint32_t qcap0 = ctx->qcap;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        std::vector<uint32_t> redo;
+        for (uint32_t i = 0; i < b->n_blocks; i++) if (out->status[i] == HP_BLOCK_QUEUE_OVERFLOW) redo.push_back(i);
+        if (redo.empty()) break;
+        if (ctx->qcap >= (1u << 24)) break;
+        ctx->qcap = std::min<uint32_t>(ctx->qcap * 4, 1u << 24);
+        // gather the sub-batch on the host
+        std::vector<uint64_t> var_off{0}, read_off{0}, cell_off{0};
+        std::vector<uint32_t> rs, re;
+        std::vector<uint8_t> al, ql, ig, sn;
+        uint32_t sub_max = 0;
+        for (uint32_t i : redo) {
+            const uint64_t v0 = b->var_off[i], v1 = b->var_off[i + 1];
+            sub_max = std::max<uint32_t>(sub_max, (uint32_t)(v1 - v0));
+            ig.insert(ig.end(), b->ignored + v0, b->ignored + v1);
+            sn.insert(sn.end(), b->is_snv + v0, b->is_snv + v1);
+            var_off.push_back(var_off.back() + (v1 - v0));
+            for (uint64_t r = b->read_off[i]; r < b->read_off[i + 1]; r++) {
+                rs.push_back(b->read_start[r]); re.push_back(b->read_end[r]);
+                al.insert(al.end(), b->alleles + b->cell_off[r], b->alleles + b->cell_off[r + 1]);
+                ql.insert(ql.end(), b->quals + b->cell_off[r], b->quals + b->cell_off[r + 1]);
+                cell_off.push_back(cell_off.back() + (b->cell_off[r + 1] - b->cell_off[r]));
+            }
+            read_off.push_back(rs.size());
+        }
+        hp_block_batch sb;
+        sb.n_blocks = (uint32_t)redo.size();
+        sb.var_off = var_off.data(); sb.read_off = read_off.data(); sb.read_start = rs.data(); sb.read_end = re.data();
+        sb.cell_off = cell_off.data(); sb.alleles = al.data(); sb.quals = ql.data(); sb.ignored = ig.data(); sb.is_snv = sn.data();
+        const uint64_t nv = var_off.back();
+        std::vector<uint8_t> h1(nv), h2(nv);
+        std::vector<hp_phase_stats> stats(redo.size());
+        std::vector<int32_t> status(redo.size());
+        std::vector<uint64_t> heur(out->heuristic ? nv + redo.size() : 0);
+        std::vector<hp_astar_counters> ctr(out->counters ? redo.size() : 0);
+        hp_astar_out so;
+        so.h1 = h1.data(); so.h2 = h2.data(); so.stats = stats.data(); so.status = status.data();
+        so.heuristic = out->heuristic ? heur.data() : nullptr; so.counters = out->counters ? ctr.data() : nullptr;
+        // keep the slab arena under ~24 GB
+        const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64) * astar_solve_warps();
+        int max_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>(ctx->sm_count, (24ull << 30) / std::max<uint64_t>(slab, 1)));
+        rc = astar_host_once(ctx, &sb, &so, sub_max, max_ctas);
+        if (rc != HP_OK) { ctx->qcap = qcap0; return rc; }
+        for (size_t k = 0; k < redo.size(); k++) {
+            const uint32_t i = redo[k];
+            const uint64_t v0 = b->var_off[i], n = b->var_off[i + 1] - v0;
+            memcpy(out->h1 + v0, h1.data() + var_off[k], n); memcpy(out->h2 + v0, h2.data() + var_off[k], n);
+            out->stats[i] = stats[k]; out->status[i] = status[k];
+            if (out->heuristic) memcpy(out->heuristic + v0 + i, heur.data() + var_off[k] + k, 8 * (n + 1));
+            if (out->counters) out->counters[i] = ctr[k];
+        }
+    }
+    ctx->qcap = qcap0;
+    return HP_OK;
+}
+
+int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads, const uint32_t* read_start, const uint32_t* read_end,
+                       const uint64_t* cell_off, const uint8_t* alleles, const uint8_t* quals, const uint8_t* ignored,
+                       const uint8_t* is_snv, uint8_t* h1, uint8_t* h2, hp_phase_stats* stats) {
+    if (!ctx) return HP_ERR_INVALID_INPUT;
+    uint64_t var_off[2] = {0, n_var}, read_off[2] = {0, n_reads};
+    hp_block_batch b;
+    b.n_blocks = 1; b.var_off = var_off; b.read_off = read_off; b.read_start = read_start; b.read_end = read_end;
+    b.cell_off = cell_off; b.alleles = alleles; b.quals = quals; b.ignored = ignored; b.is_snv = is_snv;
+    int32_t status = -1;
+    hp_astar_out o;
+    o.h1 = h1; o.h2 = h2; o.stats = stats; o.status = &status; o.heuristic = nullptr; o.counters = nullptr;
+    int rc = hp_astar_solve_batch(ctx, &b, &o);
+    if (rc != HP_OK) return rc;
+    if (status != HP_BLOCK_OK) {
+        // the reference panics here (astar_phaser.rs:439, 529, 631)
+        return fail(ctx, HP_ERR_INVALID_INPUT, "block rejected with per-block status " + std::to_string(status));
+    }
+    return HP_OK;
+}
+
+}  // extern "C"

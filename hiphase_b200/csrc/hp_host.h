@@ -1,0 +1,47 @@
+// hp_host.h -- host-side context shared by the API translation units.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hiphase_b200.h"
+#include "hp_device.cuh"
+
+namespace hp {
+
+// Grow-only device buffer.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes);
+    void release();
+};
+
+// kernel launchers (astar_kernels.cu)
+size_t astar_smem_bytes(uint32_t sub_capl);
+int astar_solve_warps();
+uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words);
+cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream);
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, cudaStream_t stream);
+
+}  // namespace hp
+
+struct hp_ctx {
+    hp_params params;
+    int device = 0;
+    int sm_count = 0;
+    uint32_t sub_capl = 0;
+    uint32_t qcap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_pending = false;
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+    std::string err;
+    // A* workspaces
+    hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, order, heur, ticket, slabs, stage_in, stage_out;
+    // WFA workspaces
+    hp::DevBuf wfa_ws, wfa_in, wfa_out;
+};

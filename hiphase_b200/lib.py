@@ -1,0 +1,108 @@
+"""Loader for the product library hiphase_b200/csrc/libhiphase_b200.so (the C ABI of include/hiphase_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no B200 is visible, every call fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+from . import _abi as A
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(CSRC, "libhiphase_b200.so")
+
+EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
+           "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
+           "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align")
+
+_LIB = None
+
+
+class HiPhaseB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("hiphase_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(force=False):
+    """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.run(["make", "-s", "-C", CSRC], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise HiPhaseB200Error(A.HP_ERR_INTERNAL, "CUDA extension not built: %s is missing (run __graft_entry__.build())" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.hp_abi_version.restype = C.c_int
+        L.hp_default_params.argtypes = [C.POINTER(A.hp_params)]
+        L.hp_ctx_create.argtypes = [C.POINTER(A.hp_params), C.c_int, C.POINTER(C.c_void_p)]
+        L.hp_ctx_destroy.argtypes = [C.c_void_p]
+        L.hp_last_error.restype = C.c_char_p
+        L.hp_last_error.argtypes = [C.c_void_p]
+        L.hp_astar_solve_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.POINTER(A.hp_astar_out)]
+        L.hp_astar_solve_device.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.c_uint64, C.c_uint64, C.c_uint64,
+                                            C.c_uint32, C.POINTER(A.hp_astar_out), C.c_void_p]
+        L.hp_astar_solve_one.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, A.u32p, A.u32p, A.u64p, A.u8p, A.u8p, A.u8p,
+                                         A.u8p, A.u8p, A.u8p, C.POINTER(A.hp_phase_stats)]
+        L.hp_launch_count.restype = C.c_uint64
+        L.hp_launch_count.argtypes = [C.c_void_p]
+        L.hp_last_kernel_ms.restype = C.c_float
+        L.hp_last_kernel_ms.argtypes = [C.c_void_p]
+        L.hp_wfa_align_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_wfa_batch), C.POINTER(A.hp_wfa_out)]
+        L.hp_wfa_graph_align.argtypes = [C.c_void_p, C.c_uint32, A.u8p, A.u64p, A.u32p, A.u64p, A.u8p, C.c_uint64,
+                                         C.c_uint64, C.c_uint32, A.i32p, A.u32p, A.u64p]
+        _LIB = L
+    return _LIB
+
+
+class Context:
+    """hp_ctx handle.  One per thread (src/main.rs:385-408 runs one solve_block per worker)."""
+
+    def __init__(self, params=None, device=-1):
+        self.params = params or A.default_params()
+        self._h = C.c_void_p()
+        rc = lib().hp_ctx_create(C.byref(self.params), int(device), C.byref(self._h))
+        if rc != A.HP_OK:
+            raise HiPhaseB200Error(rc, (lib().hp_last_error(None) or b"").decode())
+
+    def close(self):
+        if self._h:
+            lib().hp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != A.HP_OK:
+            raise HiPhaseB200Error(rc, (lib().hp_last_error(self._h) or b"").decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self):
+        return int(lib().hp_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        return float(lib().hp_last_kernel_ms(self._h))
+
+    # ---- A* ----
+    def astar_solve_batch(self, batch, want_heuristic=False, want_counters=False):
+        """Host buffers in / out (H2D + kernels + D2H): the end-to-end call.  Returns an AstarOut."""
+        out = A.AstarOut(batch, want_heuristic, want_counters)
+        bs, os_ = batch.as_struct(), out.as_struct()
+        self.check(lib().hp_astar_solve_batch(self._h, C.byref(bs), C.byref(os_)))
+        return out
+
+    def astar_solve_device(self, dev_batch_struct, n_vars, n_reads, n_cells, max_block_vars, dev_out_struct, stream):
+        self.check(lib().hp_astar_solve_device(self._h, C.byref(dev_batch_struct), n_vars, n_reads, n_cells,
+                                               max_block_vars, C.byref(dev_out_struct), C.c_void_p(stream)))

@@ -149,11 +149,13 @@ int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* batch, hp_astar_out*
 
 /*
  * Device-resident variant: every pointer inside *batch and *out is a device pointer on the context's GPU; the
- * work is enqueued on `stream` (a cudaStream_t) and the call returns without synchronising unless the internal
- * queue slab has to be grown (then it synchronises and retries).  n_vars/n_reads/n_cells are the array lengths.
+ * work is enqueued on `stream` (a cudaStream_t) and the call returns without synchronising.  n_vars / n_reads /
+ * n_cells are the array lengths and max_block_vars the largest block's variant count (sizes the queue records).
+ * A block whose main queue outgrows its slab reports HP_BLOCK_QUEUE_OVERFLOW (hp_astar_solve_batch retries those
+ * transparently with a larger slab; this entry point leaves the retry to the caller).
  */
 int hp_astar_solve_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads,
-                          uint64_t n_cells, hp_astar_out* out, void* stream);
+                          uint64_t n_cells, uint32_t max_block_vars, hp_astar_out* out, void* stream);
 
 /* Single-block convenience with the shape of call site 1 (host buffers). */
 int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads,

@@ -1,0 +1,149 @@
+"""Parity of the CUDA A* path (through the C ABI) against the CPU oracle: bit-exact haplotypes, PhaseStats,
+heuristic vector and work counters on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from hiphase_b200 import _abi as A
+from hiphase_b200 import lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lib.Context(device=0)
+    yield c
+    c.close()
+
+
+def assert_parity(batch, out, ref):
+    assert np.array_equal(out.status, ref.status), (out.status[:16], ref.status[:16])
+    bad = np.flatnonzero(~((out.stats == ref.stats)))
+    assert len(bad) == 0, ("PhaseStats differ", bad[:5], out.stats[bad[:3]], ref.stats[bad[:3]])
+    assert np.array_equal(out.h1, ref.h1) and np.array_equal(out.h2, ref.h2)
+    if out.heuristic is not None:
+        assert np.array_equal(out.heuristic, ref.heuristic)
+    if out.counters is not None:
+        assert np.array_equal(out.counters, ref.counters)
+
+
+def run_both(ctx, batch, params=None):
+    c = ctx if params is None else lib.Context(params, device=0)
+    out = c.astar_solve_batch(batch, want_heuristic=True, want_counters=True)
+    ref = O.astar_solve(batch, params, threads=8)
+    assert_parity(batch, out, ref)
+    if params is not None:
+        c.close()
+    return out, ref
+
+
+def test_c1_single_block(ctx):
+    out, _ = run_both(ctx, synth.config_c1())
+    assert out.status[0] == 0 and out.stats[0]["phased_variants"] > 0
+
+
+def test_c2_subset(ctx):
+    run_both(ctx, synth.config_c2(n_blocks=64))
+
+
+def test_c2_dense_subset(ctx):
+    run_both(ctx, synth.config_c2_dense(n_blocks=6))
+
+
+def test_c3_subset_mixed_sizes(ctx):
+    run_both(ctx, synth.config_c3(n_blocks=48))
+
+
+def _rand_blocks(seed, n, nlo, nhi, smax_hi=14, p_err=0.05, p_amb=0.05, p_gap=0.03):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        N = int(rng.integers(nlo, nhi + 1))
+        R = int(rng.integers(2, 4 * N + 3))
+        smax = max(2, min(N, int(rng.integers(2, smax_hi))))
+        out.append(synth.gen_block(rng, N, R, lambda r, k, s=smax: r.integers(1, s + 1, k), p_err, p_amb, p_gap, p_ignored=0.08))
+    return out
+
+
+def test_random_small_blocks(ctx):
+    run_both(ctx, A.BlockBatch.from_blocks(_rand_blocks(21, 200, 1, 60)))
+
+
+def test_long_reads_multiword(ctx):
+    # read regions longer than 64 and 128 variants: multi-word plane records in both solvers
+    run_both(ctx, A.BlockBatch.from_blocks(_rand_blocks(22, 24, 150, 400, smax_hi=300)))
+
+
+def test_pruning_and_full_prune(ctx):
+    params = A.hp_params(10, 1, 500, 500)
+    batch = A.BlockBatch.from_blocks(_rand_blocks(23, 40, 20, 60, p_err=0.3))
+    out, ref = run_both(ctx, batch, params)
+    assert (ref.stats["pruned_solutions"] > 0).any()
+
+
+def test_noisy_default_params(ctx):
+    run_both(ctx, A.BlockBatch.from_blocks(_rand_blocks(24, 12, 150, 300, smax_hi=30, p_err=0.2)))
+
+
+def test_arbitrary_quals(ctx):
+    # local-realignment style quals: arbitrary u8 values, non-zero quals on ambiguous cells (read_segments.rs:233-241)
+    rng = np.random.default_rng(25)
+    blocks = _rand_blocks(25, 60, 2, 50)
+    for b in blocks:
+        b["reads"] = [(s, a, rng.integers(0, 256, len(a)).astype(np.uint8)) for (s, a, q) in b["reads"]]
+    run_both(ctx, A.BlockBatch.from_blocks(blocks))
+
+
+def test_edge_blocks(ctx):
+    blocks = [{"n_var": 1, "reads": []}, {"n_var": 3, "reads": []}, {"n_var": 2, "reads": [(0, [0, 1], [9, 9])]},
+              {"n_var": 5, "reads": [(1, [1, 3, 0], [7, 0, 7])], "ignored": [0, 0, 1, 0, 0]}]
+    out, _ = run_both(ctx, A.BlockBatch.from_blocks(blocks))
+    assert out.h1[:1].tolist() == [0] and out.h2[:1].tolist() == [1]
+
+
+def test_rejected_blocks_report_status(ctx):
+    blocks = [{"n_var": 4, "reads": [(0, [0, 1, 0, 1], [5, 5, 5, 5])], "ignored": [0, 1, 0, 0]},
+              {"n_var": 4, "reads": [(0, [0, 1, 0, 1], [5, 5, 5, 5])]}]
+    batch = A.BlockBatch.from_blocks(blocks)
+    out = ctx.astar_solve_batch(batch)
+    assert out.status.tolist() == [A.HP_BLOCK_IGNORED_NOT_NOOVERLAP, A.HP_BLOCK_OK]
+    ref = O.astar_solve(batch)
+    assert ref.status.tolist() == out.status.tolist()
+    assert np.array_equal(out.h1[4:], ref.h1[4:])
+
+
+def test_solve_one_call_site_shape(ctx):
+    import ctypes as C
+    b = synth.config_c1()
+    h1 = np.zeros(b.n_vars, np.uint8); h2 = np.zeros(b.n_vars, np.uint8)
+    st = A.hp_phase_stats()
+    rc = lib.lib().hp_astar_solve_one(ctx.handle, b.n_vars, b.n_reads, A.ptr(b.read_start, A.u32p), A.ptr(b.read_end, A.u32p),
+                                      A.ptr(b.cell_off, A.u64p), A.ptr(b.alleles, A.u8p), A.ptr(b.quals, A.u8p),
+                                      A.ptr(b.ignored, A.u8p), A.ptr(b.is_snv, A.u8p), A.ptr(h1, A.u8p), A.ptr(h2, A.u8p), C.byref(st))
+    assert rc == 0
+    ref = O.astar_solve(b)
+    assert np.array_equal(h1, ref.h1) and np.array_equal(h2, ref.h2) and st.actual_cost == ref.stats[0]["actual_cost"]
+
+
+def test_full_c2_properties(ctx):
+    # full BASELINE size (1000 blocks): size-independent properties + oracle on a sample
+    batch = synth.config_c2(n_blocks=1000)
+    out = ctx.astar_solve_batch(batch, want_heuristic=True)
+    assert (out.status == 0).all()
+    st = out.stats
+    n = np.diff(batch.var_off.astype(np.int64))
+    assert (st["actual_cost"] >= st["estimated_cost"]).all()
+    assert ((st["phased_variants"] + st["homozygous_variants"] + st["skipped_variants"]) == n).all()
+    ign = batch.ignored.astype(bool)
+    assert (out.h1[ign] == 2).all() and (out.h2[ign] == 2).all() and (out.h1[~ign] < 2).all()
+    # idempotence: a second run gives identical bytes
+    out2 = ctx.astar_solve_batch(batch, want_heuristic=True)
+    assert np.array_equal(out.h1, out2.h1) and np.array_equal(out.stats, out2.stats)
+    idx = np.arange(0, 1000, 37)
+    sub = batch.select(idx)
+    ref = O.astar_solve(sub, threads=8)
+    for k, i in enumerate(idx):
+        v0, v1 = int(batch.var_off[i]), int(batch.var_off[i + 1])
+        s0 = int(sub.var_off[k])
+        assert np.array_equal(out.h1[v0:v1], ref.h1[s0:s0 + v1 - v0]) and out.stats[i] == ref.stats[k]
