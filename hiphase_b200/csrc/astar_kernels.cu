@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
     __shared__ uint32_t s_maxspan;
     __shared__ uint8_t s_div[256];
     __shared__ uint32_t s_partial[kPrepThreads];
-    __shared__ uint32_t s_g, s_planes;
+    __shared__ uint32_t s_g, s_planes, s_maxact;
 
     if (tid < 8) s_presence[tid] = 0;
-    if (tid == 0) { s_qsum = 0; s_status = HP_BLOCK_OK; s_maxspan = 0; }
+    if (tid == 0) { s_qsum = 0; s_status = HP_BLOCK_OK; s_maxspan = 0; s_maxact = 0; }
     __syncthreads();
 
     uint32_t* cnt = a.act_off + v0 + b;   // N + 1 entries
@@ -110,9 +110,10 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
     const uint32_t chunk = (N + 1 + kPrepThreads - 1) / kPrepThreads;
     const uint32_t lo = min(N + 1, tid * chunk), hi = min(N + 1, lo + chunk);
     {
-        uint32_t sum = 0;
-        for (uint32_t i = lo; i < hi; i++) sum += __ldcg(&cnt[i]);
+        uint32_t sum = 0, mx = 0;
+        for (uint32_t i = lo; i < hi; i++) { const uint32_t x = __ldcg(&cnt[i]); sum += x; mx = max(mx, x); }
         s_partial[tid] = sum;
+        if (mx) atomicMax(&s_maxact, mx);
     }
     __syncthreads();
     if (tid == 0) {
@@ -126,7 +127,9 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
     }
     __syncthreads();
 
-    // ---- pass 2: bit planes + active lists ----
+    if (tid == 0 && s_maxact >= 0xffffu && s_status == HP_BLOCK_OK) s_status = HP_BLOCK_TOO_DENSE;
+    __syncthreads();
+    // ---- pass 2: bit planes, active lists and column records ----
     if (s_status == HP_BLOCK_OK) {
         for (uint64_t r = r0 + tid; r < r1; r += kPrepThreads) {
             const uint32_t s = a.read_start[r], e = a.read_end[r];
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
             uint64_t w[HP_PLANE_STRIDE];
 #pragma unroll
             for (int k = 0; k < (int)HP_PLANE_STRIDE; k++) w[k] = 0;
+            uint32_t prev_slot = 0xffffu;            // slot of this read in the previous column's active list
             for (uint32_t i = 0; i < e - s; i++) {
                 const uint8_t al = a.alleles[c + i];
                 const uint32_t p = s + i;
@@ -146,7 +150,11 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) if (q >> k & 1u) w[2 + k] |= bit;
                 const uint32_t slot = atomicAdd(&cur[p], 1u);
-                a.act_idx[c0 + __ldcg(&cnt[p]) + slot] = (uint32_t)(r - r0);
+                const uint64_t at = c0 + __ldcg(&cnt[p]) + slot;
+                a.act_idx[at] = (uint32_t)(r - r0);
+                // column record: qual | allele<<8 | ends<<10 | carry<<16 (carry = slot in column p-1, 0xffff = read starts here)
+                a.col[at] = (uint32_t)a.quals[c + i] | ((uint32_t)al << 8) | ((i + 1 == e - s) ? (1u << 10) : 0u) | (prev_slot << 16);
+                prev_slot = slot;
                 if ((i & 63) == 63 || i + 1 == e - s) {
 #pragma unroll
                     for (int k = 0; k < (int)HP_PLANE_STRIDE; k++) { rec[k] = w[k]; w[k] = 0; }
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
         BlkMeta m;
         m.var_base = v0; m.read_base = r0; m.cell_base = c0;
         m.n_var = N; m.n_reads = R; m.n_cells = (uint32_t)(c1 - c0);
-        m.qgcd = g; m.n_planes = s_planes; m.status = s_status; m.max_span = s_maxspan; m.pad = 0;
+        m.qgcd = g; m.n_planes = s_planes; m.status = s_status; m.max_span = s_maxspan; m.max_act = s_maxact;
         a.meta[b] = m;
     }
 }
@@ -171,60 +179,136 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
 // ---- warp reductions -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t wsum(uint32_t x) { return __reduce_add_sync(HP_FULL_MASK, x); }
 __device__ __forceinline__ uint32_t wmin(uint32_t x) { return __reduce_min_sync(HP_FULL_MASK, x); }
+__device__ __forceinline__ uint64_t wmin64(uint64_t x) {
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    const uint32_t mhi = wmin(hi);
+    const uint32_t mlo = wmin(hi == mhi ? lo : 0xffffffffu);
+    return ((uint64_t)mhi << 32) | mlo;
+}
 
-// Per-lane accumulators of one expansion: deltas of the four children (0|1),(1|0),(0/0),(1/1) and of the
-// single (2,2) child of an ignored variant; "t" = all active reads, "f" = reads that end at this column.
-struct ChildAcc {
-    uint32_t t01, t10, t00, t11, f01, f10, f00, f11, tb, fb;
+// ---- bit-plane scoring (the from-scratch path) --------------------------------------------------------------
+// Scores one read against both haplotypes of a node over read coordinates [max(0,o), o+L):
+//   o     = read coordinate of haplotype position 0   (problem_offset - read.start, may be negative)
+//   L     = haplotype length
+//   HapFn = functor(which, bitpos) -> 64 haplotype bits starting at haplotype position bitpos (may be < 0)
+// This is ReadSegment::score_partial_haplotype (read_segments.rs:177-206) for h1 and h2 at once:
+// cost = qgcd * sum_b 2^b * popc(range & ((hap ^ allele_bits) | non_binary) & quality_plane_b).
+template <class HapFn>
+__device__ __forceinline__ void score_planes(const AstarArgs& a, const BlkMeta& m, const ReadMeta rm, int o, int L,
+                                             HapFn hap, uint32_t& s1, uint32_t& s2) {
+    s1 = 0; s2 = 0;
+    const int c_lo = max(0, o), c_hi = o + L;
+    if (c_hi <= c_lo) return;
+    const int k_lo = c_lo >> 6, k_hi = (c_hi - 1) >> 6;
+    const uint64_t* rec = a.planes + (uint64_t)rm.word_idx * HP_PLANE_STRIDE;
+    for (int k = k_lo; k <= k_hi; k++) {
+        const uint64_t* w = rec + (uint64_t)k * HP_PLANE_STRIDE;
+        const uint64_t range = bit_range(max(0, c_lo - 64 * k), min(64, c_hi - 64 * k));
+        const uint64_t ab = __ldg(w + 0), nb = __ldg(w + 1);
+        const int i0 = 64 * k - o;                    // haplotype position of this word's bit 0
+        const uint64_t m1 = range & ((hap(0, i0) ^ ab) | nb);
+        const uint64_t m2 = range & ((hap(1, i0) ^ ab) | nb);
+        for (uint32_t bpl = 0; bpl < m.n_planes; bpl++) {
+            const uint64_t q = __ldg(w + 2 + bpl);
+            s1 += (uint32_t)__popcll(m1 & q) << bpl;
+            s2 += (uint32_t)__popcll(m2 & q) << bpl;
+        }
+    }
+    s1 *= m.qgcd; s2 *= m.qgcd;
+}
+
+// ---- incremental expansion ------------------------------------------------------------------------------------
+// Candidate children of one expansion, fixed slots (creation order of astar_phaser.rs:367-372 / 535-540):
+//   0 = (0|1), 1 = (1|0), 2 = (0/0) [also the single (2,2) child of an ignored variant], 3 = (1/1)
+// For the read in active-list slot j of column p the parent holds (s1, s2) = its cost against h1 / h2 so far;
+// the four children only need A0 = s1+q0, A1 = s1+q1, B0 = s2+q0, B1 = s2+q1 where q0/q1 is the column's
+// quality if the read's allele mismatches 0/1.  Those four values per slot stay in registers ("cache"): when a
+// child of this expansion is popped next, its (s1, s2) vector is one shuffle away (slot -> slot of the previous
+// column through the column record's carry index).
+template <int K>
+struct ExpCache {
+    uint32_t a0[K > 0 ? K : 1], a1[K > 0 ? K : 1], b0[K > 0 ? K : 1], b1[K > 0 ? K : 1], w[K > 0 ? K : 1];
+    uint32_t first_idx;    // node index of the first child of the cached expansion (0xffffffff = empty)
+    uint32_t present;      // 4-bit mask of candidates that were created
 };
 
-// Scores one active read against both parent haplotypes and accumulates the child deltas.
-//   o      = read coordinate of haplotype position 0   (problem_offset - read.start, may be negative)
-//   L      = parent haplotype length (positions [0, L) are set)
-//   HapFn  = functor(which, bitpos) -> 64 haplotype bits starting at haplotype position bitpos (may be < 0)
-template <class HapFn>
-__device__ __forceinline__ void score_read(const AstarArgs& a, const BlkMeta& m, const ReadMeta rm, int o, int L,
-                                           uint32_t p, bool bad_col, HapFn hap, ChildAcc& acc, uint64_t& cells) {
-    // parent scores over read coordinates [max(0,o), o+L)
-    uint32_t s1 = 0, s2 = 0;
-    const int c_lo = max(0, o), c_hi = o + L;           // c_hi > c_lo whenever L > 0 and the read is active at p
-    if (c_hi > c_lo) {
-        const int k_lo = c_lo >> 6, k_hi = (c_hi - 1) >> 6;
-        const uint64_t* rec = a.planes + (uint64_t)rm.word_idx * HP_PLANE_STRIDE;
-        for (int k = k_lo; k <= k_hi; k++) {
-            const uint64_t* w = rec + (uint64_t)k * HP_PLANE_STRIDE;
-            const uint64_t range = bit_range(max(0, c_lo - 64 * k), min(64, c_hi - 64 * k));
-            const uint64_t ab = __ldg(w + 0), nb = __ldg(w + 1);
-            const int i0 = 64 * k - o;                    // haplotype position of this word's bit 0
-            const uint64_t m1 = range & ((hap(0, i0) ^ ab) | nb);
-            const uint64_t m2 = range & ((hap(1, i0) ^ ab) | nb);
-            for (uint32_t bpl = 0; bpl < m.n_planes; bpl++) {
-                const uint64_t q = __ldg(w + 2 + bpl);
-                s1 += (uint32_t)__popcll(m1 & q) << bpl;
-                s2 += (uint32_t)__popcll(m2 & q) << bpl;
-            }
+enum VecSrc { SRC_ROOT = 0, SRC_CACHE = 1, SRC_PLANES = 2 };
+
+template <int K, bool kCount, class HapFn>
+__device__ __forceinline__ void expand(const AstarArgs& a, const BlkMeta& m, uint32_t lane, const uint32_t* colp,
+                                       const uint32_t* aidxp, const ReadMeta* rmeta, uint32_t A, uint32_t p, int off,
+                                       int L, bool bad_col, bool ident, int src, uint32_t x1, uint32_t x2, HapFn hap,
+                                       ExpCache<K>& cache, uint32_t (&tot)[4], uint32_t (&fro)[4], uint64_t& cells) {
+    uint32_t at[4] = {0, 0, 0, 0}, af[4] = {0, 0, 0, 0};
+    if constexpr (K == 0) {
+        // generic path: any number of active reads, always from the bit planes
+        for (uint32_t j = lane; j < A; j += 32) {
+            const uint32_t c = __ldg(colp + j);
+            const ReadMeta rm = rmeta[__ldg(aidxp + j)];
+            uint32_t s1 = 0, s2 = 0;
+            if (src != SRC_ROOT) score_planes(a, m, rm, off - (int)rm.start, L, hap, s1, s2);
+            const uint32_t q = c & 0xffu, al = (c >> 8) & 3u;
+            const bool ends = (c >> 10) & 1u;
+            const uint32_t q0 = (!bad_col && al != 0u) ? q : 0u, q1 = (!bad_col && al != 1u) ? q : 0u;
+            const uint32_t A0 = s1 + q0, A1 = s1 + q1, B0 = s2 + q0, B1 = s2 + q1;
+            const uint32_t c01 = min(A0, B1), c10 = min(A1, B0), c00 = min(A0, B0), c11 = min(A1, B1);
+            at[0] += c01; at[1] += c10; at[2] += c00; at[3] += c11;
+            if (ends) { af[0] += c01; af[1] += c10; af[2] += c00; af[3] += c11; }
+            if (kCount) cells += (uint64_t)(p + 1 - (uint32_t)max((int)rm.start, off));
         }
-        s1 *= m.qgcd; s2 *= m.qgcd;
-    }
-    const bool ends = (rm.end <= p + 1);
-    if (bad_col) {
-        const uint32_t c = min(s1, s2);
-        acc.tb += c; if (ends) acc.fb += c;
     } else {
-        const uint32_t ci = rm.cell_rel + (p - rm.start);
-        const uint32_t al = __ldg(a.alleles + m.cell_base + ci);
-        const uint32_t q = __ldg(a.quals + m.cell_base + ci);
-        const uint32_t q0 = (al != 0u) ? q : 0u;         // cost of haplotype allele 0 at this column
-        const uint32_t q1 = (al != 1u) ? q : 0u;         // cost of haplotype allele 1
-        const uint32_t c01 = min(s1 + q0, s2 + q1);
-        const uint32_t c10 = min(s1 + q1, s2 + q0);
-        const uint32_t c00 = min(s1, s2) + q0;
-        const uint32_t c11 = min(s1, s2) + q1;
-        acc.t01 += c01; acc.t10 += c10; acc.t00 += c00; acc.t11 += c11;
-        if (ends) { acc.f01 += c01; acc.f10 += c10; acc.f00 += c00; acc.f11 += c11; }
+        const ExpCache<K> old = cache;      // the gathers read the previous expansion while this one is written
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t j = lane + 32u * k;
+            const bool valid = j < A;
+            const uint32_t c = valid ? __ldg(colp + j) : 0xffff0000u;
+            uint32_t s1 = 0, s2 = 0, wv = 0;
+            if (src == SRC_CACHE) {
+                const uint32_t carry = c >> 16;
+                const uint32_t sl = carry & 31u;
+                uint32_t v1 = __shfl_sync(HP_FULL_MASK, x1 ? old.a1[0] : old.a0[0], sl);
+                uint32_t v2 = __shfl_sync(HP_FULL_MASK, x2 ? old.b1[0] : old.b0[0], sl);
+                uint32_t vw = kCount ? __shfl_sync(HP_FULL_MASK, old.w[0], sl) : 0u;
+                if constexpr (K > 1) {
+#pragma unroll
+                    for (int kk = 1; kk < K; kk++) {
+                        const uint32_t u1 = __shfl_sync(HP_FULL_MASK, x1 ? old.a1[kk] : old.a0[kk], sl);
+                        const uint32_t u2 = __shfl_sync(HP_FULL_MASK, x2 ? old.b1[kk] : old.b0[kk], sl);
+                        const uint32_t uw = kCount ? __shfl_sync(HP_FULL_MASK, old.w[kk], sl) : 0u;
+                        if ((carry >> 5) == (uint32_t)kk) { v1 = u1; v2 = u2; vw = uw; }
+                    }
+                }
+                if (carry != 0xffffu) { s1 = v1; s2 = v2; wv = vw; }
+            } else if (src == SRC_PLANES) {
+                if (valid) {
+                    const ReadMeta rm = rmeta[__ldg(aidxp + j)];
+                    score_planes(a, m, rm, off - (int)rm.start, L, hap, s1, s2);
+                    wv = p - (uint32_t)max((int)rm.start, off);
+                }
+            }
+            const uint32_t q = c & 0xffu, al = (c >> 8) & 3u;
+            const bool ends = (c >> 10) & 1u;
+            const uint32_t q0 = (!bad_col && al != 0u) ? q : 0u, q1 = (!bad_col && al != 1u) ? q : 0u;
+            const uint32_t A0 = s1 + q0, A1 = s1 + q1, B0 = s2 + q0, B1 = s2 + q1;
+            const uint32_t c01 = min(A0, B1), c10 = min(A1, B0), c00 = min(A0, B0), c11 = min(A1, B1);
+            at[0] += c01; at[1] += c10; at[2] += c00; at[3] += c11;
+            if (ends) { af[0] += c01; af[1] += c10; af[2] += c00; af[3] += c11; }
+            cache.a0[k] = A0; cache.a1[k] = A1; cache.b0[k] = B0; cache.b1[k] = B1;
+            if (kCount) { cache.w[k] = wv + 1; if (valid) cells += wv + 1; }
+        }
     }
-    cells += (uint64_t)(p + 1 - (uint32_t)max((int)rm.start, (int)rm.start + o));   // w_r = p+1 - max(start, offset)
+    // only the candidates that will be created are reduced
+    tot[2] = wsum(at[2]); fro[2] = wsum(af[2]);
+    if (!bad_col) {
+        tot[0] = wsum(at[0]); fro[0] = wsum(af[0]);
+        tot[3] = wsum(at[3]); fro[3] = wsum(af[3]);
+        if (!ident) { tot[1] = wsum(at[1]); fro[1] = wsum(af[1]); }
+    }
 }
+
+// present-candidate mask of an expansion
+__device__ __forceinline__ uint32_t present_mask(bool bad_col, bool ident) { return bad_col ? 0x4u : (ident ? 0xdu : 0xfu); }
 
 // ---- sub-solver key: [total:32][63-hets:6][node_index:20][len:6] -------------------------------------------
 __device__ __forceinline__ uint64_t sub_key(uint32_t total, uint32_t hets, uint32_t idx, uint32_t len) {
@@ -246,122 +330,170 @@ struct WarpCtx {
 };
 
 // astar_subsolver (astar_phaser.rs:311-405).  Returns est in .x, solved depth in .y (both warp-uniform).
+//
+// "cur" is the node on top of the queue, held in registers.  After an expansion the best child becomes cur
+// directly when its key beats the queue minimum (the dive): it is never written to the queue, and its score
+// vector comes from the expansion cache.  Otherwise cur is pushed and a real pop (redux.sync select) happens.
+template <int K, bool kCount>
 __device__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uint32_t v, uint32_t clip, uint64_t badwin,
                            uint32_t blk) {
     const uint32_t lane = w.lane;
     const uint32_t* aoff = a.act_off + m.var_base + blk;
     const uint32_t* aidx = a.act_idx + m.cell_base;
+    const uint32_t* col = a.col + m.cell_base;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
     const uint32_t base = lane * w.capl;
 
-    // queue state: cached stripe minimum + stripe count, in registers
-    uint64_t ckey = ~0ull;
+    // queue state: cached stripe minimum + stripe count in registers; qmin = warp-uniform queue minimum
+    uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
-    if (lane == 0) {                                                     // root: AstarNode::new(H[v+1]), :325
-        w.sq_key[base] = sub_key(w.hring[(v + 1) & 63], 0, 0, 0);
-        w.sq_h1[base] = 0; w.sq_h2[base] = 0; w.sq_frozen[base] = 0;
-        ckey = w.sq_key[base]; cnt = 1;
-    }
-    __syncwarp();
-    uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 1;
+    // root: AstarNode::new(H[v+1]) (:325), kept in registers as the current top
+    uint64_t cur_key = sub_key(w.hring[(v + 1) & 63], 0, 0, 0), cur_h1 = 0, cur_h2 = 0;
+    uint32_t cur_frozen = 0;
+    bool have_cur = true;
+    ExpCache<K> cache;
+    cache.first_idx = 0xffffffffu; cache.present = 0;
+    uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 0;
     const uint32_t max_visits = a.min_queue_size / 10 + a.queue_increment * clip;    // :266, :333
 
     for (;;) {
-        // ---- peek: warp-wide minimum of the cached stripe minima ----
-        const uint32_t khi = (uint32_t)(ckey >> 32), klo = (uint32_t)ckey;
-        const uint32_t mhi = wmin(khi);
-        const uint32_t mlo = wmin(khi == mhi ? klo : 0xffffffffu);
-        const uint32_t L = mlo & 63u;
+        if (!have_cur || qmin < cur_key) {
+            if (have_cur) {                                              // the dive broke: cur goes back to the queue
+                const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
+                if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
+                uint32_t target = rr & 31u; rr++;
+                if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                if (lane == target) {
+                    w.sq_key[base + cnt] = cur_key; w.sq_h1[base + cnt] = cur_h1; w.sq_h2[base + cnt] = cur_h2;
+                    w.sq_frozen[base + cnt] = cur_frozen;
+                    if (cur_key < ckey) { ckey = cur_key; cpos = cnt; }
+                    cnt++;
+                }
+                __syncwarp();
+            }
+            // ---- real pop: the entry whose key is qmin ----
+            if (qmin == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }
+            const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
+            const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
+            const uint32_t slot = owner * w.capl + pos;
+            cur_key = qmin; cur_h1 = w.sq_h1[slot]; cur_h2 = w.sq_h2[slot]; cur_frozen = w.sq_frozen[slot];
+            __syncwarp();
+            if ((int)lane == owner) {                                    // remove + rescan own stripe
+                cnt--;
+                if (pos != cnt) {
+                    w.sq_key[slot] = w.sq_key[base + cnt]; w.sq_h1[slot] = w.sq_h1[base + cnt];
+                    w.sq_h2[slot] = w.sq_h2[base + cnt]; w.sq_frozen[slot] = w.sq_frozen[base + cnt];
+                }
+                ckey = ~0ull; cpos = 0;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint64_t k = w.sq_key[base + i];
+                    if (k < ckey) { ckey = k; cpos = i; }
+                }
+            }
+            qmin = wmin64(ckey);
+            have_cur = true;
+        }
+        // ---- cur is the top of the queue (peek) ----
+        const uint32_t L = (uint32_t)cur_key & 63u;
+        const uint32_t total = (uint32_t)(cur_key >> 32);
         if (L >= clip) {                                                 // :395-399 (peek, not pop)
-            max_cost = max(max_cost, mhi);
+            max_cost = max(max_cost, total);
             next_expected++;
             break;
         }
         if (visits >= max_visits) break;
-        const int owner = __ffs(__ballot_sync(HP_FULL_MASK, khi == mhi && klo == mlo)) - 1;
-        const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
-        const uint32_t slot = owner * w.capl + pos;
-        const uint64_t ph1 = w.sq_h1[slot], ph2 = w.sq_h2[slot];
-        const uint32_t pfrozen = w.sq_frozen[slot];
-        const uint32_t phets = 63u - ((mlo >> 26) & 63u);
-        __syncwarp();
-        if ((int)lane == owner) {                                        // remove + rescan own stripe
-            cnt--;
-            if (pos != cnt) {
-                w.sq_key[slot] = w.sq_key[base + cnt]; w.sq_h1[slot] = w.sq_h1[base + cnt];
-                w.sq_h2[slot] = w.sq_h2[base + cnt]; w.sq_frozen[slot] = w.sq_frozen[base + cnt];
-            }
-            ckey = ~0ull; cpos = 0;
-            for (uint32_t i = 0; i < cnt; i++) {
-                const uint64_t k = w.sq_key[base + i];
-                if (k < ckey) { ckey = k; cpos = i; }
-            }
-        }
         visits++;
         w.pops++;
-        if (L == next_expected) { max_cost = max(max_cost, mhi); next_expected++; }   // :342-346
+        if (L == next_expected) { max_cost = max(max_cost, total); next_expected++; }   // :342-346
 
-        // ---- expand: score the active reads of column p against both parent haplotypes ----
+        // ---- expand ----
         const uint32_t p = v + L;
         const bool bad_col = (badwin >> L) & 1ull;
         const uint32_t heur = w.hring[(p + 1) & 63];
-        const uint32_t a0 = __ldg(aoff + p), a1 = __ldg(aoff + p + 1);
-        ChildAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t o0 = __ldg(aoff + p), o1 = __ldg(aoff + p + 1);
+        const uint32_t idx = ((uint32_t)cur_key >> 6) & 0xfffffu;
+        const uint32_t hets = 63u - (((uint32_t)cur_key >> 26) & 63u);
+        const bool ident = (cur_h1 == cur_h2);
+        int src = SRC_PLANES;
+        uint32_t x1 = 0, x2 = 0;
+        if (L == 0) src = SRC_ROOT;
+        else if (K > 0 && idx - cache.first_idx < (uint32_t)__popc(cache.present)) {
+            src = SRC_CACHE;
+            const uint32_t cslot = __fns(cache.present, 0, (int)(idx - cache.first_idx) + 1);
+            x1 = (cslot == 1u || cslot == 3u); x2 = (cslot == 0u || cslot == 3u);
+        }
+        auto hap = [&](int which, int i0) { return shift_signed(which ? cur_h2 : cur_h1, i0); };
+        uint32_t tot[4], fro[4];
         uint64_t cells = 0;
-        auto hap = [&](int which, int i0) { return shift_signed(which ? ph2 : ph1, i0); };
-        for (uint32_t j = a0 + lane; j < a1; j += 32) {
-            const ReadMeta rm = rmeta[__ldg(aidx + j)];
-            score_read(a, m, rm, (int)v - (int)rm.start, (int)L, p, bad_col, hap, acc, cells);
-        }
-        const bool ident = (ph1 == ph2);
-        uint32_t nchild;
-        uint32_t ctot[4], cfro[4], chet[4];
-        uint64_t ch1[4], ch2[4];
-        const uint64_t bit = 1ull << L;
-        if (bad_col) {
-            nchild = 1;
-            ctot[0] = pfrozen + wsum(acc.tb) + heur; cfro[0] = pfrozen + wsum(acc.fb);
-            chet[0] = phets; ch1[0] = ph1; ch2[0] = ph2;
-            if (ctot[0] != mhi) w.status = HP_BLOCK_ASSERT;               // :360
-        } else {
-            const uint32_t t01 = wsum(acc.t01), t00 = wsum(acc.t00), t11 = wsum(acc.t11);
-            const uint32_t f01 = wsum(acc.f01), f00 = wsum(acc.f00), f11 = wsum(acc.f11);
-            nchild = 0;
-            ctot[nchild] = pfrozen + t01 + heur; cfro[nchild] = pfrozen + f01; chet[nchild] = phets + 1;
-            ch1[nchild] = ph1; ch2[nchild] = ph2 | bit; nchild++;
-            if (!ident) {                                                // :376 symmetry break
-                const uint32_t t10 = wsum(acc.t10), f10 = wsum(acc.f10);
-                ctot[nchild] = pfrozen + t10 + heur; cfro[nchild] = pfrozen + f10; chet[nchild] = phets + 1;
-                ch1[nchild] = ph1 | bit; ch2[nchild] = ph2; nchild++;
-            }
-            ctot[nchild] = pfrozen + t00 + heur; cfro[nchild] = pfrozen + f00; chet[nchild] = phets;
-            ch1[nchild] = ph1; ch2[nchild] = ph2; nchild++;
-            ctot[nchild] = pfrozen + t11 + heur; cfro[nchild] = pfrozen + f11; chet[nchild] = phets;
-            ch1[nchild] = ph1 | bit; ch2[nchild] = ph2 | bit; nchild++;
-        }
-        w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild;
+        expand<K, kCount>(a, m, lane, col + o0, aidx + o0, rmeta, o1 - o0, p, (int)v, (int)L, bad_col, ident, src, x1, x2,
+                          hap, cache, tot, fro, cells);
+        const uint32_t present = present_mask(bad_col, ident);
+        const uint32_t nchild = __popc(present);
+        cache.first_idx = next_idx; cache.present = present;
+        if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
 
-        // ---- push children, round-robin over the stripes ----
-        const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, cnt >= w.capl);
+        // keys of the candidates, in creation order
+        const uint64_t bit = bad_col ? 0ull : (1ull << L);
+        uint64_t key[4];
+        uint32_t best = 2;
 #pragma unroll
         for (uint32_t c = 0; c < 4; c++) {
-            if (c < nchild) {
-                uint32_t target = (rr + c) & 31u;
-                if (fullmask) {                                          // rare: pick any stripe with room
-                    const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
-                    if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
-                    if (!((room >> target) & 1u)) target = __ffs(room) - 1;
-                }
-                if (lane == target) {
-                    const uint64_t key = sub_key(ctot[c], chet[c], next_idx + c, L + 1);
-                    w.sq_key[base + cnt] = key; w.sq_h1[base + cnt] = ch1[c]; w.sq_h2[base + cnt] = ch2[c];
-                    w.sq_frozen[base + cnt] = cfro[c];
-                    if (key < ckey) { ckey = key; cpos = cnt; }
+            const uint32_t ord = __popc(present & ((1u << c) - 1u));
+            const uint32_t ch = hets + ((c < 2 && !bad_col) ? 1u : 0u);
+            key[c] = ((present >> c) & 1u) ? sub_key(cur_frozen + tot[c] + heur, ch, next_idx + ord, L + 1) : ~0ull;
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) if (key[c] < key[best]) best = c;
+        if (bad_col && cur_frozen + tot[2] + heur != total) { w.status = HP_BLOCK_ASSERT; break; }   // :360
+
+        // ---- push the siblings of the best child (one lane each, round-robin over the stripes) ----
+        {
+            const uint32_t c = (lane - rr) & 31u;
+            const bool mine = c < 4u && ((present >> c) & 1u) && c != best;
+            const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl);
+            if (fullmask == 0) {
+                if (mine) {
+                    const uint64_t k = (c == 0) ? key[0] : (c == 1) ? key[1] : (c == 2) ? key[2] : key[3];
+                    const uint32_t fr = cur_frozen + ((c == 0) ? fro[0] : (c == 1) ? fro[1] : (c == 2) ? fro[2] : fro[3]);
+                    w.sq_key[base + cnt] = k;
+                    w.sq_h1[base + cnt] = cur_h1 | ((c == 1u || c == 3u) ? bit : 0ull);
+                    w.sq_h2[base + cnt] = cur_h2 | ((c == 0u || c == 3u) ? bit : 0ull);
+                    w.sq_frozen[base + cnt] = fr;
+                    if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
+            } else {                                                     // rare: a target stripe is full
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if (((present >> cc) & 1u) && cc != best) {
+                        const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
+                        if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
+                        uint32_t target = (rr + cc) & 31u;
+                        if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                        if (lane == target) {
+                            w.sq_key[base + cnt] = key[cc];
+                            w.sq_h1[base + cnt] = cur_h1 | ((cc == 1u || cc == 3u) ? bit : 0ull);
+                            w.sq_h2[base + cnt] = cur_h2 | ((cc == 0u || cc == 3u) ? bit : 0ull);
+                            w.sq_frozen[base + cnt] = cur_frozen + fro[cc];
+                            if (key[cc] < ckey) { ckey = key[cc]; cpos = cnt; }
+                            cnt++;
+                        }
+                    }
+                }
             }
+            rr += 4;
+#pragma unroll
+            for (uint32_t cc = 0; cc < 4; cc++) if (cc != best && key[cc] < qmin) qmin = key[cc];
         }
-        rr += nchild; next_idx += nchild;
+        next_idx += nchild;
+        // ---- the best child is the new cur ----
+        {
+            const uint32_t bf = (best == 0) ? fro[0] : (best == 1) ? fro[1] : (best == 2) ? fro[2] : fro[3];
+            cur_key = key[best];
+            cur_h1 |= (best == 1u || best == 3u) ? bit : 0ull;
+            cur_h2 |= (best == 0u || best == 3u) ? bit : 0ull;
+            cur_frozen += bf;
+        }
         __syncwarp();
         if (w.status != HP_BLOCK_OK) break;
     }
@@ -372,7 +504,7 @@ __device__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uin
 struct Slab {
     uint64_t* khi;       // [qcap] total << 32 | (0xffffffff - hets)
     uint32_t* kidx;      // [qcap] node index
-    uint32_t* klen;      // [qcap]
+    uint32_t* klen;      // [qcap] length | identical-haplotypes flag << 31
     uint32_t* kfrozen;   // [qcap]
     uint32_t* krec;      // [qcap] record slot
     uint32_t* freelist;  // [qcap]
@@ -401,40 +533,44 @@ __device__ __forceinline__ Slab carve_slab(uint8_t* p, uint32_t qcap, uint32_t h
     return s;
 }
 
-// Main-queue cached minimum of one stripe (registers of the owning lane).
-struct MainMin {
-    uint64_t hi;     // ~0 when the stripe is empty
+// 96-bit main-queue key: hi = total << 32 | (0xffffffff - hets), then the node index.
+struct MainKey {
+    uint64_t hi;
     uint32_t idx;
-    uint32_t pos;
 };
-
 __device__ __forceinline__ bool key_less(uint64_t hi_a, uint32_t idx_a, uint64_t hi_b, uint32_t idx_b) {
     return hi_a < hi_b || (hi_a == hi_b && idx_a < idx_b);
 }
-
-// warp-cooperative scan of stripe `owner` (cnt_o entries) -> its minimum; result valid on every lane
-__device__ __forceinline__ MainMin stripe_min(const Slab& s, uint32_t scap, int owner, uint32_t cnt_o, uint32_t lane) {
-    MainMin best = {~0ull, 0xffffffffu, 0};
-    const uint32_t b0 = owner * scap;
-    for (uint32_t i = lane; i < cnt_o; i += 32) {
-        const uint64_t hi = __ldcg(s.khi + b0 + i);
-        const uint32_t idx = __ldcg(s.kidx + b0 + i);
-        if (key_less(hi, idx, best.hi, best.idx)) { best.hi = hi; best.idx = idx; best.pos = i; }
-    }
-    const uint32_t t = (uint32_t)(best.hi >> 32), h = (uint32_t)best.hi;
+__device__ __forceinline__ MainKey wmin96(uint64_t hi, uint32_t idx) {
+    const uint32_t t = (uint32_t)(hi >> 32), h = (uint32_t)hi;
     const uint32_t mt = wmin(t);
     const uint32_t mh = wmin(t == mt ? h : 0xffffffffu);
-    const uint32_t mi = wmin((t == mt && h == mh) ? best.idx : 0xffffffffu);
-    const uint32_t win = __ballot_sync(HP_FULL_MASK, t == mt && h == mh && best.idx == mi);
-    const int wl = __ffs(win) - 1;
-    MainMin r;
-    r.hi = ((uint64_t)mt << 32) | mh;
-    r.idx = mi;
-    r.pos = __shfl_sync(HP_FULL_MASK, best.pos, wl);
+    const uint32_t mi = wmin((t == mt && h == mh) ? idx : 0xffffffffu);
+    MainKey r; r.hi = ((uint64_t)mt << 32) | mh; r.idx = mi;
     return r;
 }
 
+// warp-cooperative scan of stripe `owner` (cnt_o entries) -> its minimum and position; valid on every lane
+__device__ __forceinline__ void stripe_min(const Slab& s, uint32_t scap, int owner, uint32_t cnt_o, uint32_t lane,
+                                           uint64_t& out_hi, uint32_t& out_idx, uint32_t& out_pos) {
+    uint64_t bhi = ~0ull; uint32_t bidx = 0xffffffffu, bpos = 0;
+    const uint32_t b0 = owner * scap;
+    for (uint32_t i = lane; i < cnt_o; i += 32) {
+        const uint64_t hi = s.khi[b0 + i];
+        const uint32_t idx = s.kidx[b0 + i];
+        if (key_less(hi, idx, bhi, bidx)) { bhi = hi; bidx = idx; bpos = i; }
+    }
+    const MainKey mk = wmin96(bhi, bidx);
+    const int wl = __ffs(__ballot_sync(HP_FULL_MASK, bhi == mk.hi && bidx == mk.idx)) - 1;
+    out_hi = mk.hi; out_idx = mk.idx;
+    out_pos = __shfl_sync(HP_FULL_MASK, bpos, wl);
+}
+
 // astar_solver main loop (astar_phaser.rs:480-633) for one block, after the heuristic pre-pass.
+// Same structure as sub_solve: cur in registers, dive when the best child beats the queue minimum.  Nodes carry
+// full-length haplotype records in the slab (the reference clones h1/h2 per node, :79-82); the best child
+// inherits its parent's record in place.
+template <int K, bool kCount>
 __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, const Slab& s, uint32_t blk,
                            const uint32_t* Hg) {
     const uint32_t lane = w.lane;
@@ -443,68 +579,83 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     const uint32_t scap = a.qcap / 32;
     const uint32_t* aoff = a.act_off + m.var_base + blk;
     const uint32_t* aidx = a.act_idx + m.cell_base;
+    const uint32_t* col = a.col + m.cell_base;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
     const uint8_t* ign = a.ignored + m.var_base;
 
-    // tracker (PQueueHapTracker, :171-231)
-    for (uint32_t i = lane; i <= N; i += 32) __stcg(s.lencnt + i, 0u);
-    uint32_t trk_total = 0, trk_thresh = 0;
+    // tracker (PQueueHapTracker, :171-231): counts in the slab, totals in registers
+    for (uint32_t i = lane; i <= N; i += 32) s.lencnt[i] = 0u;
+    __syncwarp();
+    uint32_t trk_total = 1, trk_thresh = 0;                              // root counted (:488)
     uint32_t curr_thresh = a.min_queue_size;
     const uint32_t max_queue = 10u * a.min_queue_size;                   // :457
     uint32_t min_progress = 0, next_expected = 0;
     uint64_t num_pruned = 0;
-    uint32_t next_idx = 1, rr = 1, qsize = 0;
-    uint32_t free_top = 0, rec_next = 0;
+    uint32_t next_idx = 1, rr = 0, qsize = 1;                            // qsize = pqueue.len() (cur included)
+    uint32_t free_top = 0, rec_next = 1;                                 // record 0 = root
+    if (lane == 0) atomicAdd(s.lencnt + 0, 1u);
 
-    MainMin cm = {~0ull, 0xffffffffu, 0};
-    uint32_t cnt = 0;
-    // root node (:485-488): record 0, empty haplotypes
-    if (lane == 0) {
-        const uint32_t h0 = __ldcg(Hg + 0);
-        __stcg(s.khi + 0, ((uint64_t)h0 << 32) | 0xffffffffull);
-        __stcg(s.kidx + 0, 0u); __stcg(s.klen + 0, 0u); __stcg(s.kfrozen + 0, 0u); __stcg(s.krec + 0, 0u);
-        __stcg(s.lencnt + 0, 1u);
-        cm.hi = ((uint64_t)h0 << 32) | 0xffffffffull; cm.idx = 0; cm.pos = 0; cnt = 1;
-    }
-    rec_next = 1; qsize = 1; trk_total = 1;
-    __syncwarp();
+    // per-lane cached stripe minimum + warp-uniform queue minimum
+    uint64_t c_hi = ~0ull; uint32_t c_idx = 0xffffffffu, c_pos = 0, cnt = 0;
+    MainKey qmin; qmin.hi = ~0ull; qmin.idx = 0xffffffffu;
+    // current top (root, :485-487)
+    uint64_t cur_hi = ((uint64_t)Hg[0] << 32) | 0xffffffffull;
+    uint32_t cur_idx = 0, cur_len = 0, cur_frozen = 0, cur_rec = 0;
+    bool cur_ident = true, have_cur = true;
+    ExpCache<K> cache;
+    cache.first_idx = 0xffffffffu; cache.present = 0;
 
-    uint32_t top_slot = 0, top_total = 0;
     for (;;) {
-        // ---- peek ----
-        const uint32_t t = (uint32_t)(cm.hi >> 32), h = (uint32_t)cm.hi;
-        const uint32_t mt = wmin(t);
-        const uint32_t mh = wmin(t == mt ? h : 0xffffffffu);
-        const uint32_t mi = wmin((t == mt && h == mh) ? cm.idx : 0xffffffffu);
-        const int owner = __ffs(__ballot_sync(HP_FULL_MASK, t == mt && h == mh && cm.idx == mi)) - 1;
-        const uint32_t pos = __shfl_sync(HP_FULL_MASK, cm.pos, owner);
-        const uint32_t slot = owner * scap + pos;
-        const uint32_t L = __ldcg(s.klen + slot);
-        top_slot = slot; top_total = mt;
-        if (L >= N) break;                                                // :492
-        const uint32_t pfrozen = __ldcg(s.kfrozen + slot);
-        const uint32_t prec = __ldcg(s.krec + slot);
-        const uint32_t phets = 0xffffffffu - mh;
-        __syncwarp();
-        // ---- pop: owner moves its last entry into the hole, then the warp rescans that stripe ----
-        const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
-        if ((int)lane == owner) {
-            cnt--;
-            if (pos != cnt) {
-                const uint32_t last = owner * scap + cnt;
-                __stcg(s.khi + slot, __ldcg(s.khi + last)); __stcg(s.kidx + slot, __ldcg(s.kidx + last));
-                __stcg(s.klen + slot, __ldcg(s.klen + last)); __stcg(s.kfrozen + slot, __ldcg(s.kfrozen + last));
-                __stcg(s.krec + slot, __ldcg(s.krec + last));
+        if (!have_cur || key_less(qmin.hi, qmin.idx, cur_hi, cur_idx)) {
+            if (have_cur) {                                              // cur goes back to the queue
+                const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
+                if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+                uint32_t target = rr & 31u; rr++;
+                if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                if (lane == target) {
+                    const uint32_t e = lane * scap + cnt;
+                    s.khi[e] = cur_hi; s.kidx[e] = cur_idx; s.klen[e] = cur_len | (cur_ident ? 0x80000000u : 0u);
+                    s.kfrozen[e] = cur_frozen; s.krec[e] = cur_rec;
+                    if (key_less(cur_hi, cur_idx, c_hi, c_idx)) { c_hi = cur_hi; c_idx = cur_idx; c_pos = cnt; }
+                    cnt++;
+                }
+                __syncwarp();
             }
+            // ---- real pop ----
+            if (qmin.hi == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }   // empty queue: the reference panics (:631)
+            const int owner = __ffs(__ballot_sync(HP_FULL_MASK, c_hi == qmin.hi && c_idx == qmin.idx)) - 1;
+            const uint32_t pos = __shfl_sync(HP_FULL_MASK, c_pos, owner);
+            const uint32_t slot = owner * scap + pos;
+            cur_hi = qmin.hi; cur_idx = qmin.idx;
+            const uint32_t lenf = s.klen[slot];
+            cur_len = lenf & 0x7fffffffu; cur_ident = (lenf >> 31) != 0;
+            cur_frozen = s.kfrozen[slot]; cur_rec = s.krec[slot];
+            const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
+            __syncwarp();
+            if ((int)lane == owner) {
+                cnt--;
+                if (pos != cnt) {
+                    const uint32_t last = owner * scap + cnt;
+                    s.khi[slot] = s.khi[last]; s.kidx[slot] = s.kidx[last]; s.klen[slot] = s.klen[last];
+                    s.kfrozen[slot] = s.kfrozen[last]; s.krec[slot] = s.krec[last];
+                }
+            }
+            __syncwarp();
+            {
+                uint64_t nhi; uint32_t nidx, npos;
+                stripe_min(s, scap, owner, cnt_o, lane, nhi, nidx, npos);
+                if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
+            }
+            qmin = wmin96(c_hi, c_idx);
+            have_cur = true;
         }
-        __syncwarp();
-        {
-            const MainMin nm = stripe_min(s, scap, owner, cnt_o, lane);
-            if ((int)lane == owner) cm = nm;
-        }
+        // ---- cur is the top ----
+        const uint32_t L = cur_len;
+        const uint32_t total = (uint32_t)(cur_hi >> 32);
+        if (L >= N) break;                                                // :492
+        // pop bookkeeping: hap_tracker.remove_hap (:495)
         qsize--;
-        // hap_tracker.remove_hap (:495)
-        if (lane == 0) __stcg(s.lencnt + L, __ldcg(s.lencnt + L) - 1u);
+        if (lane == 0) atomicAdd(s.lencnt + L, 0xffffffffu);
         if (L >= trk_thresh) trk_total--;
         w.pops++;
         if (L == next_expected) {                                         // :497-504
@@ -514,8 +665,9 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         if (L < min_progress) {                                           // :507-515
             if (num_pruned == 0) curr_thresh = a.min_queue_size;
             num_pruned++;
-            if (lane == 0) __stcg(s.freelist + free_top, prec);
+            if (lane == 0) s.freelist[free_top] = cur_rec;
             free_top++;
+            have_cur = false;
             __syncwarp();
             continue;
         }
@@ -523,145 +675,171 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         // ---- expand ----
         const uint32_t p = L;
         const bool bad_col = __ldg(ign + p) != 0;
-        const uint32_t heur = __ldcg(Hg + p + 1);
-        const uint64_t* prow = s.recs + (uint64_t)prec * 2 * HW;
-        const uint32_t a0 = __ldg(aoff + p), a1 = __ldg(aoff + p + 1);
-        ChildAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        uint64_t cells = 0;
+        const uint32_t heur = Hg[p + 1];
+        const uint32_t hets = 0xffffffffu - (uint32_t)cur_hi;
+        const uint64_t* prow = s.recs + (uint64_t)cur_rec * 2 * HW;
+        const uint32_t o0 = __ldg(aoff + p), o1 = __ldg(aoff + p + 1);
         const int nwords = (int)((L + 63) >> 6);                          // words of the parent that hold set bits
+        int src = SRC_PLANES;
+        uint32_t x1 = 0, x2 = 0;
+        if (L == 0) src = SRC_ROOT;
+        else if (K > 0 && cur_idx - cache.first_idx < (uint32_t)__popc(cache.present)) {
+            src = SRC_CACHE;
+            const uint32_t cslot = __fns(cache.present, 0, (int)(cur_idx - cache.first_idx) + 1);
+            x1 = (cslot == 1u || cslot == 3u); x2 = (cslot == 0u || cslot == 3u);
+        }
         auto hap = [&](int which, int i0) -> uint64_t {                   // 64 bits from haplotype position i0 >= 0
             const uint64_t* hw = prow + (which ? HW : 0);
             const int wi = i0 >> 6, sh = i0 & 63;
-            uint64_t x = (wi < nwords) ? (__ldcg(hw + wi) >> sh) : 0ull;
-            if (sh && wi + 1 < nwords) x |= __ldcg(hw + wi + 1) << (64 - sh);
+            uint64_t x = (wi < nwords) ? (hw[wi] >> sh) : 0ull;
+            if (sh && wi + 1 < nwords) x |= hw[wi + 1] << (64 - sh);
             return x;
         };
-        for (uint32_t j = a0 + lane; j < a1; j += 32) {
-            const ReadMeta rm = rmeta[__ldg(aidx + j)];
-            score_read(a, m, rm, -(int)rm.start, (int)L, p, bad_col, hap, acc, cells);
-        }
-        // parent words: identical test (:163) and the source of the child copies
-        bool differ = false;
-        for (int wi = lane; wi < nwords; wi += 32) differ |= (__ldcg(prow + wi) != __ldcg(prow + HW + wi));
-        const bool ident = !__any_sync(HP_FULL_MASK, differ);
+        uint32_t tot[4], fro[4];
+        uint64_t cells = 0;
+        expand<K, kCount>(a, m, lane, col + o0, aidx + o0, rmeta, o1 - o0, p, 0, (int)L, bad_col, cur_ident, src, x1, x2,
+                          hap, cache, tot, fro, cells);
+        const uint32_t present = present_mask(bad_col, cur_ident);
+        const uint32_t nchild = __popc(present);
+        cache.first_idx = next_idx; cache.present = present;
+        if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
+        if (bad_col && cur_frozen + tot[2] + heur != total) { w.status = HP_BLOCK_ASSERT; break; }   // :529
+        if (qsize + nchild + 64 > a.qcap || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
 
-        uint32_t nchild;
-        uint32_t ctot[4], cfro[4], chet[4];
-        uint32_t ca1[4], ca2[4];
-        if (bad_col) {
-            nchild = 1;
-            ctot[0] = pfrozen + wsum(acc.tb) + heur; cfro[0] = pfrozen + wsum(acc.fb); chet[0] = phets;
-            ca1[0] = 0; ca2[0] = 0;
-            if (ctot[0] != mt) w.status = HP_BLOCK_ASSERT;                // :529
-        } else {
-            const uint32_t t01 = wsum(acc.t01), t00 = wsum(acc.t00), t11 = wsum(acc.t11);
-            const uint32_t f01 = wsum(acc.f01), f00 = wsum(acc.f00), f11 = wsum(acc.f11);
-            nchild = 0;
-            ctot[nchild] = pfrozen + t01 + heur; cfro[nchild] = pfrozen + f01; chet[nchild] = phets + 1;
-            ca1[nchild] = 0; ca2[nchild] = 1; nchild++;
-            if (!ident) {
-                const uint32_t t10 = wsum(acc.t10), f10 = wsum(acc.f10);
-                ctot[nchild] = pfrozen + t10 + heur; cfro[nchild] = pfrozen + f10; chet[nchild] = phets + 1;
-                ca1[nchild] = 1; ca2[nchild] = 0; nchild++;
-            }
-            ctot[nchild] = pfrozen + t00 + heur; cfro[nchild] = pfrozen + f00; chet[nchild] = phets;
-            ca1[nchild] = 0; ca2[nchild] = 0; nchild++;
-            ctot[nchild] = pfrozen + t11 + heur; cfro[nchild] = pfrozen + f11; chet[nchild] = phets;
-            ca1[nchild] = 1; ca2[nchild] = 1; nchild++;
+        // keys, creation order
+        uint64_t khi[4]; uint32_t kix[4];
+        uint32_t best = 2;
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) {
+            const uint32_t ord = __popc(present & ((1u << c) - 1u));
+            const uint32_t ch = hets + ((c < 2 && !bad_col) ? 1u : 0u);
+            const bool pr = (present >> c) & 1u;
+            khi[c] = pr ? (((uint64_t)(cur_frozen + tot[c] + heur) << 32) | (uint64_t)(0xffffffffu - ch)) : ~0ull;
+            kix[c] = pr ? next_idx + ord : 0xffffffffu;
         }
-        w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild;
-        if (qsize + nchild > a.qcap - 32 || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) if (key_less(khi[c], kix[c], khi[best], kix[best])) best = c;
 
-        // ---- allocate child records: recycled slots first, then fresh ones ----
+        // ---- records: siblings get copies of the parent's words + their allele bit; the best child then takes the
+        //      parent's record in place ----
         uint32_t crec[4];
         {
+            const uint32_t nsib = nchild - 1;
             uint32_t mine = 0;
-            if (lane < nchild) mine = (lane < free_top) ? __ldcg(s.freelist + free_top - 1 - lane) : rec_next + (lane - free_top);
+            if (lane < nsib) mine = (lane < free_top) ? s.freelist[free_top - 1 - lane] : rec_next + (lane - min(free_top, nsib));
+            uint32_t ordinal = 0;
 #pragma unroll
-            for (uint32_t c = 0; c < 4; c++) crec[c] = __shfl_sync(HP_FULL_MASK, mine, c);
-            const uint32_t from_free = min(nchild, free_top);
-            free_top -= from_free; rec_next += nchild - from_free;
+            for (uint32_t c = 0; c < 4; c++) {
+                const bool sib = ((present >> c) & 1u) && c != best;
+                crec[c] = sib ? __shfl_sync(HP_FULL_MASK, mine, ordinal & 31u) : cur_rec;
+                if (sib) ordinal++;
+            }
+            const uint32_t from_free = min(nsib, free_top);
+            free_top -= from_free; rec_next += nsib - from_free;
         }
-        // ---- write child haplotype records: parent words + the new allele bit ----
         {
             const int wl = (int)(L >> 6);
-            const uint64_t bit = 1ull << (L & 63);
+            const uint64_t bit = bad_col ? 0ull : (1ull << (L & 63));
             for (int wi = lane; wi <= wl; wi += 32) {
                 uint64_t w1 = 0, w2 = 0;
-                if (wi < nwords) { w1 = __ldcg(prow + wi); w2 = __ldcg(prow + HW + wi); }
+                if (wi < nwords) { w1 = prow[wi]; w2 = prow[HW + wi]; }
 #pragma unroll
                 for (uint32_t c = 0; c < 4; c++) {
-                    if (c < nchild) {
+                    if (((present >> c) & 1u) && (c != best || wi == wl)) {   // best: only the word that changes
                         uint64_t* crow = s.recs + (uint64_t)crec[c] * 2 * HW;
-                        __stcg(crow + wi, (wi == wl && ca1[c]) ? (w1 | bit) : w1);
-                        __stcg(crow + HW + wi, (wi == wl && ca2[c]) ? (w2 | bit) : w2);
+                        crow[wi] = (wi == wl && (c == 1u || c == 3u)) ? (w1 | bit) : w1;
+                        crow[HW + wi] = (wi == wl && (c == 0u || c == 3u)) ? (w2 | bit) : w2;
                     }
                 }
             }
         }
-        // ---- push the queue entries ----
-        const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, cnt >= scap);
-#pragma unroll
-        for (uint32_t c = 0; c < 4; c++) {
-            if (c < nchild) {
-                uint32_t target = (rr + c) & 31u;
-                if (fullmask) {
-                    const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
-                    if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
-                    if (!((room >> target) & 1u)) target = __ffs(room) - 1;
-                }
-                if (lane == target) {
+        // ---- push the siblings ----
+        {
+            const uint32_t c = (lane - rr) & 31u;
+            const bool mine = c < 4u && ((present >> c) & 1u) && c != best;
+            const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= scap);
+            const uint32_t cident = (cur_ident && c >= 2u) ? 0x80000000u : 0u;
+            if (fullmask == 0) {
+                if (mine) {
+                    const uint64_t hi = (c == 0) ? khi[0] : (c == 1) ? khi[1] : (c == 2) ? khi[2] : khi[3];
+                    const uint32_t ix = (c == 0) ? kix[0] : (c == 1) ? kix[1] : (c == 2) ? kix[2] : kix[3];
+                    const uint32_t fr = cur_frozen + ((c == 0) ? fro[0] : (c == 1) ? fro[1] : (c == 2) ? fro[2] : fro[3]);
+                    const uint32_t rc = (c == 0) ? crec[0] : (c == 1) ? crec[1] : (c == 2) ? crec[2] : crec[3];
                     const uint32_t e = lane * scap + cnt;
-                    const uint64_t hi = ((uint64_t)ctot[c] << 32) | (uint64_t)(0xffffffffu - chet[c]);
-                    __stcg(s.khi + e, hi); __stcg(s.kidx + e, next_idx + c); __stcg(s.klen + e, L + 1);
-                    __stcg(s.kfrozen + e, cfro[c]); __stcg(s.krec + e, crec[c]);
-                    if (key_less(hi, next_idx + c, cm.hi, cm.idx)) { cm.hi = hi; cm.idx = next_idx + c; cm.pos = cnt; }
+                    s.khi[e] = hi; s.kidx[e] = ix; s.klen[e] = (L + 1) | cident; s.kfrozen[e] = fr; s.krec[e] = rc;
+                    if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = cnt; }
                     cnt++;
                 }
+            } else {
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if (((present >> cc) & 1u) && cc != best) {
+                        const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
+                        if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+                        uint32_t target = (rr + cc) & 31u;
+                        if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                        if (lane == target) {
+                            const uint32_t e = lane * scap + cnt;
+                            s.khi[e] = khi[cc]; s.kidx[e] = kix[cc];
+                            s.klen[e] = (L + 1) | ((cur_ident && cc >= 2u) ? 0x80000000u : 0u);
+                            s.kfrozen[e] = cur_frozen + fro[cc]; s.krec[e] = crec[cc];
+                            if (key_less(khi[cc], kix[cc], c_hi, c_idx)) { c_hi = khi[cc]; c_idx = kix[cc]; c_pos = cnt; }
+                            cnt++;
+                        }
+                    }
+                }
             }
+            rr += 4;
+#pragma unroll
+            for (uint32_t cc = 0; cc < 4; cc++)
+                if (cc != best && key_less(khi[cc], kix[cc], qmin.hi, qmin.idx)) { qmin.hi = khi[cc]; qmin.idx = kix[cc]; }
         }
         if (w.status != HP_BLOCK_OK) break;
-        rr += nchild; next_idx += nchild; qsize += nchild;
-        // parent record back to the free list; tracker.add_hap(L+1) x nchild (:531, :558)
-        if (lane == 0) {
-            __stcg(s.freelist + free_top, prec);
-            __stcg(s.lencnt + L + 1, __ldcg(s.lencnt + L + 1) + nchild);
-        }
-        free_top++;
+        next_idx += nchild; qsize += nchild;
+        // tracker.add_hap(L+1) x nchild (:531, :558)
+        if (lane == 0) atomicAdd(s.lencnt + L + 1, nchild);
         if (L + 1 >= trk_thresh) trk_total += nchild;
+        // ---- the best child is the new cur (record inherited in place) ----
+        {
+            const uint32_t bf = (best == 0) ? fro[0] : (best == 1) ? fro[1] : (best == 2) ? fro[2] : fro[3];
+            cur_hi = khi[best]; cur_idx = kix[best]; cur_len = L + 1; cur_frozen += bf;
+            cur_ident = cur_ident && best >= 2u;
+        }
         __syncwarp();
 
         // ---- pruning bookkeeping (:564-585) ----
         while (trk_total > curr_thresh && min_progress < next_expected) {
             min_progress++;
             uint32_t dropped = 0;
-            if (lane == 0) dropped = __ldcg(s.lencnt + min_progress - 1);
+            if (lane == 0) dropped = atomicAdd(s.lencnt + min_progress - 1, 0u);
             dropped = __shfl_sync(HP_FULL_MASK, dropped, 0);
             trk_total -= dropped; trk_thresh = min_progress;
             if (qsize > max_queue) {
-                // "full prune": every entry shorter than min_progress gets the cleared priority (cost 0)
+                // "full prune": every queued entry shorter than min_progress gets the cleared priority (cost 0);
+                // cur has length >= next_expected >= min_progress and is never affected
                 const uint32_t b0 = lane * scap;
-                cm.hi = ~0ull; cm.idx = 0xffffffffu; cm.pos = 0;
+                c_hi = ~0ull; c_idx = 0xffffffffu; c_pos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
-                    uint64_t hi = __ldcg(s.khi + b0 + i);
-                    const uint32_t idx = __ldcg(s.kidx + b0 + i);
-                    if (__ldcg(s.klen + b0 + i) < min_progress) { hi &= 0xffffffffull; __stcg(s.khi + b0 + i, hi); }
-                    if (key_less(hi, idx, cm.hi, cm.idx)) { cm.hi = hi; cm.idx = idx; cm.pos = i; }
+                    uint64_t hi = s.khi[b0 + i];
+                    const uint32_t ix = s.kidx[b0 + i];
+                    if ((s.klen[b0 + i] & 0x7fffffffu) < min_progress) { hi &= 0xffffffffull; s.khi[b0 + i] = hi; }
+                    if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = i; }
                 }
                 __syncwarp();
+                qmin = wmin96(c_hi, c_idx);
             }
         }
     }
     if (w.status != HP_BLOCK_OK) return;
 
     // ---- final node (:588-628) ----
-    const uint32_t frec = __ldcg(s.krec + top_slot);
-    const uint64_t* frow = s.recs + (uint64_t)frec * 2 * HW;
+    const uint32_t top_total = (uint32_t)(cur_hi >> 32);
+    const uint64_t* frow = s.recs + (uint64_t)cur_rec * 2 * HW;
     uint32_t phased = 0, phased_snv = 0, skipped = 0;
     const uint8_t* snv = a.is_snv + m.var_base;
     for (uint32_t i = lane; i < N; i += 32) {
-        uint32_t b1 = (uint32_t)(__ldcg(frow + (i >> 6)) >> (i & 63)) & 1u;
-        uint32_t b2 = (uint32_t)(__ldcg(frow + HW + (i >> 6)) >> (i & 63)) & 1u;
+        uint32_t b1 = (uint32_t)(frow[i >> 6] >> (i & 63)) & 1u;
+        uint32_t b2 = (uint32_t)(frow[HW + (i >> 6)] >> (i & 63)) & 1u;
         if (__ldg(ign + i)) { b1 = 2; b2 = 2; skipped++; }
         else if (b1 != b2) { phased++; if (__ldg(snv + i)) phased_snv++; }
         a.out_h1[m.var_base + i] = (uint8_t)b1;
@@ -671,16 +849,49 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     if (lane == 0) {
         uint64_t* st = a.out_stats + (uint64_t)blk * 7;
         st[0] = num_pruned;
-        st[1] = __ldcg(Hg + 0);
+        st[1] = Hg[0];
         st[2] = top_total;
         st[3] = phased; st[4] = phased_snv; st[5] = N - phased - skipped; st[6] = skipped;
-        if (top_total < __ldcg(Hg + 0)) w.status = HP_BLOCK_ASSERT;        // phase_stats.rs:163
     }
-    w.status = __shfl_sync(HP_FULL_MASK, w.status, 0);
+    if (top_total < Hg[0]) w.status = HP_BLOCK_ASSERT;                     // phase_stats.rs:163
+}
+
+// One phase block, start to finish, by one warp.
+template <int K, bool kCount>
+__device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, const Slab& slab, uint32_t blk) {
+    const uint32_t N = m.n_var;
+    uint32_t* Hg = a.heur + m.var_base + blk;
+    // ---- calculate_astar_heuristic (:246-292) ----
+    const uint8_t* ign = a.ignored + m.var_base;
+    if (w.lane == 0) { w.hring[N & 63] = 0; Hg[N] = 0; }
+    __syncwarp();
+    uint32_t clip = 1;
+    uint64_t badwin = 0;
+    for (uint32_t v = N; v-- > 0;) {
+        const uint32_t bad_v = __ldg(ign + v);
+        badwin = (badwin << 1) | (bad_v ? 1ull : 0ull);
+        const uint2 r = sub_solve<K, kCount>(a, m, w, v, clip, badwin, blk);
+        if (w.status != HP_BLOCK_OK) return;
+        const uint32_t est = r.x, solved = r.y;
+        if (solved < min(clip, 2u)) { w.status = HP_BLOCK_ASSERT; return; }          // :268
+        const uint32_t hnext = w.hring[(v + 1) & 63];
+        uint32_t hv;
+        if (bad_v) hv = hnext;
+        else {
+            if (est < hnext) { w.status = HP_BLOCK_ASSERT; return; }                  // :284
+            hv = est;
+        }
+        __syncwarp();
+        if (w.lane == 0) { w.hring[v & 63] = hv; Hg[v] = hv; }
+        __syncwarp();
+        clip = min(solved + 1, HP_MAX_SEGMENT);                                      // :288
+    }
+    main_solve<K, kCount>(a, m, w, slab, blk, Hg);
 }
 
 constexpr int kSolveWarps = 8;
 
+template <bool kCount>
 __global__ void __launch_bounds__(kSolveWarps * 32, 1) astar_solve_kernel(AstarArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5;
@@ -708,46 +919,25 @@ __global__ void __launch_bounds__(kSolveWarps * 32, 1) astar_solve_kernel(AstarA
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
         w.status = m.status;
-        const uint32_t N = m.n_var;
-        uint32_t* Hg = a.heur + m.var_base + blk;
 
         if (w.status == HP_BLOCK_OK) {
-            // ---- calculate_astar_heuristic (:246-292) ----
-            const uint8_t* ign = a.ignored + m.var_base;
-            if (w.lane == 0) { w.hring[N & 63] = 0; Hg[N] = 0; }
-            __syncwarp();
-            uint32_t clip = 1;
-            uint64_t badwin = 0;
-            for (uint32_t v = N; v-- > 0;) {
-                const uint32_t bad_v = __ldg(ign + v);
-                badwin = (badwin << 1) | (bad_v ? 1ull : 0ull);
-                const uint2 r = sub_solve(a, m, w, v, clip, badwin, blk);
-                if (w.status != HP_BLOCK_OK) break;
-                const uint32_t est = r.x, solved = r.y;
-                if (solved < min(clip, 2u)) { w.status = HP_BLOCK_ASSERT; break; }          // :268
-                const uint32_t hnext = w.hring[(v + 1) & 63];
-                uint32_t hv;
-                if (bad_v) hv = hnext;
-                else {
-                    if (est < hnext) { w.status = HP_BLOCK_ASSERT; break; }                  // :284
-                    hv = est;
-                }
-                __syncwarp();
-                if (w.lane == 0) { w.hring[v & 63] = hv; __stcg(Hg + v, hv); }
-                __syncwarp();
-                clip = min(solved + 1, HP_MAX_SEGMENT);                                      // :288
-            }
+            // register-resident score vectors cover up to 32*K active reads per column
+            if (m.max_act <= 32) solve_block<1, kCount>(a, m, w, slab, blk);
+            else if (m.max_act <= 64) solve_block<2, kCount>(a, m, w, slab, blk);
+            else solve_block<0, kCount>(a, m, w, slab, blk);
         }
-        if (w.status == HP_BLOCK_OK) main_solve(a, m, w, slab, blk, Hg);
+        w.status = __shfl_sync(HP_FULL_MASK, w.status, 0);
 
         // ---- per-block outputs ----
         __syncwarp();
         if (w.status != HP_BLOCK_OK) {
             if (w.lane < 7) a.out_stats[(uint64_t)blk * 7 + w.lane] = 0;
         }
-        if (a.out_heur && w.status == HP_BLOCK_OK)
-            for (uint32_t i = w.lane; i <= N; i += 32) a.out_heur[m.var_base + blk + i] = __ldcg(Hg + i);
-        if (a.out_counters) {
+        if (a.out_heur && w.status == HP_BLOCK_OK) {
+            const uint32_t* Hg = a.heur + m.var_base + blk;
+            for (uint32_t i = w.lane; i <= m.n_var; i += 32) a.out_heur[m.var_base + blk + i] = Hg[i];
+        }
+        if (kCount && a.out_counters) {
             const uint64_t cells = __reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells & 0xffffffffu)) +
                                    ((uint64_t)__reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells >> 32)) << 32);
             if (w.lane == 0) {
@@ -779,9 +969,16 @@ cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream) {
 
 cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, cudaStream_t stream) {
     const size_t smem = astar_smem_bytes(a.sub_capl);
-    cudaError_t e = cudaFuncSetAttribute(astar_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    astar_solve_kernel<<<n_ctas, kSolveWarps * 32, smem, stream>>>(a);
+    cudaError_t e;
+    if (a.out_counters) {
+        e = cudaFuncSetAttribute(astar_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        astar_solve_kernel<true><<<n_ctas, kSolveWarps * 32, smem, stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(astar_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        astar_solve_kernel<false><<<n_ctas, kSolveWarps * 32, smem, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

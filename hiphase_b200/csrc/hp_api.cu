@@ -86,7 +86,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     const uint64_t n_vb = n_vars + nb;
     if (!ctx->meta.reserve(sizeof(BlkMeta) * (size_t)nb) || !ctx->rmeta.reserve(sizeof(ReadMeta) * (size_t)(n_reads + 1)) ||
         !ctx->planes.reserve(8ull * HP_PLANE_STRIDE * n_words) || !ctx->act_off.reserve(4 * n_vb) ||
-        !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->order.reserve(4ull * nb) ||
+        !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->col.reserve(4 * (n_cells + 1)) || !ctx->order.reserve(4ull * nb) ||
         !ctx->heur.reserve(4 * n_vb) || !ctx->ticket.reserve(256 + 4 * 64))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "workspace allocation failed");
 
@@ -106,7 +106,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     pa.read_end = batch->read_end; pa.cell_off = batch->cell_off; pa.alleles = batch->alleles; pa.quals = batch->quals;
     pa.ignored = batch->ignored;
     pa.meta = (BlkMeta*)ctx->meta.ptr; pa.rmeta = (ReadMeta*)ctx->rmeta.ptr; pa.planes = (uint64_t*)ctx->planes.ptr;
-    pa.act_off = (uint32_t*)ctx->act_off.ptr; pa.act_cur = (uint32_t*)ctx->act_cur.ptr; pa.act_idx = (uint32_t*)ctx->act_idx.ptr;
+    pa.act_off = (uint32_t*)ctx->act_off.ptr; pa.act_cur = (uint32_t*)ctx->act_cur.ptr; pa.act_idx = (uint32_t*)ctx->act_idx.ptr; pa.col = (uint32_t*)ctx->col.ptr;
     HP_CUDA(ctx, launch_astar_prep(pa, stream));
     ctx->launches++;
 
@@ -121,7 +121,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     AstarArgs a;
     a.n_blocks = nb;
     a.alleles = batch->alleles; a.quals = batch->quals; a.ignored = batch->ignored; a.is_snv = batch->is_snv;
-    a.meta = pa.meta; a.rmeta = pa.rmeta; a.planes = pa.planes; a.act_off = pa.act_off; a.act_idx = pa.act_idx;
+    a.meta = pa.meta; a.rmeta = pa.rmeta; a.planes = pa.planes; a.act_off = pa.act_off; a.act_idx = pa.act_idx; a.col = pa.col;
     a.order = (uint32_t*)ctx->order.ptr;
     a.heur = (uint32_t*)ctx->heur.ptr; a.ticket = (uint32_t*)ctx->ticket.ptr;
     a.slabs = (uint8_t*)ctx->slabs.ptr; a.slab_bytes = slab_bytes; a.qcap = ctx->qcap; a.hap_words = hap_words;
@@ -195,7 +195,7 @@ void hp_ctx_destroy(hp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->meta, &ctx->rmeta, &ctx->planes, &ctx->act_off, &ctx->act_cur, &ctx->act_idx, &ctx->order,
+    for (DevBuf* b : {&ctx->meta, &ctx->rmeta, &ctx->planes, &ctx->act_off, &ctx->act_cur, &ctx->act_idx, &ctx->col, &ctx->order,
                       &ctx->heur, &ctx->ticket, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);

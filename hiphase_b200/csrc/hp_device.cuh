@@ -21,7 +21,7 @@ struct BlkMeta {
     uint32_t n_planes;     // bit planes needed for qual / qgcd
     int32_t  status;       // HP_BLOCK_*
     uint32_t max_span;     // longest read region
-    uint32_t pad;
+    uint32_t max_act;      // largest number of reads covering one variant
 };
 
 // Per-read metadata (16 B, one LDG.128).
@@ -46,6 +46,7 @@ struct AstarArgs {
     const uint64_t* planes;      // [n_words * HP_PLANE_STRIDE]
     const uint32_t* act_off;     // [n_vars + n_blocks] per block N+1 offsets (relative to cell_base) into act_idx
     const uint32_t* act_idx;     // [n_cells] block-relative read index of each (variant, covering read) pair
+    const uint32_t* col;         // [n_cells] column record of the same pair: qual | allele<<8 | ends<<10 | carry<<16
     const uint32_t* order;       // [n_blocks] processing order (largest first)
     // scratch
     uint32_t* heur;              // [n_vars + n_blocks] H[] per block (u32 is exact: total quals < 2^31 is enforced)
@@ -84,6 +85,7 @@ struct PrepArgs {
     uint32_t* act_off;   // zero-initialised; first used as per-variant counters, then overwritten with offsets
     uint32_t* act_cur;   // zero-initialised cursors
     uint32_t* act_idx;
+    uint32_t* col;
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

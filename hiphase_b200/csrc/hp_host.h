@@ -41,7 +41,7 @@ struct hp_ctx {
     uint64_t launches = 0;
     std::string err;
     // A* workspaces
-    hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, order, heur, ticket, slabs, stage_in, stage_out;
+    hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, slabs, stage_in, stage_out;
     // WFA workspaces
     hp::DevBuf wfa_ws, wfa_in, wfa_out;
 };

@@ -49,6 +49,7 @@ extern "C" {
 #define HP_BLOCK_COST_OVERFLOW     2   /* sum of all quals in the block >= 2^31: 32-bit cost path refused       */
 #define HP_BLOCK_QUEUE_OVERFLOW    3   /* internal: main queue outgrew its slab (retried transparently)         */
 #define HP_BLOCK_ASSERT            4   /* a reference assert! would have fired (e.g. astar_phaser.rs:284, 529)  */
+#define HP_BLOCK_TOO_DENSE         5   /* more than 65534 reads cover one variant: outside the kernel's range   */
 
 /* per-job status written to hp_wfa_out.status */
 #define HP_WFA_OK                  0
