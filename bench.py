@@ -159,12 +159,15 @@ def main():
     o_stats = torch.zeros(nb * 7, dtype=torch.int64, device=dev)
     o_status = torch.full((nb,), -1, dtype=torch.int32, device=dev)
     o_ctr = torch.zeros(nb * 4, dtype=torch.int64, device=dev)
+    dout_ctr = A.hp_astar_out(dptr(o_h1, A.u8p), dptr(o_h2, A.u8p), C.cast(o_stats.data_ptr(), C.POINTER(A.hp_phase_stats)),
+                              dptr(o_status, A.i32p), A.u64p(), C.cast(o_ctr.data_ptr(), C.POINTER(A.hp_astar_counters)))
+    # the timed steps run the production kernel (no work counters); one warm-up step runs the counting variant
     dout = A.hp_astar_out(dptr(o_h1, A.u8p), dptr(o_h2, A.u8p), C.cast(o_stats.data_ptr(), C.POINTER(A.hp_phase_stats)),
-                          dptr(o_status, A.i32p), A.u64p(), C.cast(o_ctr.data_ptr(), C.POINTER(A.hp_astar_counters)))
+                          dptr(o_status, A.i32p), A.u64p(), C.POINTER(A.hp_astar_counters)())
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_device():
-        ctx.astar_solve_device(dbatch, batch.n_vars, batch.n_reads, batch.n_cells, max_n, dout, torch.cuda.current_stream().cuda_stream)
+    def step_device(o=None):
+        ctx.astar_solve_device(dbatch, batch.n_vars, batch.n_reads, batch.n_cells, max_n, o or dout, torch.cuda.current_stream().cuda_stream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -172,6 +175,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    step_device(dout_ctr)
     for _ in range(args.warmup):
         flush.fill_(1)
         step_device()

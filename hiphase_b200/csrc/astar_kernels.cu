@@ -309,18 +309,22 @@ __device__ __forceinline__ void expand(const AstarArgs& a, const BlkMeta& m, uin
 
 // present-candidate mask of an expansion
 __device__ __forceinline__ uint32_t present_mask(bool bad_col, bool ident) { return bad_col ? 0x4u : (ident ? 0xdu : 0xfu); }
-
-// ---- sub-solver key: [total:32][63-hets:6][node_index:20][len:6] -------------------------------------------
-__device__ __forceinline__ uint64_t sub_key(uint32_t total, uint32_t hets, uint32_t idx, uint32_t len) {
-    return ((uint64_t)total << 32) | ((uint64_t)(63u - hets) << 26) | ((uint64_t)idx << 6) | len;
+// candidate slot of the d-th created child of an expansion with that mask
+__device__ __forceinline__ uint32_t slot_of_ordinal(uint32_t present, uint32_t d) {
+    return present == 0xfu ? d : (present == 0xdu ? d + (d > 0u ? 1u : 0u) : 2u);
 }
 
+// ---- sub-solver key: [total:32][63-hets:6][node_index:20][len:6] -------------------------------------------
+__device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+// One sub-solver queue entry (32 B = two 128-bit shared-memory transactions).
+struct __align__(16) SubEntry {
+    uint64_t key, h1, h2;
+    uint32_t frozen, pad;
+};
+
 struct WarpCtx {
-    // shared-memory views of this warp's sub-solver queue (stripe-major: lane l owns [l*capl, (l+1)*capl))
-    uint64_t* sq_key;
-    uint64_t* sq_h1;
-    uint64_t* sq_h2;
-    uint32_t* sq_frozen;
+    SubEntry* sq;           // this warp's sub-solver queue in shared memory (stripe-major: lane l owns [l*capl, (l+1)*capl))
     uint32_t* hring;        // H[] ring buffer, 64 entries
     uint32_t capl;
     uint32_t lane;
@@ -328,6 +332,12 @@ struct WarpCtx {
     uint64_t evals, sum_lp, pops, cells;
     int status;
 };
+
+__device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1, uint64_t h2, uint32_t frozen) {
+    uint4* p = reinterpret_cast<uint4*>(e);
+    p[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
+    p[1] = make_uint4((uint32_t)h2, (uint32_t)(h2 >> 32), frozen, 0u);
+}
 
 // astar_subsolver (astar_phaser.rs:311-405).  Returns est in .x, solved depth in .y (both warp-uniform).
 //
@@ -342,158 +352,160 @@ __device__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uin
     const uint32_t* aidx = a.act_idx + m.cell_base;
     const uint32_t* col = a.col + m.cell_base;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
-    const uint32_t base = lane * w.capl;
+    SubEntry* stripe = w.sq + lane * w.capl;
 
     // queue state: cached stripe minimum + stripe count in registers; qmin = warp-uniform queue minimum
     uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
     // root: AstarNode::new(H[v+1]) (:325), kept in registers as the current top
-    uint64_t cur_key = sub_key(w.hring[(v + 1) & 63], 0, 0, 0), cur_h1 = 0, cur_h2 = 0;
-    uint32_t cur_frozen = 0;
-    bool have_cur = true;
+    uint32_t cur_total = w.hring[(v + 1) & 63], cur_lo = 63u << 26, cur_frozen = 0;
+    uint64_t cur_h1 = 0, cur_h2 = 0;
+    int cur_src = SRC_ROOT;
+    uint32_t cur_x1 = 0, cur_x2 = 0;
     ExpCache<K> cache;
     cache.first_idx = 0xffffffffu; cache.present = 0;
     uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 0;
     const uint32_t max_visits = a.min_queue_size / 10 + a.queue_increment * clip;    // :266, :333
 
     for (;;) {
-        if (!have_cur || qmin < cur_key) {
-            if (have_cur) {                                              // the dive broke: cur goes back to the queue
+        if (qmin < mk64(cur_total, cur_lo)) {
+            // ---- the dive broke: cur goes back to the queue, then a real pop of the entry whose key is qmin ----
+            {
                 const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
                 if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
                 uint32_t target = rr & 31u; rr++;
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
-                    w.sq_key[base + cnt] = cur_key; w.sq_h1[base + cnt] = cur_h1; w.sq_h2[base + cnt] = cur_h2;
-                    w.sq_frozen[base + cnt] = cur_frozen;
-                    if (cur_key < ckey) { ckey = cur_key; cpos = cnt; }
+                    const uint64_t k = mk64(cur_total, cur_lo);
+                    sub_store(stripe + cnt, k, cur_h1, cur_h2, cur_frozen);
+                    if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
                 __syncwarp();
             }
-            // ---- real pop: the entry whose key is qmin ----
-            if (qmin == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
-            const uint32_t slot = owner * w.capl + pos;
-            cur_key = qmin; cur_h1 = w.sq_h1[slot]; cur_h2 = w.sq_h2[slot]; cur_frozen = w.sq_frozen[slot];
+            const SubEntry* e = w.sq + owner * w.capl + pos;
+            cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
+            cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
             __syncwarp();
             if ((int)lane == owner) {                                    // remove + rescan own stripe
                 cnt--;
                 if (pos != cnt) {
-                    w.sq_key[slot] = w.sq_key[base + cnt]; w.sq_h1[slot] = w.sq_h1[base + cnt];
-                    w.sq_h2[slot] = w.sq_h2[base + cnt]; w.sq_frozen[slot] = w.sq_frozen[base + cnt];
+                    const uint4* sp = reinterpret_cast<const uint4*>(stripe + cnt);
+                    uint4* dp = reinterpret_cast<uint4*>(stripe + pos);
+                    dp[0] = sp[0]; dp[1] = sp[1];
                 }
                 ckey = ~0ull; cpos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
-                    const uint64_t k = w.sq_key[base + i];
+                    const uint64_t k = stripe[i].key;
                     if (k < ckey) { ckey = k; cpos = i; }
                 }
             }
             qmin = wmin64(ckey);
-            have_cur = true;
+            // where does this node's score vector come from?
+            const uint32_t d = ((cur_lo >> 6) & 0xfffffu) - cache.first_idx;
+            if ((cur_lo & 63u) == 0u) cur_src = SRC_ROOT;
+            else if (K > 0 && d < (uint32_t)__popc(cache.present)) {
+                const uint32_t cs = slot_of_ordinal(cache.present, d);
+                cur_src = SRC_CACHE; cur_x1 = cs & 1u; cur_x2 = (0x9u >> cs) & 1u;
+            } else cur_src = SRC_PLANES;
         }
         // ---- cur is the top of the queue (peek) ----
-        const uint32_t L = (uint32_t)cur_key & 63u;
-        const uint32_t total = (uint32_t)(cur_key >> 32);
+        const uint32_t L = cur_lo & 63u;
         if (L >= clip) {                                                 // :395-399 (peek, not pop)
-            max_cost = max(max_cost, total);
+            max_cost = max(max_cost, cur_total);
             next_expected++;
             break;
         }
         if (visits >= max_visits) break;
         visits++;
-        w.pops++;
-        if (L == next_expected) { max_cost = max(max_cost, total); next_expected++; }   // :342-346
+        if (L == next_expected) { max_cost = max(max_cost, cur_total); next_expected++; }   // :342-346
 
         // ---- expand ----
         const uint32_t p = v + L;
         const bool bad_col = (badwin >> L) & 1ull;
         const uint32_t heur = w.hring[(p + 1) & 63];
         const uint32_t o0 = __ldg(aoff + p), o1 = __ldg(aoff + p + 1);
-        const uint32_t idx = ((uint32_t)cur_key >> 6) & 0xfffffu;
-        const uint32_t hets = 63u - (((uint32_t)cur_key >> 26) & 63u);
         const bool ident = (cur_h1 == cur_h2);
-        int src = SRC_PLANES;
-        uint32_t x1 = 0, x2 = 0;
-        if (L == 0) src = SRC_ROOT;
-        else if (K > 0 && idx - cache.first_idx < (uint32_t)__popc(cache.present)) {
-            src = SRC_CACHE;
-            const uint32_t cslot = __fns(cache.present, 0, (int)(idx - cache.first_idx) + 1);
-            x1 = (cslot == 1u || cslot == 3u); x2 = (cslot == 0u || cslot == 3u);
-        }
         auto hap = [&](int which, int i0) { return shift_signed(which ? cur_h2 : cur_h1, i0); };
         uint32_t tot[4], fro[4];
         uint64_t cells = 0;
-        expand<K, kCount>(a, m, lane, col + o0, aidx + o0, rmeta, o1 - o0, p, (int)v, (int)L, bad_col, ident, src, x1, x2,
-                          hap, cache, tot, fro, cells);
+        expand<K, kCount>(a, m, lane, col + o0, aidx + o0, rmeta, o1 - o0, p, (int)v, (int)L, bad_col, ident, cur_src,
+                          cur_x1, cur_x2, hap, cache, tot, fro, cells);
         const uint32_t present = present_mask(bad_col, ident);
-        const uint32_t nchild = __popc(present);
+        const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
         cache.first_idx = next_idx; cache.present = present;
-        if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
+        if (kCount) { w.pops++; w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
 
-        // keys of the candidates, in creation order
-        const uint64_t bit = bad_col ? 0ull : (1ull << L);
-        uint64_t key[4];
-        uint32_t best = 2;
-#pragma unroll
-        for (uint32_t c = 0; c < 4; c++) {
-            const uint32_t ord = __popc(present & ((1u << c) - 1u));
-            const uint32_t ch = hets + ((c < 2 && !bad_col) ? 1u : 0u);
-            key[c] = ((present >> c) & 1u) ? sub_key(cur_frozen + tot[c] + heur, ch, next_idx + ord, L + 1) : ~0ull;
-        }
-#pragma unroll
-        for (uint32_t c = 0; c < 4; c++) if (key[c] < key[best]) best = c;
-        if (bad_col && cur_frozen + tot[2] + heur != total) { w.status = HP_BLOCK_ASSERT; break; }   // :360
+        // candidate keys.  total_c = frozen + tot_c + heur; the low words are ordered lo0 < lo1 < lo2 < lo3 (more
+        // hets first, then creation order), so ties on the total are won by the lowest candidate slot.
+        const uint32_t fh = cur_frozen + heur;
+        const uint32_t t0 = bad_col ? 0xffffffffu : fh + tot[0];
+        const uint32_t t1 = (bad_col || ident) ? 0xffffffffu : fh + tot[1];
+        const uint32_t t2 = fh + tot[2];
+        const uint32_t t3 = bad_col ? 0xffffffffu : fh + tot[3];
+        if (bad_col && t2 != cur_total) { w.status = HP_BLOCK_ASSERT; break; }             // :360
+        const uint32_t lo_base = (cur_lo & 0xfc000000u) | (next_idx << 6) | (L + 1);
+        const uint32_t lo0 = lo_base - (1u << 26), lo1 = lo0 + 64u;
+        const uint32_t lo2 = lo_base + (bad_col ? 0u : (ident ? 64u : 128u)), lo3 = lo2 + 64u;
+        const uint32_t tmin = min(min(t0, t1), min(t2, t3));
+        const uint32_t best = (t0 == tmin) ? 0u : (t1 == tmin) ? 1u : (t2 == tmin) ? 2u : 3u;
 
         // ---- push the siblings of the best child (one lane each, round-robin over the stripes) ----
+        const uint64_t bit = bad_col ? 0ull : (1ull << L);
         {
             const uint32_t c = (lane - rr) & 31u;
             const bool mine = c < 4u && ((present >> c) & 1u) && c != best;
             const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl);
+            const uint32_t mt = (c == 0u) ? t0 : (c == 1u) ? t1 : (c == 2u) ? t2 : t3;
+            const uint32_t ml = (c == 0u) ? lo0 : (c == 1u) ? lo1 : (c == 2u) ? lo2 : lo3;
+            const uint32_t mf = cur_frozen + ((c == 0u) ? fro[0] : (c == 1u) ? fro[1] : (c == 2u) ? fro[2] : fro[3]);
             if (fullmask == 0) {
                 if (mine) {
-                    const uint64_t k = (c == 0) ? key[0] : (c == 1) ? key[1] : (c == 2) ? key[2] : key[3];
-                    const uint32_t fr = cur_frozen + ((c == 0) ? fro[0] : (c == 1) ? fro[1] : (c == 2) ? fro[2] : fro[3]);
-                    w.sq_key[base + cnt] = k;
-                    w.sq_h1[base + cnt] = cur_h1 | ((c == 1u || c == 3u) ? bit : 0ull);
-                    w.sq_h2[base + cnt] = cur_h2 | ((c == 0u || c == 3u) ? bit : 0ull);
-                    w.sq_frozen[base + cnt] = fr;
+                    const uint64_t k = mk64(mt, ml);
+                    sub_store(stripe + cnt, k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
             } else {                                                     // rare: a target stripe is full
-#pragma unroll
                 for (uint32_t cc = 0; cc < 4; cc++) {
                     if (((present >> cc) & 1u) && cc != best) {
                         const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
                         if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
-                        uint32_t target = (rr + cc) & 31u;
+                        const uint32_t src_lane = (rr + cc) & 31u;        // the lane that computed this child's fields
+                        uint32_t target = src_lane;
                         if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                        const uint32_t xt = __shfl_sync(HP_FULL_MASK, mt, src_lane), xl = __shfl_sync(HP_FULL_MASK, ml, src_lane);
+                        const uint32_t xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
                         if (lane == target) {
-                            w.sq_key[base + cnt] = key[cc];
-                            w.sq_h1[base + cnt] = cur_h1 | ((cc == 1u || cc == 3u) ? bit : 0ull);
-                            w.sq_h2[base + cnt] = cur_h2 | ((cc == 0u || cc == 3u) ? bit : 0ull);
-                            w.sq_frozen[base + cnt] = cur_frozen + fro[cc];
-                            if (key[cc] < ckey) { ckey = key[cc]; cpos = cnt; }
+                            const uint64_t k = mk64(xt, xl);
+                            sub_store(stripe + cnt, k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
+                            if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
                     }
                 }
             }
             rr += 4;
-#pragma unroll
-            for (uint32_t cc = 0; cc < 4; cc++) if (cc != best && key[cc] < qmin) qmin = key[cc];
+        }
+        // queue minimum now includes the siblings
+        {
+            const uint64_t k0 = (best == 0u) ? ~0ull : mk64(t0, lo0), k1 = (best == 1u) ? ~0ull : mk64(t1, lo1);
+            const uint64_t k2 = (best == 2u) ? ~0ull : mk64(t2, lo2), k3 = (best == 3u) ? ~0ull : mk64(t3, lo3);
+            const uint64_t ka = k0 < k1 ? k0 : k1, kb = k2 < k3 ? k2 : k3;
+            const uint64_t kc = ka < kb ? ka : kb;
+            qmin = kc < qmin ? kc : qmin;
         }
         next_idx += nchild;
-        // ---- the best child is the new cur ----
-        {
-            const uint32_t bf = (best == 0) ? fro[0] : (best == 1) ? fro[1] : (best == 2) ? fro[2] : fro[3];
-            cur_key = key[best];
-            cur_h1 |= (best == 1u || best == 3u) ? bit : 0ull;
-            cur_h2 |= (best == 0u || best == 3u) ? bit : 0ull;
-            cur_frozen += bf;
-        }
+        // ---- the best child is the new cur; its score vector is in the expansion cache ----
+        cur_total = tmin;
+        cur_lo = (best == 0u) ? lo0 : (best == 1u) ? lo1 : (best == 2u) ? lo2 : lo3;
+        cur_frozen += (best == 0u) ? fro[0] : (best == 1u) ? fro[1] : (best == 2u) ? fro[2] : fro[3];
+        cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
+        cur_h1 |= cur_x1 ? bit : 0ull;
+        cur_h2 |= cur_x2 ? bit : 0ull;
+        cur_src = (K > 0) ? SRC_CACHE : SRC_PLANES;
         __syncwarp();
         if (w.status != HP_BLOCK_OK) break;
     }
@@ -685,8 +697,8 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         if (L == 0) src = SRC_ROOT;
         else if (K > 0 && cur_idx - cache.first_idx < (uint32_t)__popc(cache.present)) {
             src = SRC_CACHE;
-            const uint32_t cslot = __fns(cache.present, 0, (int)(cur_idx - cache.first_idx) + 1);
-            x1 = (cslot == 1u || cslot == 3u); x2 = (cslot == 0u || cslot == 3u);
+            const uint32_t cslot = slot_of_ordinal(cache.present, cur_idx - cache.first_idx);
+            x1 = cslot & 1u; x2 = (0x9u >> cslot) & 1u;
         }
         auto hap = [&](int which, int i0) -> uint64_t {                   // 64 bits from haplotype position i0 >= 0
             const uint64_t* hw = prow + (which ? HW : 0);
@@ -899,13 +911,10 @@ __global__ void __launch_bounds__(kSolveWarps * 32, 1) astar_solve_kernel(AstarA
     w.lane = lane_id();
     w.capl = a.sub_capl;
     const uint32_t cap = w.capl * 32;
-    const size_t per_warp = (size_t)cap * 28 + 64 * 4;
-    uint8_t* base = smem_raw + warp * ((per_warp + 15) & ~(size_t)15);
-    w.sq_key = (uint64_t*)base;
-    w.sq_h1 = w.sq_key + cap;
-    w.sq_h2 = w.sq_h1 + cap;
-    w.sq_frozen = (uint32_t*)(w.sq_h2 + cap);
-    w.hring = w.sq_frozen + cap;
+    const size_t per_warp = (size_t)cap * sizeof(SubEntry) + 64 * 4;
+    uint8_t* base = smem_raw + warp * per_warp;
+    w.sq = (SubEntry*)base;
+    w.hring = (uint32_t*)(base + (size_t)cap * sizeof(SubEntry));
 
     const uint32_t gwarp = blockIdx.x * kSolveWarps + warp;
     const Slab slab = carve_slab(a.slabs + (uint64_t)gwarp * a.slab_bytes, a.qcap, a.hap_words);
@@ -955,7 +964,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32, 1) astar_solve_kernel(AstarA
 namespace hp {
 
 size_t astar_smem_bytes(uint32_t sub_capl) {
-    const size_t per_warp = ((size_t)sub_capl * 32 * 28 + 64 * 4 + 15) & ~(size_t)15;
+    const size_t per_warp = (size_t)sub_capl * 32 * sizeof(SubEntry) + 64 * 4;
     return per_warp * kSolveWarps;
 }
 int astar_solve_warps() { return kSolveWarps; }
