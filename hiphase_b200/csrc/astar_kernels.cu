@@ -345,7 +345,7 @@ __device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1
 // directly when its key beats the queue minimum (the dive): it is never written to the queue, and its score
 // vector comes from the expansion cache.  Otherwise cur is pushed and a real pop (redux.sync select) happens.
 template <int K, bool kCount>
-__device__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uint32_t v, uint32_t clip, uint64_t badwin,
+__device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uint32_t v, uint32_t clip, uint64_t badwin,
                            uint32_t blk) {
     const uint32_t lane = w.lane;
     const uint32_t* aoff = a.act_off + m.var_base + blk;
@@ -510,6 +510,282 @@ __device__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uin
         if (w.status != HP_BLOCK_OK) break;
     }
     return make_uint2(max_cost, next_expected - 1);
+}
+
+// astar_subsolver, register-resident fast path for blocks with at most 32*K reads per column.
+//
+// Critical path per pop (the dive): select (s1,s2) of the chosen child -> A0..B1 -> four mins -> deltas against
+// base = min(s1,s2) -> 2 redux.sync on 16-bit packed deltas -> child totals -> best child -> next pop.
+//   * child total = cur_total - H[p] + H[p+1] + sum_r delta_c(r): the parent's fluid cost is already inside its
+//     total, and each delta is <= the column quality (<= 255), so two deltas share one 32-bit redux.
+//   * the frozen part (reads ending at this column) is only reduced when some read ends here.
+//   * the four child values per read are shuffled into the NEXT column's slot order right away (carry index of the
+//     prefetched column record), off the critical path, so the next pop starts with two selects.
+template <int K, bool kCount>
+__device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uint32_t v, uint32_t clip, uint64_t badwin,
+                                uint32_t blk) {
+    const uint32_t lane = w.lane;
+    const uint32_t N = m.n_var;
+    const uint32_t* aoff = a.act_off + m.var_base + blk;
+    const uint32_t* aidx = a.act_idx + m.cell_base;
+    const uint32_t* col = a.col + m.cell_base;
+    const ReadMeta* rmeta = a.rmeta + m.read_base;
+    SubEntry* stripe = w.sq + lane * w.capl;
+    constexpr uint32_t kEmpty = 0xffff0000u;      // column record of an unused slot: no carry, quality 0
+
+    // queue state
+    uint64_t ckey = ~0ull, qmin = ~0ull;
+    uint32_t cpos = 0, cnt = 0;
+    // current top (root, :325)
+    uint32_t cur_total = w.hring[(v + 1) & 63], cur_lo = 63u << 26, cur_frozen = 0;
+    uint64_t cur_h1 = 0, cur_h2 = 0;
+    int cur_src = SRC_ROOT;
+    uint32_t cur_x1 = 0, cur_x2 = 0;
+    uint32_t heur_p = cur_total;                    // heuristic term inside cur_total (root quirk: H[v+1])
+    // children of the last expansion, already in the slot order of the column after it
+    uint32_t nA0[K], nA1[K], nB0[K], nB1[K], nW[K];
+    uint32_t cache_first = 0xffffffffu, cache_present = 0;
+    // column records of the current column p (slot = lane + 32k) and the offsets of p and p+1
+    uint32_t o_p = __ldg(aoff + v), o_p1 = __ldg(aoff + v + 1);
+    uint32_t colc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        nA0[k] = nA1[k] = nB0[k] = nB1[k] = nW[k] = 0;
+        colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+    }
+    uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 0;
+    const uint32_t max_visits = a.min_queue_size / 10 + a.queue_increment * clip;    // :266, :333
+
+    for (;;) {
+        if (qmin < mk64(cur_total, cur_lo)) {
+            // ---- the dive broke: cur goes back to the queue, then a real pop of the entry whose key is qmin ----
+            {
+                const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
+                if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
+                uint32_t target = rr & 31u; rr++;
+                if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                if (lane == target) {
+                    const uint64_t k = mk64(cur_total, cur_lo);
+                    sub_store(stripe + cnt, k, cur_h1, cur_h2, cur_frozen);
+                    if (k < ckey) { ckey = k; cpos = cnt; }
+                    cnt++;
+                }
+                __syncwarp();
+            }
+            const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
+            const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
+            const SubEntry* e = w.sq + owner * w.capl + pos;
+            cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
+            cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
+            __syncwarp();
+            if ((int)lane == owner) {                                    // remove + rescan own stripe
+                cnt--;
+                if (pos != cnt) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(stripe + cnt);
+                    uint4* dp = reinterpret_cast<uint4*>(stripe + pos);
+                    dp[0] = sp[0]; dp[1] = sp[1];
+                }
+                ckey = ~0ull; cpos = 0;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint64_t k = stripe[i].key;
+                    if (k < ckey) { ckey = k; cpos = i; }
+                }
+            }
+            qmin = wmin64(ckey);
+            // re-seat the column state on this node's position
+            const uint32_t Lp = cur_lo & 63u;
+            const uint32_t pp = v + Lp;
+            const uint32_t d = ((cur_lo >> 6) & 0xfffffu) - cache_first;
+            if (Lp == 0u) cur_src = SRC_ROOT;
+            else if (d < (uint32_t)__popc(cache_present)) {
+                // a child of the last expansion: the pre-permuted vectors are for exactly this column
+                const uint32_t cs = slot_of_ordinal(cache_present, d);
+                cur_src = SRC_CACHE; cur_x1 = cs & 1u; cur_x2 = (0x9u >> cs) & 1u;
+            } else cur_src = SRC_PLANES;
+            heur_p = w.hring[(Lp == 0u ? v + 1 : pp) & 63];
+            if (pp < N) {
+                o_p = __ldg(aoff + pp); o_p1 = __ldg(aoff + pp + 1);
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+            }
+        }
+        // ---- cur is the top of the queue (peek) ----
+        const uint32_t L = cur_lo & 63u;
+        if (L >= clip) {                                                 // :395-399 (peek, not pop)
+            max_cost = max(max_cost, cur_total);
+            next_expected++;
+            break;
+        }
+        if (visits >= max_visits) break;
+        visits++;
+        if (L == next_expected) { max_cost = max(max_cost, cur_total); next_expected++; }   // :342-346
+
+        const uint32_t p = v + L;
+        const uint32_t a_cur = o_p1 - o_p;
+        // ---- prefetch the next column's records (addresses are known; validity is masked once o_p2 arrives) ----
+        const bool has_next = p + 1 < N;
+        const uint32_t o_p2 = has_next ? __ldg(aoff + p + 2) : o_p1;
+        uint32_t coln[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col + o_p1 + lane + 32u * k) : kEmpty;
+        const uint32_t heur = w.hring[(p + 1) & 63];
+        const bool bad_col = (badwin >> L) & 1ull;
+        const bool ident = (cur_h1 == cur_h2);
+
+        // ---- this node's (s1, s2) per slot ----
+        uint32_t s1[K], s2[K], wv[K];
+        if (cur_src == SRC_CACHE) {
+#pragma unroll
+            for (int k = 0; k < K; k++) { s1[k] = cur_x1 ? nA1[k] : nA0[k]; s2[k] = cur_x2 ? nB1[k] : nB0[k]; wv[k] = nW[k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) { s1[k] = 0; s2[k] = 0; wv[k] = 0; }
+            if (cur_src == SRC_PLANES) {
+                auto hap = [&](int which, int i0) { return shift_signed(which ? cur_h2 : cur_h1, i0); };
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const uint32_t j = lane + 32u * k;
+                    if (j < a_cur) {
+                        const ReadMeta rm = rmeta[__ldg(aidx + o_p + j)];
+                        score_planes(a, m, rm, (int)v - (int)rm.start, (int)L, hap, s1[k], s2[k]);
+                        wv[k] = p - (uint32_t)max((int)rm.start, (int)v);
+                    }
+                }
+            }
+        }
+        // ---- children: deltas against base, packed two per word ----
+        uint32_t A0[K], A1[K], B0[K], B1[K];
+        uint32_t pk0 = 0, pk1 = 0, e01 = 0, e10 = 0, e00 = 0, e11 = 0;
+        bool anyend = false;
+        uint64_t cells = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t c = colc[k];
+            const uint32_t q = bad_col ? 0u : (c & 0xffu);
+            const uint32_t al = (c >> 8) & 3u;
+            const uint32_t q0 = (al != 0u) ? q : 0u, q1 = (al != 1u) ? q : 0u;
+            A0[k] = s1[k] + q0; A1[k] = s1[k] + q1; B0[k] = s2[k] + q0; B1[k] = s2[k] + q1;
+            const uint32_t base = min(s1[k], s2[k]);
+            const uint32_t c01 = min(A0[k], B1[k]), c10 = min(A1[k], B0[k]), c00 = min(A0[k], B0[k]), c11 = min(A1[k], B1[k]);
+            pk0 += (c01 - base) | ((c10 - base) << 16);
+            pk1 += (c00 - base) | ((c11 - base) << 16);
+            if ((c >> 10) & 1u) { anyend = true; e01 += c01; e10 += c10; e00 += c00; e11 += c11; }
+            if (kCount) { wv[k] += 1; if (lane + 32u * k < a_cur) cells += wv[k]; }
+        }
+        const uint32_t r0 = wsum(pk0), r1 = wsum(pk1);
+        uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+        if (__ballot_sync(HP_FULL_MASK, anyend)) { f0 = wsum(e01); f1 = wsum(e10); f2 = wsum(e00); f3 = wsum(e11); }
+
+        const uint32_t present = present_mask(bad_col, ident);
+        const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
+        if (kCount) { w.pops++; w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
+
+        // candidate totals / keys; low words are ordered lo0 < lo1 < lo2 < lo3, so the first minimum wins ties
+        const uint32_t tb = cur_total - heur_p + heur;
+        const uint32_t t0 = bad_col ? 0xffffffffu : tb + (r0 & 0xffffu);
+        const uint32_t t1 = (bad_col || ident) ? 0xffffffffu : tb + (r0 >> 16);
+        const uint32_t t2 = tb + (r1 & 0xffffu);
+        const uint32_t t3 = bad_col ? 0xffffffffu : tb + (r1 >> 16);
+        if (bad_col && t2 != cur_total) { w.status = HP_BLOCK_ASSERT; break; }             // :360
+        const uint32_t lo_base = (cur_lo & 0xfc000000u) | (next_idx << 6) | (L + 1);
+        const uint32_t lo0 = lo_base - (1u << 26), lo1 = lo0 + 64u;
+        const uint32_t lo2 = lo_base + (bad_col ? 0u : (ident ? 64u : 128u)), lo3 = lo2 + 64u;
+        const uint32_t tmin = min(min(t0, t1), min(t2, t3));
+        const uint32_t best = (t0 == tmin) ? 0u : (t1 == tmin) ? 1u : (t2 == tmin) ? 2u : 3u;
+
+        // ---- children vectors into the next column's slot order (off the critical path) ----
+        {
+            const uint32_t a_next = o_p2 - o_p1;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t cn = (lane + 32u * k < a_next) ? coln[k] : kEmpty;
+                const uint32_t carry = cn >> 16, sl = carry & 31u;
+                uint32_t g0 = __shfl_sync(HP_FULL_MASK, A0[0], sl), g1 = __shfl_sync(HP_FULL_MASK, A1[0], sl);
+                uint32_t g2 = __shfl_sync(HP_FULL_MASK, B0[0], sl), g3 = __shfl_sync(HP_FULL_MASK, B1[0], sl);
+                uint32_t gw = kCount ? __shfl_sync(HP_FULL_MASK, wv[0], sl) : 0u;
+#pragma unroll
+                for (int kk = 1; kk < K; kk++) {
+                    const uint32_t u0 = __shfl_sync(HP_FULL_MASK, A0[kk], sl), u1 = __shfl_sync(HP_FULL_MASK, A1[kk], sl);
+                    const uint32_t u2 = __shfl_sync(HP_FULL_MASK, B0[kk], sl), u3 = __shfl_sync(HP_FULL_MASK, B1[kk], sl);
+                    const uint32_t uw = kCount ? __shfl_sync(HP_FULL_MASK, wv[kk], sl) : 0u;
+                    if ((carry >> 5) == (uint32_t)kk) { g0 = u0; g1 = u1; g2 = u2; g3 = u3; gw = uw; }
+                }
+                const bool has = carry != 0xffffu;
+                nA0[k] = has ? g0 : 0u; nA1[k] = has ? g1 : 0u; nB0[k] = has ? g2 : 0u; nB1[k] = has ? g3 : 0u;
+                nW[k] = has ? gw : 0u;
+                colc[k] = cn;
+            }
+            o_p = o_p1; o_p1 = o_p2;
+        }
+        cache_first = next_idx; cache_present = present;
+
+        // ---- push the siblings of the best child (one lane each, round-robin over the stripes) ----
+        const uint64_t bit = bad_col ? 0ull : (1ull << L);
+        {
+            const uint32_t c = (lane - rr) & 31u;
+            const bool mine = c < 4u && ((present >> c) & 1u) && c != best;
+            const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl);
+            const uint32_t mt = (c == 0u) ? t0 : (c == 1u) ? t1 : (c == 2u) ? t2 : t3;
+            const uint32_t ml = (c == 0u) ? lo0 : (c == 1u) ? lo1 : (c == 2u) ? lo2 : lo3;
+            const uint32_t mf = cur_frozen + ((c == 0u) ? f0 : (c == 1u) ? f1 : (c == 2u) ? f2 : f3);
+            if (fullmask == 0) {
+                if (mine) {
+                    const uint64_t k = mk64(mt, ml);
+                    sub_store(stripe + cnt, k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
+                    if (k < ckey) { ckey = k; cpos = cnt; }
+                    cnt++;
+                }
+            } else {                                                     // rare: a target stripe is full
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if (((present >> cc) & 1u) && cc != best) {
+                        const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
+                        if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
+                        const uint32_t src_lane = (rr + cc) & 31u;
+                        uint32_t target = src_lane;
+                        if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                        const uint32_t xt = __shfl_sync(HP_FULL_MASK, mt, src_lane), xl = __shfl_sync(HP_FULL_MASK, ml, src_lane);
+                        const uint32_t xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
+                        if (lane == target) {
+                            const uint64_t k = mk64(xt, xl);
+                            sub_store(stripe + cnt, k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
+                            if (k < ckey) { ckey = k; cpos = cnt; }
+                            cnt++;
+                        }
+                    }
+                }
+            }
+            rr += 4;
+        }
+        // queue minimum now includes the siblings
+        {
+            const uint64_t k0 = (best == 0u) ? ~0ull : mk64(t0, lo0), k1 = (best == 1u) ? ~0ull : mk64(t1, lo1);
+            const uint64_t k2 = (best == 2u) ? ~0ull : mk64(t2, lo2), k3 = (best == 3u) ? ~0ull : mk64(t3, lo3);
+            const uint64_t ka = k0 < k1 ? k0 : k1, kb = k2 < k3 ? k2 : k3;
+            const uint64_t kc = ka < kb ? ka : kb;
+            qmin = kc < qmin ? kc : qmin;
+        }
+        next_idx += nchild;
+        // ---- the best child is the new cur ----
+        cur_total = tmin;
+        cur_lo = (best == 0u) ? lo0 : (best == 1u) ? lo1 : (best == 2u) ? lo2 : lo3;
+        cur_frozen += (best == 0u) ? f0 : (best == 1u) ? f1 : (best == 2u) ? f2 : f3;
+        cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
+        cur_h1 |= cur_x1 ? bit : 0ull;
+        cur_h2 |= cur_x2 ? bit : 0ull;
+        cur_src = SRC_CACHE;
+        heur_p = heur;
+        __syncwarp();
+        if (w.status != HP_BLOCK_OK) break;
+    }
+    return make_uint2(max_cost, next_expected - 1);
+}
+
+template <int K, bool kCount>
+__device__ __forceinline__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uint32_t v, uint32_t clip,
+                                           uint64_t badwin, uint32_t blk) {
+    if constexpr (K == 0) return sub_solve_generic<0, kCount>(a, m, w, v, clip, badwin, blk);
+    else return sub_solve_fast<K, kCount>(a, m, w, v, clip, badwin, blk);
 }
 
 // ---- main-queue slab (global memory, private to one warp) -----------------------------------------------------
@@ -873,6 +1149,7 @@ template <int K, bool kCount>
 __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, const Slab& slab, uint32_t blk) {
     const uint32_t N = m.n_var;
     uint32_t* Hg = a.heur + m.var_base + blk;
+    const long long t_start = kCount ? clock64() : 0;
     // ---- calculate_astar_heuristic (:246-292) ----
     const uint8_t* ign = a.ignored + m.var_base;
     if (w.lane == 0) { w.hring[N & 63] = 0; Hg[N] = 0; }
@@ -898,7 +1175,15 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
         __syncwarp();
         clip = min(solved + 1, HP_MAX_SEGMENT);                                      // :288
     }
+    const long long t_mid = kCount ? clock64() : 0;
+    const uint64_t pops_sub = w.pops;
     main_solve<K, kCount>(a, m, w, slab, blk, Hg);
+    if (kCount && a.dbg_cycles && w.lane == 0) {
+        a.dbg_cycles[4ull * blk + 0] = (uint64_t)(t_mid - t_start);
+        a.dbg_cycles[4ull * blk + 1] = (uint64_t)(clock64() - t_mid);
+        a.dbg_cycles[4ull * blk + 2] = pops_sub;
+        a.dbg_cycles[4ull * blk + 3] = w.pops - pops_sub;
+    }
 }
 
 constexpr int kSolveWarps = 8;

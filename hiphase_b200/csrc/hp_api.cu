@@ -86,7 +86,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     const uint64_t n_vb = n_vars + nb;
     if (!ctx->meta.reserve(sizeof(BlkMeta) * (size_t)nb) || !ctx->rmeta.reserve(sizeof(ReadMeta) * (size_t)(n_reads + 1)) ||
         !ctx->planes.reserve(8ull * HP_PLANE_STRIDE * n_words) || !ctx->act_off.reserve(4 * n_vb) ||
-        !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->col.reserve(4 * (n_cells + 1)) || !ctx->order.reserve(4ull * nb) ||
+        !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->col.reserve(4 * (n_cells + 130)) || !ctx->order.reserve(4ull * nb) ||
         !ctx->heur.reserve(4 * n_vb) || !ctx->ticket.reserve(256 + 4 * 64))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "workspace allocation failed");
 
@@ -129,6 +129,11 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     a.sub_capl = ctx->sub_capl;
     a.out_h1 = out->h1; a.out_h2 = out->h2; a.out_stats = (uint64_t*)out->stats; a.out_status = out->status;
     a.out_heur = out->heuristic; a.out_counters = (uint64_t*)out->counters;
+    a.dbg_cycles = nullptr;
+    if (out->counters && ctx->want_dbg) {
+        if (!ctx->dbg.reserve(32ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
+        a.dbg_cycles = (uint64_t*)ctx->dbg.ptr; ctx->dbg_blocks = nb;
+    }
 
     HP_CUDA(ctx, cudaEventRecord(ctx->ev0, stream));
     HP_CUDA(ctx, launch_astar_solve(a, n_ctas, stream));
@@ -196,7 +201,7 @@ void hp_ctx_destroy(hp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->meta, &ctx->rmeta, &ctx->planes, &ctx->act_off, &ctx->act_cur, &ctx->act_idx, &ctx->col, &ctx->order,
-                      &ctx->heur, &ctx->ticket, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out})
+                      &ctx->heur, &ctx->ticket, &ctx->dbg, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -204,6 +209,14 @@ void hp_ctx_destroy(hp_ctx* ctx) {
 }
 
 uint64_t hp_launch_count(const hp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Not part of the public header: per-block phase cycles of the last counting run (profiling aid for bench/profiles).
+int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
+int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
+    if (!ctx || !out || n_blocks > ctx->dbg_blocks || !ctx->dbg.ptr) return HP_ERR_INVALID_INPUT;
+    if (cudaMemcpy(out, ctx->dbg.ptr, 32ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
+    return HP_OK;
+}
 
 float hp_last_kernel_ms(const hp_ctx* cctx) {
     hp_ctx* ctx = const_cast<hp_ctx*>(cctx);

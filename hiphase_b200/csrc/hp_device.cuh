@@ -66,6 +66,7 @@ struct AstarArgs {
     int32_t*  out_status;        // [n_blocks]
     uint64_t* out_heur;          // optional [n_vars + n_blocks]
     uint64_t* out_counters;      // optional [n_blocks * 4]
+    uint64_t* dbg_cycles;        // optional [n_blocks * 4]: cycles in pre-pass, cycles in main loop, pops in each (counting variant)
 };
 
 // Arguments of astar_prep_kernel.

@@ -41,6 +41,9 @@ struct hp_ctx {
     uint64_t launches = 0;
     std::string err;
     // A* workspaces
+    bool want_dbg = false;
+    uint32_t dbg_blocks = 0;
+    hp::DevBuf dbg;
     hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, slabs, stage_in, stage_out;
     // WFA workspaces
     hp::DevBuf wfa_ws, wfa_in, wfa_out;
