@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -47,4 +48,9 @@ struct hp_ctx {
     hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, slabs, stage_in, stage_out;
     // WFA workspaces
     hp::DevBuf wfa_ws, wfa_in, wfa_out;
+    uint32_t wfa_table_cap = 1u << 15;      // (node, diagonal) hash slots per warp; grown 8x on overflow
+    std::vector<int32_t> wfa_h_status;
+    std::vector<uint32_t> wfa_h_score, wfa_h_nodes;
+    std::vector<uint8_t> wfa_h_alleles, wfa_h_quals;
+    std::vector<uint64_t> wfa_h_trav, wfa_h_ctr;
 };

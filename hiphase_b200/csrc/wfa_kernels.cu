@@ -1,17 +1,769 @@
-// wfa_kernels.cu -- graph-WFA realignment kernels (placeholder until K2 lands in this round).
+// wfa_kernels.cu -- graph-WFA realignment on sm_100a: kernel, host-side graph flattening and the C ABI entry points.
+//
+// Replaces (results identical): WFAGraph::from_reference_variants_with_hom (src/wfa_graph.rs:119-284, host side
+// here), WFAGraph::edit_distance_with_pruning (src/wfa_graph.rs:350-650, the kernel) and the traversed-nodes ->
+// allele/qual row glue of global_realignment (src/read_parsing.rs:790-835, kernel epilogue).
+//
+// Kernel design: persistent, ONE WARP PER ALIGNMENT JOB.  The reference keeps, per edit distance,
+// a hash map node -> diagonal -> [(offset, set id)] and reduces every (node, diagonal) to "furthest offset after
+// extension + union of the sets that reach it".  Extension only depends on (node, diagonal, offset), so here a wave
+// is extended when it is PUSHED and immediately reduced into its (node, diagonal) slot of a per-warp open-addressing
+// hash table in HBM/L2: slot = {max-front record, and for each of the two live ED generations: end offset +
+// traversed-node bitset}.  Per ED the warp walks the active nodes in topological order (a 1024-bit node mask lives
+// in registers, one word per lane); lanes = the node's live diagonals.  Pushes are issued in phases
+// (diag-1, diag, diag+1, then one phase per child) so that no two lanes of a phase touch the same slot.
+// Results do not depend on the visiting order of diagonals (everything cross-diagonal is a max or a set union).
+#include <algorithm>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <vector>
+
 #include "hp_host.h"
+
+namespace hp {
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-side graph / job layout
+// ---------------------------------------------------------------------------------------------------------------
+struct WfaNode {
+    uint64_t seq_off;      // offset into the byte pool selected by src
+    uint32_t len;
+    uint32_t src;          // 0 = reference bytes, 1 = variant allele bytes, 2 = explicit sequence pool
+};
+
+struct WfaJob {
+    uint64_t node_base;    // first node in the node array; child_off / amap_off rows start at node_base + job
+    uint64_t read_off;     // into read bytes
+    uint64_t row_off;      // output row start
+    uint32_t n_nodes;
+    uint32_t read_len;
+    uint32_t row_len;
+    uint32_t het_lo;       // first het variant (index into the variant table) of the row
+    int32_t  status;       // pre-set by the host for skipped / invalid jobs, else HP_WFA_OK
+    uint32_t pad;
+};
+
+struct WfaArgs {
+    uint32_t n_jobs;
+    const WfaJob* jobs;
+    const WfaNode* nodes;
+    const uint32_t* child_off;     // CSR rows per job: n_nodes + 1 entries starting at node_base + job index
+    const uint32_t* child_idx;     // job-relative node ids
+    const uint32_t* amap_off;      // same row layout as child_off
+    const uint32_t* amap;          // (het index relative to het_lo) << 1 | allele
+    const uint8_t* reference;
+    const uint8_t* allele_bytes;
+    const uint8_t* seq_pool;
+    const uint8_t* read_bytes;
+    const uint8_t* vtype;          // variant table types (quality table)
+    uint64_t prune_distance;       // UINT64_MAX = disabled
+    uint32_t max_edit_distance;
+    // workspace
+    uint8_t* slabs;
+    uint64_t slab_bytes;
+    uint32_t table_cap;            // hash slots per warp (power of two)
+    uint32_t set_words_max;        // set words the slab layout was sized for
+    uint32_t* ticket;
+    // outputs
+    int32_t*  out_status;
+    uint32_t* out_score;
+    uint8_t*  out_alleles;
+    uint8_t*  out_quals;
+    uint32_t* out_n_nodes;         // optional
+    uint64_t* out_traversed;       // optional
+    uint32_t  trav_words;
+    uint64_t* out_counters;        // optional [n_jobs * 4]
+};
+
+constexpr uint32_t kWfaMaxNodes = 1024;          // node activity mask: one 32-bit word per lane
+constexpr uint32_t kNil = 0xffffffffu;
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr int kWfaWarps = 8;
+
+__host__ __device__ inline uint32_t wfa_slot_stride(uint32_t set_words) { return 32u + 16u * set_words; }
+
+// slab layout: keys[cap] u64 | slots[cap * stride] | items[2][cap] u32 | seg_start[2][1024] | seg_len[2][1024] |
+//              late_head[1024] | chunks[cap/8 * 34] u32 | rowtmp[4096] u32
+__host__ __device__ inline uint64_t wfa_slab_bytes(uint32_t cap, uint32_t set_words) {
+    uint64_t b = (uint64_t)cap * 8 + (uint64_t)cap * wfa_slot_stride(set_words) + 2ull * cap * 4 + 5ull * kWfaMaxNodes * 4 +
+                 (uint64_t)(cap / 8) * 34 * 4 + 4096ull * 4;
+    return (b + 255) & ~255ull;
+}
+
+struct WfaSlab {
+    unsigned long long* keys;
+    uint8_t* slots;
+    uint32_t* items[2];
+    uint32_t* seg_start[2];
+    uint32_t* seg_len[2];
+    uint32_t* late_head;
+    uint32_t* chunks;      // chunk c: [next, count, 32 items]
+    uint32_t* rowtmp;
+};
+
+__device__ __forceinline__ WfaSlab wfa_carve(uint8_t* p, uint32_t cap, uint32_t set_words) {
+    WfaSlab s;
+    s.keys = (unsigned long long*)p; p += (uint64_t)cap * 8;
+    s.slots = p; p += (uint64_t)cap * wfa_slot_stride(set_words);
+    s.items[0] = (uint32_t*)p; p += (uint64_t)cap * 4;
+    s.items[1] = (uint32_t*)p; p += (uint64_t)cap * 4;
+    s.seg_start[0] = (uint32_t*)p; p += kWfaMaxNodes * 4;
+    s.seg_start[1] = (uint32_t*)p; p += kWfaMaxNodes * 4;
+    s.seg_len[0] = (uint32_t*)p; p += kWfaMaxNodes * 4;
+    s.seg_len[1] = (uint32_t*)p; p += kWfaMaxNodes * 4;
+    s.late_head = (uint32_t*)p; p += kWfaMaxNodes * 4;
+    s.chunks = (uint32_t*)p; p += (uint64_t)(cap / 8) * 34 * 4;
+    s.rowtmp = (uint32_t*)p;
+    return s;
+}
+
+// slot fields (byte offsets inside a slot)
+//   0 record u32 | 4 tag[0] u32 | 8 tag[1] u32 | 12 end[0] u32 | 16 end[1] u32 | 20 diag i32 | 24 node u32 | 28 pad
+//   32 set[0][SW] u64 | 32 + 8*SW set[1][SW] u64
+struct SlotRef {
+    uint8_t* p;
+    uint32_t sw;
+    __device__ __forceinline__ uint32_t& record() const { return *(uint32_t*)(p + 0); }
+    __device__ __forceinline__ uint32_t& tag(int g) const { return *(uint32_t*)(p + 4 + 4 * g); }
+    __device__ __forceinline__ uint32_t& end(int g) const { return *(uint32_t*)(p + 12 + 4 * g); }
+    __device__ __forceinline__ int32_t& diag() const { return *(int32_t*)(p + 20); }
+    __device__ __forceinline__ uint32_t& node() const { return *(uint32_t*)(p + 24); }
+    __device__ __forceinline__ uint64_t* set(int g) const { return (uint64_t*)(p + 32 + 8 * sw * g); }
+};
+
+struct WfaCtx {
+    const WfaArgs* a;
+    WfaSlab s;
+    uint32_t lane, cap, sw, stride;
+    const WfaNode* nodes;          // this job's nodes
+    const uint8_t* read;
+    uint32_t read_len;
+    uint32_t used;                 // hash slots in use (warp-uniform)
+    uint32_t n_chunks;             // chunk arena bump pointer (warp-uniform)
+    bool overflow;
+    uint64_t n_cmp, n_waves, n_setops;
+};
+
+__device__ __forceinline__ const uint8_t* node_seq(const WfaArgs& a, const WfaNode& n) {
+    const uint8_t* base = n.src == 0 ? a.reference : (n.src == 1 ? a.allele_bytes : a.seq_pool);
+    return base + n.seq_off;
+}
+
+__device__ __forceinline__ uint64_t wfa_key(uint32_t node, int32_t diag) { return ((uint64_t)node << 32) | (uint32_t)diag; }
+__device__ __forceinline__ uint32_t wfa_hash(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 29;
+    return (uint32_t)k;
+}
+
+// Pushes one wave per participating lane (act) of this warp into generation tag `gen_tag` (parity gp) of slot
+// (node, diag): extend from `offset`, then reduce into the slot (furthest end wins, union of sets on ties).
+// Source set = src_set (sw words) plus optionally bit `add_bit`.  Returns in `first` whether this lane created the
+// slot's data for that generation (it then has to be listed), and the slot index in `slot_out`.
+// All lanes of a call must target distinct (node, diag) pairs.
+__device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int32_t diag, uint32_t offset,
+                                         const uint64_t* src_set, uint32_t add_bit, uint32_t gen_tag, int gp, bool& first,
+                                         uint32_t& slot_out) {
+    first = false; slot_out = kNil;
+    uint32_t n_created = 0;
+    if (act) {
+        // ---- extend (wfa_graph.rs:454-459) ----
+        const WfaNode nd = c.nodes[node];
+        const uint8_t* seq = node_seq(*c.a, nd);
+        uint32_t off = offset;
+        uint32_t pos = (uint32_t)(diag + (int32_t)off);
+        while (off < nd.len && pos < c.read_len) {
+            c.n_cmp++;
+            if (__ldg(seq + off) != __ldg(c.read + pos)) break;
+            off++; pos++;
+        }
+        // ---- find or insert the slot ----
+        const uint64_t key = wfa_key(node, diag);
+        uint32_t h = wfa_hash(key) & (c.cap - 1);
+        uint32_t slot = kNil;
+        bool created = false;
+        for (uint32_t probe = 0; probe < c.cap; probe++) {
+            unsigned long long k = c.s.keys[h];
+            if (k == kEmptyKey) {
+                k = atomicCAS(&c.s.keys[h], kEmptyKey, (unsigned long long)key);
+                if (k == kEmptyKey) { slot = h; created = true; break; }
+            }
+            if (k == key) { slot = h; break; }
+            h = (h + 1) & (c.cap - 1);
+        }
+        if (slot != kNil) {
+            SlotRef sr{c.s.slots + (uint64_t)slot * c.stride, c.sw};
+            if (created) { sr.record() = 0; sr.tag(0) = kNil; sr.tag(1) = kNil; sr.diag() = diag; sr.node() = node; }
+            uint64_t* dst = sr.set(gp);
+            if (sr.tag(gp) != gen_tag) {
+                sr.tag(gp) = gen_tag; sr.end(gp) = off;
+                for (uint32_t w = 0; w < c.sw; w++) dst[w] = src_set[w];
+                if (add_bit != kNil) dst[add_bit >> 6] |= 1ull << (add_bit & 63);
+                first = true;
+            } else if (off > sr.end(gp)) {
+                sr.end(gp) = off;
+                for (uint32_t w = 0; w < c.sw; w++) dst[w] = src_set[w];
+                if (add_bit != kNil) dst[add_bit >> 6] |= 1ull << (add_bit & 63);
+            } else if (off == sr.end(gp)) {
+                for (uint32_t w = 0; w < c.sw; w++) dst[w] |= src_set[w];
+                if (add_bit != kNil) dst[add_bit >> 6] |= 1ull << (add_bit & 63);
+                c.n_setops++;
+            }
+            slot_out = slot;
+        } else {
+            c.overflow = true;
+        }
+        if (created) n_created = 1;
+    }
+    c.used += __popc(__ballot_sync(HP_FULL_MASK, n_created != 0));      // table occupancy (warp-uniform)
+    if (c.used > c.cap / 2) c.overflow = true;
+}
+
+__global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gwarp = blockIdx.x * kWfaWarps + (threadIdx.x >> 5);
+    WfaCtx c;
+    c.a = &a; c.lane = lane; c.cap = a.table_cap;
+    uint8_t* slab = a.slabs + (uint64_t)gwarp * a.slab_bytes;
+
+    for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(a.ticket, 1u);
+        j = __shfl_sync(HP_FULL_MASK, j, 0);
+        if (j >= a.n_jobs) break;
+        const WfaJob job = a.jobs[j];
+        int status = job.status;
+        uint32_t score = 0;
+        c.n_cmp = c.n_waves = c.n_setops = 0;
+        const uint32_t n_nodes = job.n_nodes;
+        const uint32_t sw = (n_nodes + 63) / 64;
+        if (status == HP_WFA_OK && (n_nodes == 0 || n_nodes > kWfaMaxNodes || sw > a.set_words_max)) status = HP_WFA_WORKSPACE_OVERFLOW;
+
+        // output row defaults: NoOverlap / 0 (read_parsing.rs:790, 803)
+        for (uint32_t i = lane; i < job.row_len; i += 32) { a.out_alleles[job.row_off + i] = HP_ALLELE_NOOVERLAP; a.out_quals[job.row_off + i] = 0; }
+        if (a.out_traversed) for (uint32_t i = lane; i < a.trav_words; i += 32) a.out_traversed[(uint64_t)j * a.trav_words + i] = 0;
+
+        if (status == HP_WFA_OK) {
+            c.sw = sw; c.stride = wfa_slot_stride(sw);
+            c.s = wfa_carve(slab, c.cap, sw);
+            c.nodes = a.nodes + job.node_base;
+            c.read = a.read_bytes + job.read_off;
+            c.read_len = job.read_len;
+            c.used = 0; c.n_chunks = 0; c.overflow = false;
+            const uint32_t* child_off = a.child_off + job.node_base + j;
+            const uint32_t sink = n_nodes - 1;
+            const uint32_t max_chunks = c.cap / 8;
+
+            for (uint32_t i = lane; i < c.cap; i += 32) c.s.keys[i] = kEmptyKey;
+            for (uint32_t i = lane; i < n_nodes; i += 32) {
+                c.s.seg_len[0][i] = 0; c.s.seg_len[1][i] = 0; c.s.late_head[i] = kNil;
+            }
+            __syncwarp();
+
+            // node activity masks: lane l owns nodes [32l, 32l+32)
+            uint32_t act_cur = 0, act_next = 0;
+            uint32_t n_items_next = 0;             // items appended to the next generation's list so far (uniform)
+
+            // ---- initial wave: node 0, diagonal 0, offset 0, set {0} (wfa_graph.rs:366-378) ----
+            {
+                uint64_t* seed = (uint64_t*)c.s.rowtmp;       // scratch: an all-zero set
+                for (uint32_t w = lane; w < sw; w += 32) seed[w] = 0;
+                __syncwarp();
+                bool first; uint32_t slot;
+                wfa_push(c, lane == 0, 0u, 0, 0u, seed, 0u, 0u, 0, first, slot);
+                if (lane == 0) { c.s.items[0][0] = slot; c.s.seg_start[0][0] = 0; c.s.seg_len[0][0] = 1; act_cur = 1u; }
+                c.used = 1;
+                __syncwarp();
+            }
+
+            uint32_t ed = 0, farthest = 0, min_prog = 0;
+            bool done = false;
+            while (!done) {
+                const int g = ed & 1, gn = g ^ 1;
+                n_items_next = 0;
+                // ---- nodes with pending waves, ascending (wfa_graph.rs:406) ----
+                for (;;) {
+                    const uint32_t lanes_with = __ballot_sync(HP_FULL_MASK, act_cur != 0);
+                    if (lanes_with == 0) break;
+                    const uint32_t wl = __ffs(lanes_with) - 1;
+                    const uint32_t word = __shfl_sync(HP_FULL_MASK, act_cur, wl);
+                    const uint32_t n = wl * 32 + (__ffs(word) - 1);
+                    if (lane == wl) act_cur &= act_cur - 1;                 // clear the lowest set bit
+
+                    const WfaNode nd = c.nodes[n];
+                    const uint32_t node_len = nd.len;
+                    const uint32_t c0 = child_off[n], c1 = child_off[n + 1];
+                    const uint32_t own_start = c.s.seg_start[g][n], own_len = c.s.seg_len[g][n];
+                    uint32_t late = c.s.late_head[n];
+                    const uint32_t next_seg_start = n_items_next;
+                    __syncwarp();
+                    if (lane == 0) { c.s.seg_len[g][n] = 0; c.s.late_head[n] = kNil; c.s.seg_start[gn][n] = next_seg_start; }
+
+                    // batches of up to 32 (node, diagonal) slots: first the node's own segment, then the late chunks
+                    uint32_t own_done = 0;
+                    for (;;) {
+                        uint32_t item = kNil;
+                        if (own_done < own_len) {
+                            if (own_done + lane < own_len) item = c.s.items[g][own_start + own_done + lane];
+                            own_done += 32;
+                        } else if (late != kNil) {
+                            const uint32_t* ch = c.s.chunks + (uint64_t)late * 34;
+                            const uint32_t cnt = ch[1];
+                            if (lane < cnt) item = ch[2 + lane];
+                            late = ch[0];
+                        } else break;
+
+                        // ---- per-slot step (wfa_graph.rs:443-573) ----
+                        const bool act = item != kNil;
+                        SlotRef sr{c.s.slots + (uint64_t)(act ? item : 0) * c.stride, sw};
+                        int32_t d = 0; uint32_t e = 0;
+                        bool alive = false;
+                        if (act) {
+                            d = sr.diag(); e = sr.end(g);
+                            c.n_waves++;
+                            const uint32_t rec = sr.record();
+                            const bool skip = e < rec || (int64_t)d + (int64_t)e < (int64_t)min_prog;     // :464-469
+                            if (!skip) { sr.record() = e; alive = true; }
+                        }
+                        const uint32_t prog = alive ? (uint32_t)(d + (int32_t)e) : 0u;
+                        farthest = max(farthest, __reduce_max_sync(HP_FULL_MASK, prog));                   // :474
+                        const bool at_end = (e == node_len);
+                        const bool read_left = act && (uint32_t)(d + (int32_t)e) < c.read_len;
+
+                        // finished?  any wave of the sink at (end of node, end of read), skipped or not (:576-629)
+                        if (n == sink) {
+                            const uint32_t fin = __ballot_sync(HP_FULL_MASK, act && at_end && (uint32_t)(d + (int32_t)e) == c.read_len);
+                            if (fin) {
+                                const uint32_t fl = __ffs(fin) - 1;
+                                const uint32_t fitem = __shfl_sync(HP_FULL_MASK, item, fl);
+                                const uint64_t* fs = SlotRef{c.s.slots + (uint64_t)fitem * c.stride, sw}.set(g);
+                                // ---- epilogue: traversed nodes -> allele / qual row (read_parsing.rs:790-835) ----
+                                for (uint32_t i = lane; i < job.row_len; i += 32) c.s.rowtmp[i] = 0;
+                                __syncwarp();
+                                const uint32_t* amap_off = a.amap_off + job.node_base + j;
+                                for (uint32_t nn = lane; nn < n_nodes; nn += 32) {
+                                    if ((fs[nn >> 6] >> (nn & 63)) & 1ull) {
+                                        for (uint32_t q = amap_off[nn]; q < amap_off[nn + 1]; q++) {
+                                            const uint32_t m = a.amap[q];
+                                            atomicOr(&c.s.rowtmp[m >> 1], 1u << (m & 1u));
+                                        }
+                                    }
+                                }
+                                __syncwarp();
+                                for (uint32_t i = lane; i < job.row_len; i += 32) {
+                                    const uint32_t seen = c.s.rowtmp[i];
+                                    uint8_t al = HP_ALLELE_NOOVERLAP, ql = 0;
+                                    if (seen == 3u) al = HP_ALLELE_AMBIGUOUS;
+                                    else if (seen) {
+                                        al = (uint8_t)(seen - 1u);
+                                        const uint8_t vt = a.vtype[job.het_lo + i];
+                                        // doubled global-realignment qualities (read_parsing.rs:18-22, 815-835)
+                                        ql = vt == HP_VT_SNV ? 160 : (vt == HP_VT_TANDEM_REPEAT ? 80 :
+                                             ((vt == HP_VT_SV_DELETION || vt == HP_VT_SV_INSERTION) ? 40 :
+                                             ((vt == HP_VT_DELETION || vt == HP_VT_INSERTION || vt == HP_VT_INDEL) ? 20 : 0)));
+                                    }
+                                    a.out_alleles[job.row_off + i] = al; a.out_quals[job.row_off + i] = ql;
+                                }
+                                if (a.out_traversed)
+                                    for (uint32_t w = lane; w < min(sw, a.trav_words); w += 32) a.out_traversed[(uint64_t)j * a.trav_words + w] = fs[w];
+                                score = ed; done = true;
+                            }
+                        }
+                        if (done) break;
+
+                        const uint64_t* myset = sr.set(g);
+                        // ---- pushes into the NEXT edit distance (same node) ----
+                        const uint32_t tag_next = ed + 1;
+                        const bool inside = alive && !at_end;
+                        const bool sink_more = alive && at_end && n == sink && read_left;
+#pragma unroll 1
+                        for (int phase = 0; phase < 3; phase++) {
+                            bool pa; int32_t pd; uint32_t po;
+                            if (phase == 0) { pa = inside; pd = d - 1; po = e + 1; }                       // graph advances
+                            else if (phase == 1) { pa = inside && read_left; pd = d; po = e + 1; }         // mismatch
+                            else { pa = (inside && read_left) || sink_more; pd = d + 1; po = e; }          // read advances
+                            if (!__any_sync(HP_FULL_MASK, pa)) continue;
+                            bool first; uint32_t slot;
+                            wfa_push(c, pa, n, pd, po, myset, kNil, tag_next, gn, first, slot);
+                            const uint32_t fm = __ballot_sync(HP_FULL_MASK, first);
+                            if (fm) {
+                                const uint32_t pos = n_items_next + __popc(fm & ((1u << lane) - 1u));
+                                if (first && pos < c.cap) c.s.items[gn][pos] = slot;
+                                n_items_next += __popc(fm);
+                                if (lane == (n >> 5)) act_next |= 1u << (n & 31);
+                            }
+                            __syncwarp();
+                        }
+                        // ---- propagation to the children within THIS edit distance (:527-553) ----
+                        const bool prop = alive && at_end && n != sink;
+                        if (__any_sync(HP_FULL_MASK, prop)) {
+                            for (uint32_t q = c0; q < c1; q++) {
+                                const uint32_t child = a.child_idx[q];
+                                bool first; uint32_t slot;
+                                wfa_push(c, prop, child, d + (int32_t)e, 0u, myset, child, ed, g, first, slot);
+                                const uint32_t fm = __ballot_sync(HP_FULL_MASK, first);
+                                if (fm) {
+                                    const uint32_t chunk = c.n_chunks++;
+                                    if (chunk < max_chunks) {
+                                        uint32_t* ch = c.s.chunks + (uint64_t)chunk * 34;
+                                        if (first) ch[2 + __popc(fm & ((1u << lane) - 1u))] = slot;
+                                        if (lane == 0) { ch[0] = c.s.late_head[child]; ch[1] = __popc(fm); c.s.late_head[child] = chunk; }
+                                    } else c.overflow = true;
+                                    if (lane == (child >> 5)) act_cur |= 1u << (child & 31);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        c.overflow = __any_sync(HP_FULL_MASK, c.overflow);
+                        if (c.overflow) break;
+                    }
+                    if (done || c.overflow) break;
+                    if (lane == 0) c.s.seg_len[gn][n] = n_items_next - next_seg_start;
+                    __syncwarp();
+                }
+                if (done) break;
+                if (c.overflow) { status = HP_WFA_WORKSPACE_OVERFLOW; break; }
+                // ---- next edit distance (:633-648) ----
+                ed++;
+                act_cur = act_next; act_next = 0;
+                c.n_chunks = 0;
+                if ((uint64_t)farthest > a.prune_distance) min_prog = farthest - (uint32_t)a.prune_distance;
+                if (ed > a.max_edit_distance) { status = HP_WFA_MAX_EDIT_DISTANCE; score = a.max_edit_distance; break; }
+                if (__ballot_sync(HP_FULL_MASK, act_cur != 0) == 0) { status = HP_WFA_WORKSPACE_OVERFLOW; break; }   // cannot happen
+            }
+        }
+        if (lane == 0) {
+            a.out_status[j] = status;
+            a.out_score[j] = (status == HP_WFA_SKIPPED) ? 0xffffffffu : score;
+            if (a.out_n_nodes) a.out_n_nodes[j] = n_nodes;
+        }
+        if (a.out_counters) {
+            const uint64_t cmp = __reduce_add_sync(HP_FULL_MASK, (uint32_t)c.n_cmp);
+            const uint64_t wv = __reduce_add_sync(HP_FULL_MASK, (uint32_t)c.n_waves);
+            const uint64_t so = __reduce_add_sync(HP_FULL_MASK, (uint32_t)c.n_setops);
+            if (lane == 0) {
+                uint64_t* o = a.out_counters + (uint64_t)j * 4;
+                o[0] = cmp; o[1] = wv; o[2] = so; o[3] = n_nodes;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: graph flattening (from_reference_variants_with_hom) and the API
+// ---------------------------------------------------------------------------------------------------------------
+struct FlatGraphs {
+    std::vector<WfaJob> jobs;
+    std::vector<WfaNode> nodes;
+    std::vector<uint32_t> child_off, child_idx, amap_off, amap;
+};
+
+// Builds the graph of one job into fg.  Node order, edges and allele map follow wfa_graph.rs:119-284:
+// variants by position (hets before homs on ties), ALT node(s) before the reference node of the same locus,
+// allele0 shares the next backbone node unless it is itself an ALT (index_allele0 != 0), reconnects at pos+ref_len.
+static bool build_job_graph(const hp_wfa_batch* b, uint32_t j, FlatGraphs& fg, WfaJob& job) {
+    const hp_variant_table& vt = b->variants;
+    const uint64_t w0 = b->ref_start[j], w1 = b->ref_end[j];
+    if (w1 > b->n_reference || w0 > w1) return false;
+    struct Item { uint32_t k; int32_t het; };
+    std::vector<Item> order;
+    for (uint32_t k = b->het_lo[j]; k < b->het_hi[j]; k++) order.push_back({k, (int32_t)(k - b->het_lo[j])});
+    for (uint32_t k = b->hom_lo[j]; k < b->hom_hi[j]; k++) order.push_back({k, -1});
+    std::stable_sort(order.begin(), order.end(), [&](const Item& x, const Item& y) { return vt.position[x.k] < vt.position[y.k]; });
+
+    struct TmpNode { WfaNode n; std::vector<uint32_t> parents; std::vector<uint32_t> alleles; };
+    std::vector<TmpNode> tn;
+    auto add = [&](uint32_t src, uint64_t off, uint32_t len, const std::vector<uint32_t>& parents) -> uint32_t {
+        TmpNode t; t.n.seq_off = off; t.n.len = len; t.n.src = src; t.parents = parents;
+        tn.push_back(std::move(t));
+        return (uint32_t)tn.size() - 1;
+    };
+    uint64_t cursor = w0;                                   // reference consumed so far
+    std::vector<uint32_t> attach;                           // parents of the next backbone node
+    std::vector<uint32_t> ref_alleles;                      // allele-0 tags waiting for the next backbone node
+    using Rejoin = std::pair<uint64_t, uint32_t>;           // (rejoin position, ALT node)
+    std::priority_queue<Rejoin, std::vector<Rejoin>, std::greater<Rejoin>> rejoin;
+    bool ok = true;
+    auto backbone_to = [&](uint64_t upto) -> uint32_t {     // emits reference[cursor, upto) as a backbone node
+        const uint32_t id = add(0, cursor, (uint32_t)(upto - cursor), attach);
+        if (!ref_alleles.empty()) { tn[id].alleles = ref_alleles; ref_alleles.clear(); }
+        cursor = upto;
+        return id;
+    };
+    auto drain_rejoins = [&](uint64_t limit) {              // all ALT nodes rejoining at positions <= limit
+        while (ok && !rejoin.empty() && rejoin.top().first <= limit) {
+            const uint64_t at = rejoin.top().first;
+            if (!(at > cursor)) { ok = false; return; }
+            const uint32_t backbone = backbone_to(at);
+            attach.assign(1, backbone);
+            while (!rejoin.empty() && rejoin.top().first == at) { attach.push_back(rejoin.top().second); rejoin.pop(); }
+        }
+    };
+    for (const Item& it : order) {
+        const uint32_t k = it.k;
+        if (vt.ignored[k] || vt.position[k] < 0) continue;
+        const uint64_t pos = (uint64_t)vt.position[k], rl = vt.ref_len[k];
+        if (pos < w0 || pos + rl > w1) continue;
+        drain_rejoins(pos);
+        if (!ok) return false;
+        if (cursor < pos || tn.empty()) {
+            const uint32_t backbone = backbone_to(pos);
+            attach.assign(1, backbone);
+        } else if (cursor != pos) return false;
+        if (vt.index_allele0[k] != 0) {                     // allele0 is an ALT of a multi-allelic site
+            const uint32_t alt = add(1, vt.allele0_off[k], vt.allele0_len[k], attach);
+            if (it.het >= 0) tn[alt].alleles.push_back(((uint32_t)it.het << 1) | 0u);
+            rejoin.push({pos + rl, alt});
+        } else if (it.het >= 0) ref_alleles.push_back(((uint32_t)it.het << 1) | 0u);
+        const uint32_t alt = add(1, vt.allele1_off[k], vt.allele1_len[k], attach);
+        if (it.het >= 0) tn[alt].alleles.push_back(((uint32_t)it.het << 1) | 1u);
+        rejoin.push({pos + rl, alt});
+    }
+    drain_rejoins(UINT64_MAX);
+    if (!ok || cursor > w1) return false;
+    backbone_to(w1);
+    if (!ref_alleles.empty()) return false;
+
+    // flatten: children CSR from the parent lists
+    const uint32_t n = (uint32_t)tn.size();
+    job.node_base = fg.nodes.size();
+    job.n_nodes = n;
+    std::vector<uint32_t> deg(n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) for (uint32_t p : tn[i].parents) deg[p + 1]++;
+    for (uint32_t i = 0; i < n; i++) deg[i + 1] += deg[i];
+    const size_t cbase = fg.child_idx.size();
+    fg.child_idx.resize(cbase + deg[n]);
+    std::vector<uint32_t> fill(deg.begin(), deg.end() - 1);
+    for (uint32_t i = 0; i < n; i++) for (uint32_t p : tn[i].parents) fg.child_idx[cbase + fill[p]++] = i;
+    for (uint32_t i = 0; i <= n; i++) fg.child_off.push_back((uint32_t)(cbase + deg[i]));
+    for (uint32_t i = 0; i < n; i++) {
+        fg.nodes.push_back(tn[i].n);
+        fg.amap_off.push_back((uint32_t)fg.amap.size());
+        for (uint32_t m : tn[i].alleles) fg.amap.push_back(m);
+    }
+    fg.amap_off.push_back((uint32_t)fg.amap.size());
+    return true;
+}
+
+static int wfa_fail(hp_ctx* ctx, int code, const std::string& msg) { if (ctx) ctx->err = msg; return code; }
+
+#define WFA_CUDA(ctx, call)                                                                                          \
+    do {                                                                                                             \
+        cudaError_t e_ = (call);                                                                                     \
+        if (e_ != cudaSuccess) { cudaGetLastError(); return wfa_fail(ctx, HP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+    } while (0)
+
+struct WfaHostInputs {
+    const uint8_t* reference; uint64_t n_reference;
+    const uint8_t* allele_bytes; uint64_t n_allele_bytes;
+    const uint8_t* seq_pool; uint64_t n_seq_pool;
+    const uint8_t* read_bytes; uint64_t n_read_bytes;
+    const uint8_t* vtype; uint64_t n_vtype;
+};
+
+// Uploads the flattened graphs + byte pools, runs the kernel, downloads the outputs.  `sel` (optional) restricts the
+// run to a subset of jobs (retry path); outputs are written at the original job indices.
+static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, uint64_t prune, uint32_t max_ed,
+                   uint64_t n_rows, hp_wfa_out* out, uint32_t table_cap, int max_ctas) {
+    const uint32_t nj = (uint32_t)fg.jobs.size();
+    if (nj == 0) return HP_OK;
+    cudaStream_t st = ctx->stream;
+    uint32_t max_nodes = 1;
+    for (const WfaJob& j : fg.jobs) if (j.status == HP_WFA_OK) max_nodes = std::max(max_nodes, std::min(j.n_nodes, kWfaMaxNodes));
+    const uint32_t sw_max = (max_nodes + 63) / 64;
+
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t in_bytes = al(sizeof(WfaJob) * nj) + al(sizeof(WfaNode) * fg.nodes.size()) + al(4 * fg.child_off.size()) +
+                            al(4 * fg.child_idx.size()) + al(4 * fg.amap_off.size()) + al(4 * fg.amap.size()) + al(in.n_reference) +
+                            al(in.n_allele_bytes) + al(in.n_seq_pool) + al(in.n_read_bytes) + al(in.n_vtype) + 4096;
+    if (!ctx->wfa_in.reserve(in_bytes)) return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA input staging allocation failed");
+    uint8_t* p = (uint8_t*)ctx->wfa_in.ptr;
+    auto up = [&](const void* src, size_t bytes) -> uint8_t* {
+        uint8_t* dst = p; p += al(bytes);
+        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+        return dst;
+    };
+    WfaArgs a;
+    a.n_jobs = nj;
+    a.jobs = (const WfaJob*)up(fg.jobs.data(), sizeof(WfaJob) * nj);
+    a.nodes = (const WfaNode*)up(fg.nodes.data(), sizeof(WfaNode) * fg.nodes.size());
+    a.child_off = (const uint32_t*)up(fg.child_off.data(), 4 * fg.child_off.size());
+    a.child_idx = (const uint32_t*)up(fg.child_idx.data(), 4 * fg.child_idx.size());
+    a.amap_off = (const uint32_t*)up(fg.amap_off.data(), 4 * fg.amap_off.size());
+    a.amap = (const uint32_t*)up(fg.amap.data(), 4 * fg.amap.size());
+    a.reference = up(in.reference, in.n_reference);
+    a.allele_bytes = up(in.allele_bytes, in.n_allele_bytes);
+    a.seq_pool = up(in.seq_pool, in.n_seq_pool);
+    a.read_bytes = up(in.read_bytes, in.n_read_bytes);
+    a.vtype = up(in.vtype, in.n_vtype);
+    a.prune_distance = prune; a.max_edit_distance = max_ed;
+
+    int n_ctas = std::min<int>((nj + kWfaWarps - 1) / kWfaWarps, ctx->sm_count * 2);
+    if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
+    a.table_cap = table_cap; a.set_words_max = sw_max;
+    a.slab_bytes = wfa_slab_bytes(table_cap, sw_max);
+    if (!ctx->wfa_ws.reserve(a.slab_bytes * (uint64_t)n_ctas * kWfaWarps + 256))
+        return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA workspace allocation failed");
+    a.slabs = (uint8_t*)ctx->wfa_ws.ptr + 256;
+    a.ticket = (uint32_t*)ctx->wfa_ws.ptr;
+    WFA_CUDA(ctx, cudaMemsetAsync(a.ticket, 0, 256, st));
+
+    const uint32_t tw = out->traversed ? out->trav_words : 0;
+    const size_t out_bytes = al(4ull * nj) * 3 + al(n_rows) * 2 + al(8ull * nj * tw) + al(32ull * nj) + 4096;
+    if (!ctx->wfa_out.reserve(out_bytes)) return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA output staging allocation failed");
+    uint8_t* q = (uint8_t*)ctx->wfa_out.ptr;
+    auto carve = [&](size_t bytes) { uint8_t* r = q; q += al(bytes); return r; };
+    a.out_status = (int32_t*)carve(4ull * nj); a.out_score = (uint32_t*)carve(4ull * nj);
+    a.out_n_nodes = (uint32_t*)carve(4ull * nj);
+    a.out_alleles = carve(n_rows); a.out_quals = carve(n_rows);
+    a.out_traversed = tw ? (uint64_t*)carve(8ull * nj * tw) : nullptr; a.trav_words = tw;
+    a.out_counters = out->counters ? (uint64_t*)carve(32ull * nj) : nullptr;
+
+    WFA_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    wfa_align_kernel<<<n_ctas, kWfaWarps * 32, 0, st>>>(a);
+    WFA_CUDA(ctx, cudaGetLastError());
+    WFA_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->launches++; ctx->timing_pending = true;
+
+    // download into temporaries, then scatter (the caller's arrays may be indexed by original job ids)
+    ctx->wfa_h_status.resize(nj); ctx->wfa_h_score.resize(nj); ctx->wfa_h_nodes.resize(nj);
+    ctx->wfa_h_alleles.resize(n_rows); ctx->wfa_h_quals.resize(n_rows);
+    ctx->wfa_h_trav.resize((size_t)nj * tw); ctx->wfa_h_ctr.resize(out->counters ? (size_t)nj * 4 : 0);
+    WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_status.data(), a.out_status, 4ull * nj, cudaMemcpyDeviceToHost, st));
+    WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_score.data(), a.out_score, 4ull * nj, cudaMemcpyDeviceToHost, st));
+    WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_nodes.data(), a.out_n_nodes, 4ull * nj, cudaMemcpyDeviceToHost, st));
+    if (n_rows) {
+        WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_alleles.data(), a.out_alleles, n_rows, cudaMemcpyDeviceToHost, st));
+        WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_quals.data(), a.out_quals, n_rows, cudaMemcpyDeviceToHost, st));
+    }
+    if (tw) WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_trav.data(), a.out_traversed, 8ull * nj * tw, cudaMemcpyDeviceToHost, st));
+    if (out->counters) WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_ctr.data(), a.out_counters, 32ull * nj, cudaMemcpyDeviceToHost, st));
+    WFA_CUDA(ctx, cudaStreamSynchronize(st));
+    return HP_OK;
+}
+
+// scatter results of a run over jobs `ids` (original job indices; rows at the original row offsets)
+static void wfa_scatter(hp_ctx* ctx, const FlatGraphs& fg, const std::vector<uint32_t>& ids, const uint64_t* orig_row_off,
+                        hp_wfa_out* out) {
+    const uint32_t tw = out->traversed ? out->trav_words : 0;
+    for (size_t k = 0; k < ids.size(); k++) {
+        const uint32_t j = ids[k];
+        out->status[j] = ctx->wfa_h_status[k];
+        out->score[j] = ctx->wfa_h_score[k];
+        if (out->n_nodes) out->n_nodes[j] = ctx->wfa_h_nodes[k];
+        const WfaJob& job = fg.jobs[k];
+        if (job.row_len) {
+            memcpy(out->alleles + orig_row_off[j], ctx->wfa_h_alleles.data() + job.row_off, job.row_len);
+            memcpy(out->quals + orig_row_off[j], ctx->wfa_h_quals.data() + job.row_off, job.row_len);
+        }
+        if (tw) memcpy(out->traversed + (size_t)j * tw, ctx->wfa_h_trav.data() + k * tw, 8ull * tw);
+        if (out->counters) memcpy(&out->counters[j], ctx->wfa_h_ctr.data() + k * 4, 32);
+    }
+}
+
+}  // namespace hp
+
+using namespace hp;
 
 extern "C" {
 
-int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch*, hp_wfa_out*) {
-    if (ctx) ctx->err = "hp_wfa_align_batch: not built yet";
-    return HP_ERR_INTERNAL;
+int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
+    if (!ctx || !b || !out || !out->status || !out->score || !out->alleles || !out->quals) return HP_ERR_INVALID_INPUT;
+    if (b->n_jobs == 0) return HP_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return wfa_fail(ctx, HP_ERR_CUDA, "cudaSetDevice failed");
+    const hp_variant_table& vt = b->variants;
+    for (uint32_t j = 0; j < b->n_jobs; j++) {
+        if (b->het_hi[j] < b->het_lo[j] || b->hom_hi[j] < b->hom_lo[j] || b->het_hi[j] > vt.n_variants || b->hom_hi[j] > vt.n_variants ||
+            b->read_off[j + 1] < b->read_off[j] || b->row_off[j + 1] - b->row_off[j] != (uint64_t)(b->het_hi[j] - b->het_lo[j]))
+            return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "malformed WFA job " + std::to_string(j));
+    }
+    const uint64_t prune = ctx->params.wfa_prune_distance == 0 ? UINT64_MAX : ctx->params.wfa_prune_distance;   // cli.rs:352-354
+    WfaHostInputs in{b->reference, b->n_reference, vt.allele_bytes, vt.n_allele_bytes, nullptr, 0, b->read_bytes,
+                     b->read_off[b->n_jobs], vt.vtype, vt.n_variants};
+
+    std::vector<uint32_t> ids(b->n_jobs);
+    for (uint32_t j = 0; j < b->n_jobs; j++) ids[j] = j;
+    uint32_t cap = ctx->wfa_table_cap;
+    for (int attempt = 0; attempt < 4 && !ids.empty(); attempt++) {
+        FlatGraphs fg;
+        fg.jobs.reserve(ids.size());
+        uint64_t rows = 0;
+        for (uint32_t j : ids) {
+            WfaJob job{};
+            job.read_off = b->read_off[j]; job.read_len = (uint32_t)(b->read_off[j + 1] - b->read_off[j]);
+            job.row_off = rows; job.row_len = b->het_hi[j] - b->het_lo[j]; job.het_lo = b->het_lo[j];
+            rows += job.row_len;
+            job.status = HP_WFA_OK;
+            if (job.row_len == 0) { job.status = HP_WFA_SKIPPED; job.node_base = fg.nodes.size(); job.n_nodes = 0; }   // read_parsing.rs:703-712
+            else if (!build_job_graph(b, j, fg, job)) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "graph construction failed for job " + std::to_string(j) + " (the reference unwrap()s this, read_parsing.rs:777)");
+            if (job.status != HP_WFA_OK) {            // keep the CSR row layout: one (empty) row per job
+                fg.child_off.push_back((uint32_t)fg.child_idx.size());
+                fg.amap_off.push_back((uint32_t)fg.amap.size());
+            }
+            fg.jobs.push_back(job);
+        }
+        // slabs: full occupancy on the first attempt, fewer and larger afterwards
+        int max_ctas = 0;
+        if (attempt > 0) max_ctas = std::max(1, (int)((8ull << 30) / (wfa_slab_bytes(cap, 16) * kWfaWarps)));
+        int rc = wfa_run(ctx, fg, in, prune, ctx->params.wfa_max_edit_distance, rows, out, cap, max_ctas);
+        if (rc != HP_OK) return rc;
+        wfa_scatter(ctx, fg, ids, b->row_off, out);
+        std::vector<uint32_t> redo;
+        for (uint32_t j : ids) if (out->status[j] == HP_WFA_WORKSPACE_OVERFLOW) redo.push_back(j);
+        ids.swap(redo);
+        cap = std::min<uint32_t>(cap * 8, 1u << 24);
+    }
+    return HP_OK;
 }
 
-int hp_wfa_graph_align(hp_ctx* ctx, uint32_t, const uint8_t*, const uint64_t*, const uint32_t*, const uint64_t*,
-                       const uint8_t*, uint64_t, uint64_t, uint32_t, int32_t*, uint32_t*, uint64_t*) {
-    if (ctx) ctx->err = "hp_wfa_graph_align: not built yet";
-    return HP_ERR_INTERNAL;
+int hp_wfa_graph_align(hp_ctx* ctx, uint32_t n_nodes, const uint8_t* seq, const uint64_t* seq_off, const uint32_t* parent_idx,
+                       const uint64_t* parent_off, const uint8_t* read, uint64_t read_len, uint64_t prune_distance,
+                       uint32_t max_edit_distance, int32_t* status, uint32_t* score, uint64_t* traversed) {
+    if (!ctx || !seq_off || !parent_off || !status || !score) return HP_ERR_INVALID_INPUT;
+    if (n_nodes == 0) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "empty graph");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return wfa_fail(ctx, HP_ERR_CUDA, "cudaSetDevice failed");
+    // add_node rules (wfa_graph.rs:298-331): root has no parents, every other node has >= 1, all parents precede
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        const uint64_t np = parent_off[i + 1] - parent_off[i];
+        if ((i == 0) != (np == 0)) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "node parent rule violated (wfa_graph.rs:302-311)");
+        for (uint64_t q = parent_off[i]; q < parent_off[i + 1]; q++)
+            if (parent_idx[q] >= i) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "parents must precede their node (wfa_graph.rs:313-317)");
+    }
+    FlatGraphs fg;
+    WfaJob job{};
+    job.node_base = 0; job.n_nodes = n_nodes; job.read_off = 0; job.read_len = (uint32_t)read_len; job.row_off = 0; job.row_len = 0;
+    job.status = HP_WFA_OK;
+    std::vector<uint32_t> deg(n_nodes + 1, 0);
+    for (uint32_t i = 0; i < n_nodes; i++) for (uint64_t q = parent_off[i]; q < parent_off[i + 1]; q++) deg[parent_idx[q] + 1]++;
+    for (uint32_t i = 0; i < n_nodes; i++) deg[i + 1] += deg[i];
+    fg.child_idx.resize(deg[n_nodes]);
+    std::vector<uint32_t> fill(deg.begin(), deg.end() - 1);
+    for (uint32_t i = 0; i < n_nodes; i++) for (uint64_t q = parent_off[i]; q < parent_off[i + 1]; q++) fg.child_idx[fill[parent_idx[q]]++] = i;
+    for (uint32_t i = 0; i <= n_nodes; i++) { fg.child_off.push_back(deg[i]); fg.amap_off.push_back(0); }
+    for (uint32_t i = 0; i < n_nodes; i++) fg.nodes.push_back(WfaNode{seq_off[i], (uint32_t)(seq_off[i + 1] - seq_off[i]), 2u});
+    fg.jobs.push_back(job);
+    WfaHostInputs in{nullptr, 0, nullptr, 0, seq, seq_off[n_nodes], read, read_len, nullptr, 0};
+    const uint32_t tw = (n_nodes + 63) / 64;
+    hp_wfa_out o{};
+    int32_t st = -1; uint32_t sc = 0;
+    std::vector<uint64_t> trav(tw, 0);
+    uint8_t dummy = 0;
+    o.status = &st; o.score = &sc; o.alleles = &dummy; o.quals = &dummy; o.traversed = trav.data(); o.trav_words = tw;
+    uint32_t cap = ctx->wfa_table_cap;
+    std::vector<uint32_t> ids{0};
+    uint64_t row0[2] = {0, 0};
+    for (int attempt = 0; attempt < 4; attempt++) {
+        int rc = wfa_run(ctx, fg, in, prune_distance, max_edit_distance, 0, &o, cap, attempt ? 1 : 0);
+        if (rc != HP_OK) return rc;
+        wfa_scatter(ctx, fg, ids, row0, &o);
+        if (st != HP_WFA_WORKSPACE_OVERFLOW) break;
+        cap = std::min<uint32_t>(cap * 8, 1u << 24);
+    }
+    if (st == HP_WFA_WORKSPACE_OVERFLOW) return wfa_fail(ctx, HP_ERR_UNSUPPORTED, "graph too large for the WFA workspace (more than 1024 nodes or wave table overflow)");
+    *status = st; *score = sc;
+    if (traversed) memcpy(traversed, trav.data(), 8ull * tw);
+    return HP_OK;
 }
 
-}
+}  // extern "C"

@@ -55,7 +55,7 @@ def lib():
         L.hp_last_kernel_ms.argtypes = [C.c_void_p]
         L.hp_wfa_align_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_wfa_batch), C.POINTER(A.hp_wfa_out)]
         L.hp_wfa_graph_align.argtypes = [C.c_void_p, C.c_uint32, A.u8p, A.u64p, A.u32p, A.u64p, A.u8p, C.c_uint64,
-                                         C.c_uint64, C.c_uint32, A.i32p, A.u32p, A.u64p]
+                                         C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), A.u64p]
         _LIB = L
     return _LIB
 
@@ -102,6 +102,31 @@ class Context:
         bs, os_ = batch.as_struct(), out.as_struct()
         self.check(lib().hp_astar_solve_batch(self._h, C.byref(bs), C.byref(os_)))
         return out
+
+    # ---- graph-WFA ----
+    def wfa_align_batch(self, batch, trav_words=0, want_counters=False):
+        """Host buffers in / out: graph construction + alignment + allele/qual rows.  Returns a WfaOut."""
+        out = A.WfaOut(batch, trav_words, want_counters)
+        bs, os_ = batch.as_struct(), out.as_struct()
+        self.check(lib().hp_wfa_align_batch(self._h, C.byref(bs), C.byref(os_)))
+        return out
+
+    def wfa_graph_align(self, seq, seq_off, parent_idx, parent_off, read, prune_distance=None, max_edit_distance=1000):
+        """Pre-built graph (WFAGraph::add_node order) vs one read -> (status, score, sorted traversed node ids)."""
+        import numpy as np
+        seq = np.ascontiguousarray(seq, np.uint8); seq_off = np.ascontiguousarray(seq_off, np.uint64)
+        parent_idx = np.ascontiguousarray(parent_idx, np.uint32); parent_off = np.ascontiguousarray(parent_off, np.uint64)
+        read = np.ascontiguousarray(read, np.uint8)
+        n = len(seq_off) - 1
+        trav = np.zeros((n + 63) // 64, np.uint64)
+        st, sc = C.c_int32(-1), C.c_uint32(0)
+        self.check(lib().hp_wfa_graph_align(self._h, n, A.ptr(seq, A.u8p) if len(seq) else A.u8p(), A.ptr(seq_off, A.u64p),
+                                            A.ptr(parent_idx, A.u32p) if len(parent_idx) else A.u32p(), A.ptr(parent_off, A.u64p),
+                                            A.ptr(read, A.u8p) if len(read) else A.u8p(), len(read),
+                                            (1 << 64) - 1 if prune_distance is None else prune_distance, max_edit_distance,
+                                            C.byref(st), C.byref(sc), A.ptr(trav, A.u64p)))
+        nodes = [i for i in range(n) if (int(trav[i // 64]) >> (i % 64)) & 1]
+        return st.value, sc.value, nodes
 
     def astar_solve_device(self, dev_batch_struct, n_vars, n_reads, n_cells, max_block_vars, dev_out_struct, stream):
         self.check(lib().hp_astar_solve_device(self._h, C.byref(dev_batch_struct), n_vars, n_reads, n_cells,

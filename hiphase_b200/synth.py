@@ -147,3 +147,178 @@ def brute_force_mec(block):
         tot += np.minimum(sc[:, None], sc[None, :])
     best = int(tot.min())
     return best
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C4: WFA-heavy workload (graph realignment jobs), SURVEY.md section 8d
+# ---------------------------------------------------------------------------------------------------------------
+_VT_SNV, _VT_INS, _VT_DEL, _VT_INDEL, _VT_SVINS, _VT_SVDEL, _VT_TR = 0, 1, 2, 3, 4, 5, 9
+_BASES = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _rand_seq(rng, n):
+    return _BASES[rng.integers(0, 4, n)]
+
+
+def gen_wfa_block(rng, window=75000, n_het=60, n_hom=90, n_reads=150, read_lo=10000, read_hi=20000,
+                  err=0.002, p_noisy=0.03, err_noisy=0.05, sv_max=2000):
+    """One block: reference window, het/hom variants (truncated alleles), reads sampled from the two haplotypes.
+    Returns dict(reference, hets=[...], homs=[...], jobs=[(ref_start, ref_end, het_lo, het_hi, hom_lo, hom_hi, read)])."""
+    ref = _rand_seq(rng, window)
+    nv = n_het + n_hom
+    pos = np.sort(rng.choice(np.arange(50, window - sv_max - 300), nv, replace=False))
+    is_het = np.zeros(nv, bool)
+    is_het[rng.choice(nv, n_het, replace=False)] = True
+    variants = []
+    for i in range(nv):
+        p = int(pos[i])
+        u = rng.random()
+        if u < 0.5:
+            rl = 1
+            alt = _BASES[(int(np.searchsorted(_BASES, ref[p])) + int(rng.integers(1, 4))) % 4: ][:1]
+            v = dict(vtype=_VT_SNV, ref_len=1, a0=ref[p:p + 1], a1=np.array(alt, np.uint8), i0=0)
+        elif u < 0.8:
+            kind = int(rng.integers(0, 3))
+            k = int(rng.integers(1, 21))
+            if kind == 0:
+                v = dict(vtype=_VT_INS, ref_len=1, a0=ref[p:p + 1], a1=np.concatenate([ref[p:p + 1], _rand_seq(rng, k)]), i0=0)
+            elif kind == 1:
+                v = dict(vtype=_VT_DEL, ref_len=k + 1, a0=ref[p:p + k + 1], a1=ref[p:p + 1], i0=0)
+            else:
+                r = int(rng.integers(2, 11))
+                v = dict(vtype=_VT_INDEL, ref_len=r, a0=ref[p:p + r], a1=np.concatenate([ref[p:p + 1], _rand_seq(rng, int(rng.integers(1, 10)))]), i0=0)
+        elif u < 0.85:      # multi-allelic indel: both alleles are ALTs (index_allele0 = 1, index_allele1 = 2)
+            r = int(rng.integers(2, 8))
+            v = dict(vtype=_VT_INDEL, ref_len=r, a0=np.concatenate([ref[p:p + 1], _rand_seq(rng, int(rng.integers(1, 6)))]),
+                     a1=np.concatenate([ref[p:p + 1], _rand_seq(rng, int(rng.integers(6, 12)))]), i0=1)
+        elif u < 0.95:      # tandem-repeat like expansion of a short motif
+            motif = _rand_seq(rng, int(rng.integers(2, 7)))
+            L = int(rng.integers(10, 60))
+            v = dict(vtype=_VT_TR, ref_len=L, a0=ref[p:p + L],
+                     a1=np.concatenate([ref[p:p + L], np.tile(motif, int(rng.integers(2, 30)))[: int(rng.integers(10, 201))]]), i0=0)
+        else:
+            L = int(rng.integers(50, sv_max + 1))
+            if rng.random() < 0.5:
+                v = dict(vtype=_VT_SVINS, ref_len=1, a0=ref[p:p + 1], a1=np.concatenate([ref[p:p + 1], _rand_seq(rng, L)]), i0=0)
+            else:
+                v = dict(vtype=_VT_SVDEL, ref_len=L + 1, a0=ref[p:p + L + 1], a1=ref[p:p + 1], i0=0)
+        v["pos"] = p
+        v["het"] = bool(is_het[i])
+        v["phase"] = int(rng.integers(0, 2))
+        variants.append(v)
+    hets = [v for v in variants if v["het"]]
+    homs = [v for v in variants if not v["het"]]
+
+    # the two haplotype sequences + reference->haplotype coordinate maps at backbone positions
+    haps, maps = [], []
+    for h in (0, 1):
+        out, cur, mp_ref, mp_hap, hp_len = [], 0, [0], [0], 0
+        for v in variants:
+            if v["pos"] < cur:
+                continue                      # overlaps the variant applied just before on this haplotype
+            allele = v["a1"] if not v["het"] else (v["a1"] if v["phase"] == h else v["a0"])
+            seg = ref[cur:v["pos"]]
+            out.append(seg); hp_len += len(seg)
+            mp_ref.append(v["pos"]); mp_hap.append(hp_len)
+            out.append(allele); hp_len += len(allele)
+            cur = v["pos"] + v["ref_len"]
+            mp_ref.append(cur); mp_hap.append(hp_len)
+        out.append(ref[cur:]); hp_len += window - cur
+        mp_ref.append(window); mp_hap.append(hp_len)
+        haps.append(np.concatenate(out))
+        maps.append((np.array(mp_ref), np.array(mp_hap)))
+
+    het_pos = np.array([v["pos"] for v in hets])
+    hom_pos = np.array([v["pos"] for v in homs])
+    spans = np.array([(v["pos"], v["pos"] + v["ref_len"]) for v in variants])
+
+    def to_hap(h, x):   # x must be a backbone position (outside every applied variant span)
+        mr, mh = maps[h]
+        k = int(np.searchsorted(mr, x, side="right")) - 1
+        return int(mh[k] + (x - mr[k]))
+
+    def free_pos(x):    # move x right until it is not inside any variant's reference span
+        for _ in range(64):
+            inside = (spans[:, 0] <= x) & (x < spans[:, 1] + 1)
+            if not inside.any():
+                return x
+            x = int(spans[inside, 1].max()) + 1
+        return x
+
+    jobs = []
+    for _ in range(n_reads):
+        h = int(rng.integers(0, 2))
+        ln = int(rng.integers(read_lo, read_hi + 1))
+        s = free_pos(int(rng.integers(0, max(1, window - ln))))
+        e = free_pos(min(window - 1, s + ln))
+        if e >= window or e <= s + 10:
+            continue
+        seq = haps[h][to_hap(h, s): to_hap(h, e)].copy()
+        er = err_noisy if rng.random() < p_noisy else err
+        n = len(seq)
+        # substitutions, deletions, insertions at rate er/3 each
+        sub = rng.random(n) < er / 3
+        seq[sub] = _BASES[rng.integers(0, 4, int(sub.sum()))]
+        keep = rng.random(n) >= er / 3
+        ins = rng.random(n) < er / 3
+        pieces = np.where(keep, 1, 0) + np.where(ins, 1, 0)
+        outseq = np.empty(int(pieces.sum()), np.uint8)
+        idx = np.cumsum(pieces) - pieces
+        outseq[idx[keep]] = seq[keep]
+        ins_at = idx[ins] + np.where(keep[ins], 1, 0)
+        outseq[ins_at] = _BASES[rng.integers(0, 4, int(ins.sum()))]
+        jobs.append((s, e, int(np.searchsorted(het_pos, s)), int(np.searchsorted(het_pos, e)),
+                     int(np.searchsorted(hom_pos, s)), int(np.searchsorted(hom_pos, e)), outseq, h))
+    return dict(reference=ref, hets=hets, homs=homs, jobs=jobs)
+
+
+def config_c4(n_blocks=500, first_block=0, **kw):
+    """C4: WFA-heavy realignment jobs.  Returns (WfaBatch, job_block[ n_jobs ], blocks_meta)."""
+    from ._abi import WfaBatch
+    refs, ref_base = [], 0
+    vt = {k: [] for k in ("position", "ref_len", "allele0_off", "allele0_len", "allele1_off", "allele1_len", "index_allele0", "vtype", "ignored")}
+    blob = []
+    blob_len = 0
+    rs, re, hl, hh, ml, mh, reads, job_block, meta = [], [], [], [], [], [], [], [], []
+    nvar = 0
+    for b in range(first_block, first_block + n_blocks):
+        rng = np.random.default_rng(block_seed(4, b))
+        blk = gen_wfa_block(rng, **kw)
+        het_base = nvar
+        for v in blk["hets"] + blk["homs"]:
+            vt["position"].append(v["pos"] + ref_base); vt["ref_len"].append(v["ref_len"])
+            vt["allele0_off"].append(blob_len); vt["allele0_len"].append(len(v["a0"])); blob.append(v["a0"]); blob_len += len(v["a0"])
+            vt["allele1_off"].append(blob_len); vt["allele1_len"].append(len(v["a1"])); blob.append(v["a1"]); blob_len += len(v["a1"])
+            vt["index_allele0"].append(v["i0"]); vt["vtype"].append(v["vtype"]); vt["ignored"].append(0)
+            nvar += 1
+        hom_base = het_base + len(blk["hets"])
+        for (s, e, a, bb, c, d, seq, h) in blk["jobs"]:
+            rs.append(s + ref_base); re.append(e + ref_base)
+            hl.append(het_base + a); hh.append(het_base + bb); ml.append(hom_base + c); mh.append(hom_base + d)
+            reads.append(seq); job_block.append(b - first_block)
+        meta.append(dict(n_het=len(blk["hets"]), het_base=het_base, vtypes=[v["vtype"] for v in blk["hets"]],
+                         phase=[v["phase"] for v in blk["hets"]]))
+        refs.append(blk["reference"]); ref_base += len(blk["reference"])
+    vt["allele_bytes"] = np.concatenate(blob) if blob else np.zeros(0, np.uint8)
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])])
+    batch = WfaBatch(vt, np.concatenate(refs), rs, re, hl, hh, ml, mh, np.concatenate(reads), read_off)
+    return batch, np.array(job_block), meta
+
+
+def blocks_from_wfa_rows(batch, out, job_block, meta, min_set=2):
+    """WFA rows -> A* phase blocks (one ReadSegment per job; reads with < min_set set alleles are dropped,
+    read_parsing.rs:612-629).  Jobs that hit MaxEditDistance (status 1) or were skipped contribute nothing."""
+    blocks = [dict(n_var=m["n_het"], reads=[], is_snv=(np.array(m["vtypes"]) == 0).astype(np.uint8)) for m in meta]
+    for j in range(batch.n_jobs):
+        if out.status[j] != 0:
+            continue
+        m = meta[job_block[j]]
+        r0, r1 = int(batch.row_off[j]), int(batch.row_off[j + 1])
+        a, q = out.alleles[r0:r1], out.quals[r0:r1]
+        sset = np.flatnonzero(a < 2)
+        if len(sset) < min_set:
+            continue
+        lo, hi = int(sset[0]), int(sset[-1]) + 1
+        start = int(batch.het_lo[j]) - m["het_base"] + lo
+        blocks[job_block[j]]["reads"].append((start, a[lo:hi].copy(), q[lo:hi].copy()))
+    return BlockBatch.from_blocks(blocks)

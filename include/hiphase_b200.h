@@ -55,7 +55,8 @@ extern "C" {
 #define HP_WFA_OK                  0
 #define HP_WFA_MAX_EDIT_DISTANCE   1   /* WFAGraphError::MaxEditDistance, src/wfa_graph.rs:645-648              */
 #define HP_WFA_SKIPPED             2   /* job overlaps no het variant (read_parsing.rs:703-712)                 */
-#define HP_WFA_WORKSPACE_OVERFLOW  3   /* internal: wave/set pool outgrew its slab (retried transparently)      */
+#define HP_WFA_WORKSPACE_OVERFLOW  3   /* wave table outgrew its slab (retried transparently up to 4x) or the   */
+                                       /* graph has more than 1024 nodes (outside the kernel's range)           */
 
 /* AlleleType, src/data_types/read_segments.rs:5-16 */
 #define HP_ALLELE_REFERENCE  0

@@ -1,0 +1,118 @@
+"""Parity of the CUDA graph-WFA path (through the C ABI) against the reference's known-answer vectors and the
+CPU oracle: status, edit distance, traversed-node set and the allele / quality rows, bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import golden, wfa_batch_single
+from hiphase_b200 import _abi as A
+from hiphase_b200 import lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lib.Context(device=0)
+    yield c
+    c.close()
+
+
+def _flat(nodes):
+    seq, seq_off, par, par_off = [], [0], [], [0]
+    for n in nodes:
+        seq += list(n["seq"]); seq_off.append(len(seq))
+        par += sorted(n["parents"]); par_off.append(len(par))
+    return np.array(seq, np.uint8), seq_off, np.array(par, np.uint32), par_off
+
+
+@pytest.mark.parametrize("case", golden("wfa_graphs.json")["hand_built"], ids=lambda c: c["name"])
+def test_hand_built_graphs(ctx, case):
+    seq, seq_off, par, par_off = _flat(case["nodes"])
+    for c in case["cases"]:
+        st, score, nodes = ctx.wfa_graph_align(seq, seq_off, par, par_off, c["read"])
+        assert st == A.HP_WFA_OK and score == c["score"], (c, st, score)
+        if "nodes" in c:
+            assert nodes == c["nodes"]
+
+
+def test_graph_rules_rejected(ctx):
+    with pytest.raises(lib.HiPhaseB200Error):
+        ctx.wfa_graph_align([1, 2], [0, 1, 2], [], [0, 0, 0], [1, 2])            # second node without a parent
+    with pytest.raises(lib.HiPhaseB200Error):
+        ctx.wfa_graph_align([1, 2], [0, 1, 2], [0, 1], [0, 1, 2], [1, 2])        # root with a parent
+
+
+def test_max_edit_distance_status(ctx):
+    st, score, nodes = ctx.wfa_graph_align(list(range(8)), [0, 8], [], [0, 0], [9] * 8, max_edit_distance=3)
+    assert st == A.HP_WFA_MAX_EDIT_DISTANCE and score == 3 and nodes == []
+
+
+@pytest.mark.parametrize("case", golden("wfa_graphs.json")["from_variants"], ids=lambda c: c["name"])
+def test_from_variants_golden(ctx, case):
+    reads = [c["read"] for c in case["cases"]] or ["A"]
+    batch = wfa_batch_single(case["reference"], case["hets"], case["homs"], case["ref_start"], case["ref_end"], reads)
+    out = ctx.wfa_align_batch(batch, trav_words=1)
+    ref = O.wfa_align(batch, trav_words=1)
+    assert (out.n_nodes == case["num_nodes"]).all()
+    for j, c in enumerate(case["cases"]):
+        assert out.status[j] == A.HP_WFA_OK and out.score[j] == c["score"]
+        assert [i for i in range(case["num_nodes"]) if (int(out.traversed[j]) >> i) & 1] == c["nodes"]
+    assert np.array_equal(out.alleles, ref.alleles) and np.array_equal(out.quals, ref.quals)
+    assert np.array_equal(out.status, ref.status) and np.array_equal(out.score, ref.score)
+
+
+def _assert_wfa_parity(out, ref):
+    assert np.array_equal(out.status, ref.status), (np.flatnonzero(out.status != ref.status)[:10], out.status[:20], ref.status[:20])
+    assert np.array_equal(out.score, ref.score)
+    assert np.array_equal(out.n_nodes, ref.n_nodes)
+    assert np.array_equal(out.traversed, ref.traversed)
+    assert np.array_equal(out.alleles, ref.alleles) and np.array_equal(out.quals, ref.quals)
+
+
+def test_c4_small_vs_oracle(ctx):
+    batch, jb, meta = synth.config_c4(2, window=30000, n_het=30, n_hom=40, n_reads=24, read_lo=4000, read_hi=9000, sv_max=600)
+    out = ctx.wfa_align_batch(batch, trav_words=8)
+    ref = O.wfa_align(batch, threads=8, trav_words=8)
+    assert ref.failures == 0
+    _assert_wfa_parity(out, ref)
+    assert (out.status == A.HP_WFA_OK).sum() > 10
+
+
+def test_c4_noisy_reads_and_pruning_off(ctx):
+    # high error rate: deep edit distances, wide wavefronts, max-ED failures; and the same with pruning disabled
+    batch, jb, meta = synth.config_c4(1, window=12000, n_het=25, n_hom=25, n_reads=16, read_lo=1500, read_hi=3000, sv_max=300,
+                                      err=0.03, p_noisy=0.3, err_noisy=0.25)
+    for prune, max_ed in ((500, 500), (0, 120), (40, 500)):
+        params = A.hp_params(1000, 3, prune, max_ed)
+        c2 = lib.Context(params, device=0)
+        out = c2.wfa_align_batch(batch, trav_words=4)
+        ref = O.wfa_align(batch, params, threads=8, trav_words=4)
+        _assert_wfa_parity(out, ref)
+        c2.close()
+
+
+def test_skipped_and_empty_jobs(ctx):
+    case = [c for c in golden("wfa_graphs.json")["from_variants"] if c["name"] == "test_multiple_variants"][0]
+    batch = wfa_batch_single(case["reference"], case["hets"], case["homs"], 0, 5, ["AAAAA", "", "ACACA"])
+    batch.het_hi[1] = batch.het_lo[1]          # job 1 overlaps no het variant -> skipped (read_parsing.rs:703-712)
+    batch = A.WfaBatch({k: getattr(batch, k) for k in ("position", "ref_len", "allele0_off", "allele0_len", "allele1_off", "allele1_len",
+                                                        "index_allele0", "vtype", "ignored", "allele_bytes")},
+                       batch.reference, batch.ref_start, batch.ref_end, batch.het_lo, batch.het_hi, batch.hom_lo, batch.hom_hi,
+                       batch.read_bytes, batch.read_off)
+    out = ctx.wfa_align_batch(batch, trav_words=1)
+    ref = O.wfa_align(batch, trav_words=1)
+    assert out.status.tolist() == [A.HP_WFA_OK, A.HP_WFA_SKIPPED, A.HP_WFA_OK] == ref.status.tolist()
+    assert np.array_equal(out.alleles, ref.alleles) and np.array_equal(out.quals, ref.quals)
+
+
+def test_c4_rows_feed_astar(ctx):
+    # K2 -> matrix rows -> K1: the blocks assembled from the CUDA rows phase identically to the oracle pipeline
+    batch, jb, meta = synth.config_c4(2, window=30000, n_het=30, n_hom=40, n_reads=40, read_lo=4000, read_hi=9000, sv_max=600)
+    out = ctx.wfa_align_batch(batch)
+    blocks = synth.blocks_from_wfa_rows(batch, out, jb, meta)
+    got = ctx.astar_solve_batch(blocks)
+    ref_rows = O.wfa_align(batch, threads=8)
+    ref_blocks = synth.blocks_from_wfa_rows(batch, ref_rows, jb, meta)
+    want = O.astar_solve(ref_blocks, threads=4)
+    assert np.array_equal(got.h1, want.h1) and np.array_equal(got.h2, want.h2) and np.array_equal(got.stats, want.stats)
