@@ -238,9 +238,14 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
-    # ---- result hand-off between ranks: the only collective is a tiny checksum gather of the results ----
+    # ---- result hand-off between ranks (outside the timed region): the only collective on the path.  Per-block
+    #      PhaseStats records are all-gathered over NCCL and re-ordered by global block index.
     checksum = int(o_h1.to(torch.int64).sum().item() * 3 + o_h2.to(torch.int64).sum().item())
     if world > 1:
+        from hiphase_b200 import sharding
+        ids = np.arange(rank * nb, (rank + 1) * nb, dtype=np.int64)
+        stats_all = sharding.gather_block_records(ids, o_stats.cpu().numpy().reshape(nb, 7), nb * world)
+        assert stats_all.shape == (nb * world, 7) and (stats_all[:, 2] >= stats_all[:, 1]).all()
         t = torch.tensor([checksum], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         checksum = int(t.item())
