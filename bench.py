@@ -143,6 +143,8 @@ def main():
     batch = synth.config_c2(n_blocks=nb, first_block=rank * nb, n_var=N_VAR, n_reads=N_READS)
     max_n = int(np.diff(batch.var_off.astype(np.int64)).max())
     ctx = lib.Context(device=local_rank)
+    if os.environ.get("HP_TEAM"):
+        ctx.set_team(int(os.environ["HP_TEAM"]))      # experiment knob: speculative team size (default: automatic)
 
     # device-resident copy of the batch (reference u8 layout) + device outputs
     dten = {k: torch.from_numpy(getattr(batch, k).view(np.int64) if getattr(batch, k).dtype == np.uint64 else

@@ -16,6 +16,8 @@
 //     (<= 1 + 3*(100+3*40) nodes, 40-bit haplotypes) lives in shared memory as 32 lane-owned stripes with the
 //     stripe minimum cached in registers (pop = 2 redux.sync + ballot); the main queue lives in a per-warp slab
 //     in HBM/L2 with full-length haplotype records.
+#include <algorithm>
+
 #include "hp_device.cuh"
 #include "../../include/hiphase_b200.h"
 
@@ -324,13 +326,21 @@ struct __align__(16) SubEntry {
 };
 
 struct WarpCtx {
-    SubEntry* sq;           // this warp's sub-solver queue in shared memory (stripe-major: lane l owns [l*capl, (l+1)*capl))
-    uint32_t* hring;        // H[] ring buffer, 64 entries
-    uint32_t capl;
+    SubEntry* sq;           // this warp's sub-solver queue: first capl_s entries of every stripe, in shared memory
+    SubEntry* sq_spill;     // ... and the rest of every stripe in the warp's global slab (rarely touched)
+    uint32_t* hring;        // H[] ring buffer, 64 entries, shared by the warps of a team
+    uint32_t capl;          // stripe capacity (entries per lane)
+    uint32_t capl_s;        // of which in shared memory
     uint32_t lane;
+    uint32_t h_floor;       // speculation: H[] entries below this index are not known yet and read as H[h_floor]
     // counters
     uint64_t evals, sum_lp, pops, cells;
     int status;
+    // entry i of stripe `stripe`
+    __device__ __forceinline__ SubEntry* ent(uint32_t stripe, uint32_t i) const {
+        return i < capl_s ? sq + stripe * capl_s + i : sq_spill + stripe * (capl - capl_s) + (i - capl_s);
+    }
+    __device__ __forceinline__ uint32_t H(uint32_t idx) const { return hring[max(idx, h_floor) & 63u]; }
 };
 
 __device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1, uint64_t h2, uint32_t frozen) {
@@ -352,13 +362,12 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
     const uint32_t* aidx = a.act_idx + m.cell_base;
     const uint32_t* col = a.col + m.cell_base;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
-    SubEntry* stripe = w.sq + lane * w.capl;
 
     // queue state: cached stripe minimum + stripe count in registers; qmin = warp-uniform queue minimum
     uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
     // root: AstarNode::new(H[v+1]) (:325), kept in registers as the current top
-    uint32_t cur_total = w.hring[(v + 1) & 63], cur_lo = 63u << 26, cur_frozen = 0;
+    uint32_t cur_total = w.H(v + 1), cur_lo = 63u << 26, cur_frozen = 0;
     uint64_t cur_h1 = 0, cur_h2 = 0;
     int cur_src = SRC_ROOT;
     uint32_t cur_x1 = 0, cur_x2 = 0;
@@ -377,7 +386,7 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint64_t k = mk64(cur_total, cur_lo);
-                    sub_store(stripe + cnt, k, cur_h1, cur_h2, cur_frozen);
+                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, cur_frozen);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -385,20 +394,20 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
             }
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
-            const SubEntry* e = w.sq + owner * w.capl + pos;
+            const SubEntry* e = w.ent(owner, pos);
             cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
             cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
             __syncwarp();
             if ((int)lane == owner) {                                    // remove + rescan own stripe
                 cnt--;
                 if (pos != cnt) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(stripe + cnt);
-                    uint4* dp = reinterpret_cast<uint4*>(stripe + pos);
+                    const uint4* sp = reinterpret_cast<const uint4*>(w.ent(lane, cnt));
+                    uint4* dp = reinterpret_cast<uint4*>(w.ent(lane, pos));
                     dp[0] = sp[0]; dp[1] = sp[1];
                 }
                 ckey = ~0ull; cpos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
-                    const uint64_t k = stripe[i].key;
+                    const uint64_t k = w.ent(lane, i)->key;
                     if (k < ckey) { ckey = k; cpos = i; }
                 }
             }
@@ -425,7 +434,7 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
         // ---- expand ----
         const uint32_t p = v + L;
         const bool bad_col = (badwin >> L) & 1ull;
-        const uint32_t heur = w.hring[(p + 1) & 63];
+        const uint32_t heur = w.H(p + 1);
         const uint32_t o0 = __ldg(aoff + p), o1 = __ldg(aoff + p + 1);
         const bool ident = (cur_h1 == cur_h2);
         auto hap = [&](int which, int i0) { return shift_signed(which ? cur_h2 : cur_h1, i0); };
@@ -464,7 +473,7 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
             if (fullmask == 0) {
                 if (mine) {
                     const uint64_t k = mk64(mt, ml);
-                    sub_store(stripe + cnt, k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
+                    sub_store(w.ent(lane, cnt), k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -480,7 +489,7 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
                         const uint32_t xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
                         if (lane == target) {
                             const uint64_t k = mk64(xt, xl);
-                            sub_store(stripe + cnt, k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
+                            sub_store(w.ent(lane, cnt), k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
                             if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
@@ -530,14 +539,13 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     const uint32_t* aidx = a.act_idx + m.cell_base;
     const uint32_t* col = a.col + m.cell_base;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
-    SubEntry* stripe = w.sq + lane * w.capl;
     constexpr uint32_t kEmpty = 0xffff0000u;      // column record of an unused slot: no carry, quality 0
 
     // queue state
     uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
     // current top (root, :325)
-    uint32_t cur_total = w.hring[(v + 1) & 63], cur_lo = 63u << 26, cur_frozen = 0;
+    uint32_t cur_total = w.H(v + 1), cur_lo = 63u << 26, cur_frozen = 0;
     uint64_t cur_h1 = 0, cur_h2 = 0;
     int cur_src = SRC_ROOT;
     uint32_t cur_x1 = 0, cur_x2 = 0;
@@ -566,7 +574,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint64_t k = mk64(cur_total, cur_lo);
-                    sub_store(stripe + cnt, k, cur_h1, cur_h2, cur_frozen);
+                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, cur_frozen);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -574,20 +582,20 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             }
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
-            const SubEntry* e = w.sq + owner * w.capl + pos;
+            const SubEntry* e = w.ent(owner, pos);
             cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
             cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
             __syncwarp();
             if ((int)lane == owner) {                                    // remove + rescan own stripe
                 cnt--;
                 if (pos != cnt) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(stripe + cnt);
-                    uint4* dp = reinterpret_cast<uint4*>(stripe + pos);
+                    const uint4* sp = reinterpret_cast<const uint4*>(w.ent(lane, cnt));
+                    uint4* dp = reinterpret_cast<uint4*>(w.ent(lane, pos));
                     dp[0] = sp[0]; dp[1] = sp[1];
                 }
                 ckey = ~0ull; cpos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
-                    const uint64_t k = stripe[i].key;
+                    const uint64_t k = w.ent(lane, i)->key;
                     if (k < ckey) { ckey = k; cpos = i; }
                 }
             }
@@ -602,7 +610,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 const uint32_t cs = slot_of_ordinal(cache_present, d);
                 cur_src = SRC_CACHE; cur_x1 = cs & 1u; cur_x2 = (0x9u >> cs) & 1u;
             } else cur_src = SRC_PLANES;
-            heur_p = w.hring[(Lp == 0u ? v + 1 : pp) & 63];
+            heur_p = w.H(Lp == 0u ? v + 1 : pp);
             if (pp < N) {
                 o_p = __ldg(aoff + pp); o_p1 = __ldg(aoff + pp + 1);
 #pragma unroll
@@ -629,7 +637,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         uint32_t coln[K];
 #pragma unroll
         for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col + o_p1 + lane + 32u * k) : kEmpty;
-        const uint32_t heur = w.hring[(p + 1) & 63];
+        const uint32_t heur = w.H(p + 1);
         const bool bad_col = (badwin >> L) & 1ull;
         const bool ident = (cur_h1 == cur_h2);
 
@@ -732,7 +740,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             if (fullmask == 0) {
                 if (mine) {
                     const uint64_t k = mk64(mt, ml);
-                    sub_store(stripe + cnt, k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
+                    sub_store(w.ent(lane, cnt), k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -748,7 +756,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                         const uint32_t xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
                         if (lane == target) {
                             const uint64_t k = mk64(xt, xl);
-                            sub_store(stripe + cnt, k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
+                            sub_store(w.ent(lane, cnt), k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
                             if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
@@ -1144,102 +1152,196 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     if (top_total < Hg[0]) w.status = HP_BLOCK_ASSERT;                     // phase_stats.rs:163
 }
 
-// One phase block, start to finish, by one warp.
+// ---- team: the warps of one CTA work on one phase block ---------------------------------------------------------
+// The heuristic pre-pass is a chain: sub-solve v needs H[v+1..v+40] and the clip size left by sub-solve v+1.  But
+// H[v] == H[v+1] for most variants, so warp i of the team solves variant v_hi - i SPECULATIVELY, reading every not yet
+// known H entry as H[v_hi+1] and assuming every earlier sub-solve of the round solves its full clip.  After a CTA
+// barrier the results are verified in chain order and the longest valid prefix is committed (warp 0 never
+// speculates, so every round commits at least one variant).  Results are exactly those of the serial chain.
+constexpr int kMaxTeam = 4;
+
+struct TeamShared {
+    uint32_t blk;
+    uint32_t est[kMaxTeam], solved[kMaxTeam];
+    int32_t status[kMaxTeam];
+    int32_t final_status;
+    unsigned long long ctr[4];       // accepted work counters (evals, cells, sum_lp, pops)
+    uint32_t hring[64];
+};
+
+__device__ __forceinline__ uint64_t bad_window(const uint8_t* ign, uint32_t v, uint32_t N, uint32_t lane) {
+    // bit i = ignored[v + i], i < 40
+    const uint32_t lo = __ballot_sync(HP_FULL_MASK, v + lane < N && __ldg(ign + v + lane) != 0);
+    const uint32_t hi = __ballot_sync(HP_FULL_MASK, lane < 8 && v + 32 + lane < N && __ldg(ign + v + 32 + lane) != 0);
+    return ((uint64_t)hi << 32) | lo;
+}
+
 template <int K, bool kCount>
-__device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, const Slab& slab, uint32_t blk) {
+__device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, const Slab& slab, uint32_t blk,
+                            TeamShared& ts, uint32_t warp, uint32_t team) {
     const uint32_t N = m.n_var;
     uint32_t* Hg = a.heur + m.var_base + blk;
     const long long t_start = kCount ? clock64() : 0;
-    // ---- calculate_astar_heuristic (:246-292) ----
     const uint8_t* ign = a.ignored + m.var_base;
-    if (w.lane == 0) { w.hring[N & 63] = 0; Hg[N] = 0; }
-    __syncwarp();
-    uint32_t clip = 1;
-    uint64_t badwin = 0;
-    for (uint32_t v = N; v-- > 0;) {
-        const uint32_t bad_v = __ldg(ign + v);
-        badwin = (badwin << 1) | (bad_v ? 1ull : 0ull);
-        const uint2 r = sub_solve<K, kCount>(a, m, w, v, clip, badwin, blk);
-        if (w.status != HP_BLOCK_OK) return;
-        const uint32_t est = r.x, solved = r.y;
-        if (solved < min(clip, 2u)) { w.status = HP_BLOCK_ASSERT; return; }          // :268
-        const uint32_t hnext = w.hring[(v + 1) & 63];
-        uint32_t hv;
-        if (bad_v) hv = hnext;
-        else {
-            if (est < hnext) { w.status = HP_BLOCK_ASSERT; return; }                  // :284
-            hv = est;
+    if (threadIdx.x == 0) { ts.hring[N & 63] = 0; Hg[N] = 0; ts.final_status = HP_BLOCK_OK; }
+    if (threadIdx.x < 4) ts.ctr[threadIdx.x] = 0;
+    __syncthreads();
+
+    // ---- calculate_astar_heuristic (:246-292), `team` variants per round ----
+    int v_hi = (int)N - 1;
+    uint32_t clip0 = 1;
+    int status = HP_BLOCK_OK;
+    uint32_t n_rounds = 0;
+    long long t_wait = 0;
+    while (v_hi >= 0 && status == HP_BLOCK_OK) {
+        const int v = v_hi - (int)warp;
+        const uint32_t clip_guess = min(clip0 + warp, HP_MAX_SEGMENT);
+        const uint64_t e0 = w.evals, c0 = w.cells, l0 = w.sum_lp, p0 = w.pops;
+        if (v >= 0) {
+            w.h_floor = (uint32_t)v_hi + 1;
+            w.status = HP_BLOCK_OK;
+            const uint2 r = sub_solve<K, kCount>(a, m, w, (uint32_t)v, clip_guess, bad_window(ign, (uint32_t)v, N, w.lane), blk);
+            if (w.lane == 0) { ts.est[warp] = r.x; ts.solved[warp] = r.y; ts.status[warp] = w.status; }
         }
-        __syncwarp();
-        if (w.lane == 0) { w.hring[v & 63] = hv; Hg[v] = hv; }
-        __syncwarp();
-        clip = min(solved + 1, HP_MAX_SEGMENT);                                      // :288
+        const long long tw0 = kCount ? clock64() : 0;
+        __syncthreads();
+        if (kCount) t_wait += clock64() - tw0;
+        n_rounds++;
+        // ---- verify in chain order (every thread computes the same) ----
+        const uint32_t h_base = ts.hring[(v_hi + 1) & 63];
+        uint32_t h_next = h_base, clip_chk = clip0, accepted = 0;
+        uint32_t hv_out[kMaxTeam];
+        bool chain_ok = true;
+#pragma unroll
+        for (uint32_t i = 0; i < (uint32_t)kMaxTeam; i++) {
+            const int vi = v_hi - (int)i;
+            if (i < team && vi >= 0 && chain_ok && status == HP_BLOCK_OK && clip_chk == min(clip0 + i, HP_MAX_SEGMENT)) {
+                const uint32_t est = ts.est[i], solved = ts.solved[i];
+                if (ts.status[i] != HP_BLOCK_OK) status = ts.status[i];
+                else if (solved < min(clip_chk, 2u)) status = HP_BLOCK_ASSERT;                 // :268
+                else {
+                    uint32_t hv = h_next;
+                    if (!__ldg(ign + vi)) {
+                        if (est < h_next) status = HP_BLOCK_ASSERT;                              // :284
+                        hv = est;
+                    }
+                    hv_out[i] = hv;
+                    accepted = i + 1;
+                    h_next = hv;
+                    clip_chk = min(solved + 1, HP_MAX_SEGMENT);                                  // :288
+                    chain_ok = (hv == h_base);        // later warps read H[vi] as h_base
+                }
+            } else chain_ok = false;
+        }
+        if (kCount && warp < accepted && w.lane == 0) {
+            atomicAdd(&ts.ctr[0], (unsigned long long)(w.evals - e0)); atomicAdd(&ts.ctr[2], (unsigned long long)(w.sum_lp - l0));
+            atomicAdd(&ts.ctr[3], (unsigned long long)(w.pops - p0));
+        }
+        if (kCount && warp < accepted) {
+            const uint64_t dc = w.cells - c0;
+            const uint64_t tot = __reduce_add_sync(HP_FULL_MASK, (uint32_t)(dc & 0xffffffffu)) +
+                                 ((uint64_t)__reduce_add_sync(HP_FULL_MASK, (uint32_t)(dc >> 32)) << 32);
+            if (w.lane == 0) atomicAdd(&ts.ctr[1], (unsigned long long)tot);
+        }
+        __syncthreads();                      // everyone has read hring / results of this round
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kMaxTeam; i++)
+                if (i < accepted) { ts.hring[(v_hi - (int)i) & 63] = hv_out[i]; Hg[v_hi - (int)i] = hv_out[i]; }
+        }
+        v_hi -= (int)accepted;
+        clip0 = clip_chk;
+        if (accepted == 0 && status == HP_BLOCK_OK) status = HP_BLOCK_ASSERT;      // cannot happen: warp 0 is never speculative
+        __syncthreads();
     }
+    w.status = status;
+    w.h_floor = 0;
     const long long t_mid = kCount ? clock64() : 0;
-    const uint64_t pops_sub = w.pops;
-    main_solve<K, kCount>(a, m, w, slab, blk, Hg);
-    if (kCount && a.dbg_cycles && w.lane == 0) {
-        a.dbg_cycles[4ull * blk + 0] = (uint64_t)(t_mid - t_start);
-        a.dbg_cycles[4ull * blk + 1] = (uint64_t)(clock64() - t_mid);
-        a.dbg_cycles[4ull * blk + 2] = pops_sub;
-        a.dbg_cycles[4ull * blk + 3] = w.pops - pops_sub;
+    // ---- main loop: one warp ----
+    if (warp == 0) {
+        w.evals = w.sum_lp = w.pops = w.cells = 0;
+        if (w.status == HP_BLOCK_OK) main_solve<K, kCount>(a, m, w, slab, blk, Hg);
+        w.status = __shfl_sync(HP_FULL_MASK, w.status, 0);
+        if (w.lane == 0) ts.final_status = w.status;
+        if (kCount) {
+            const uint64_t tot = __reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells & 0xffffffffu)) +
+                                 ((uint64_t)__reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells >> 32)) << 32);
+            if (w.lane == 0) {
+                if (a.dbg_cycles) {
+                    a.dbg_cycles[8ull * blk + 0] = (uint64_t)(t_mid - t_start);
+                    a.dbg_cycles[8ull * blk + 1] = (uint64_t)(clock64() - t_mid);
+                    a.dbg_cycles[8ull * blk + 2] = ts.ctr[3];
+                    a.dbg_cycles[8ull * blk + 3] = w.pops;
+                    a.dbg_cycles[8ull * blk + 4] = n_rounds;
+                    a.dbg_cycles[8ull * blk + 5] = (uint64_t)t_wait;
+                    a.dbg_cycles[8ull * blk + 6] = team;
+                    a.dbg_cycles[8ull * blk + 7] = 0;
+                }
+                ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;
+            }
+        }
     }
+    __syncthreads();
 }
 
-constexpr int kSolveWarps = 8;
+constexpr int kSubCaplShared = 12;    // sub-solver queue entries per stripe kept in shared memory (rest: global spill)
 
-template <bool kCount>
-__global__ void __launch_bounds__(kSolveWarps * 32, 1) astar_solve_kernel(AstarArgs a) {
+// One kernel per score-vector class K (1: <= 32 reads per column, 2: <= 64, 0: any) keeps the register footprint of the
+// common class small.  Class c owns order[class_start[c] .. +class_count[c]) and ticket[c].
+template <int K, bool kCount>
+__global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kernel(AstarArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ TeamShared ts;
+    constexpr int cls = (K == 1) ? 0 : (K == 2 ? 1 : 2);
+    const uint32_t n_mine = a.class_info[cls], first = a.class_info[4 + cls];
     const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t team = blockDim.x >> 5;
     WarpCtx w;
     w.lane = lane_id();
     w.capl = a.sub_capl;
-    const uint32_t cap = w.capl * 32;
-    const size_t per_warp = (size_t)cap * sizeof(SubEntry) + 64 * 4;
-    uint8_t* base = smem_raw + warp * per_warp;
-    w.sq = (SubEntry*)base;
-    w.hring = (uint32_t*)(base + (size_t)cap * sizeof(SubEntry));
+    w.capl_s = min(a.sub_capl, (uint32_t)kSubCaplShared);
+    w.sq = (SubEntry*)(smem_raw + (size_t)warp * w.capl_s * 32 * sizeof(SubEntry));
+    w.hring = ts.hring;
+    w.h_floor = 0;
+    w.evals = w.sum_lp = w.pops = w.cells = 0;
 
-    const uint32_t gwarp = blockIdx.x * kSolveWarps + warp;
-    const Slab slab = carve_slab(a.slabs + (uint64_t)gwarp * a.slab_bytes, a.qcap, a.hap_words);
+    const uint32_t gwarp = blockIdx.x * team + warp;
+    uint8_t* my_slab = a.slabs + (uint64_t)gwarp * a.slab_bytes;
+    const Slab slab = carve_slab(my_slab, a.qcap, a.hap_words);
+    w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)32 * (w.capl - w.capl_s) * sizeof(SubEntry));
 
     for (;;) {
-        uint32_t t = 0;
-        if (w.lane == 0) t = atomicAdd(a.ticket, 1u);
-        t = __shfl_sync(HP_FULL_MASK, t, 0);
-        if (t >= a.n_blocks) break;
-        const uint32_t blk = a.order[t];
+        __syncthreads();
+        if (threadIdx.x == 0) ts.blk = atomicAdd(a.ticket + cls, 1u);
+        __syncthreads();
+        const uint32_t t = ts.blk;
+        if (t >= n_mine) break;
+        const uint32_t blk = a.order[first + t];
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
         w.status = m.status;
+        if (threadIdx.x == 0) ts.final_status = m.status;
 
-        if (w.status == HP_BLOCK_OK) {
-            // register-resident score vectors cover up to 32*K active reads per column
-            if (m.max_act <= 32) solve_block<1, kCount>(a, m, w, slab, blk);
-            else if (m.max_act <= 64) solve_block<2, kCount>(a, m, w, slab, blk);
-            else solve_block<0, kCount>(a, m, w, slab, blk);
-        }
-        w.status = __shfl_sync(HP_FULL_MASK, w.status, 0);
+        if (m.status == HP_BLOCK_OK) solve_block<K, kCount>(a, m, w, slab, blk, ts, warp, team);
+        __syncthreads();
+        const int status = ts.final_status;
 
-        // ---- per-block outputs ----
-        __syncwarp();
-        if (w.status != HP_BLOCK_OK) {
-            if (w.lane < 7) a.out_stats[(uint64_t)blk * 7 + w.lane] = 0;
-        }
-        if (a.out_heur && w.status == HP_BLOCK_OK) {
-            const uint32_t* Hg = a.heur + m.var_base + blk;
-            for (uint32_t i = w.lane; i <= m.n_var; i += 32) a.out_heur[m.var_base + blk + i] = Hg[i];
-        }
-        if (kCount && a.out_counters) {
-            const uint64_t cells = __reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells & 0xffffffffu)) +
-                                   ((uint64_t)__reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells >> 32)) << 32);
-            if (w.lane == 0) {
-                uint64_t* c = a.out_counters + (uint64_t)blk * 4;
-                c[0] = w.evals; c[1] = cells; c[2] = w.sum_lp; c[3] = w.pops;
+        // ---- per-block outputs (warp 0) ----
+        if (warp == 0) {
+            if (status != HP_BLOCK_OK) {
+                if (w.lane < 7) a.out_stats[(uint64_t)blk * 7 + w.lane] = 0;
             }
+            if (a.out_heur && status == HP_BLOCK_OK) {
+                const uint32_t* Hg = a.heur + m.var_base + blk;
+                for (uint32_t i = w.lane; i <= m.n_var; i += 32) a.out_heur[m.var_base + blk + i] = Hg[i];
+            }
+            if (kCount && a.out_counters && w.lane == 0) {
+                uint64_t* c = a.out_counters + (uint64_t)blk * 4;
+                if (status == HP_BLOCK_OK) { c[0] = ts.ctr[0]; c[1] = ts.ctr[1]; c[2] = ts.ctr[2]; c[3] = ts.ctr[3]; }
+                else { c[0] = c[1] = c[2] = c[3] = 0; }
+            }
+            if (w.lane == 0) a.out_status[blk] = status;
         }
-        if (w.lane == 0) a.out_status[blk] = w.status;
     }
 }
 
@@ -1248,12 +1350,17 @@ __global__ void __launch_bounds__(kSolveWarps * 32, 1) astar_solve_kernel(AstarA
 // ---- host-side launchers (called from hp_api.cu) ---------------------------------------------------------------
 namespace hp {
 
-size_t astar_smem_bytes(uint32_t sub_capl) {
-    const size_t per_warp = (size_t)sub_capl * 32 * sizeof(SubEntry) + 64 * 4;
-    return per_warp * kSolveWarps;
+size_t astar_smem_bytes(uint32_t sub_capl, int team) {
+    const uint32_t capl_s = std::min<uint32_t>(sub_capl, kSubCaplShared);
+    return (size_t)team * capl_s * 32 * sizeof(SubEntry);
 }
-int astar_solve_warps() { return kSolveWarps; }
-uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words) { return slab_bytes_for(qcap, hap_words); }
+int astar_max_team() { return kMaxTeam; }
+int astar_warps_per_sm() { return 16; }
+uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl) {
+    const uint32_t capl_s = std::min<uint32_t>(sub_capl, kSubCaplShared);
+    const uint64_t spill = (uint64_t)32 * (sub_capl - capl_s) * sizeof(SubEntry);
+    return ((slab_bytes_for(qcap, hap_words) + spill + 255) & ~255ull);
+}
 
 cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream) {
     if (pa.n_blocks == 0) return cudaSuccess;
@@ -1261,19 +1368,26 @@ cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, cudaStream_t stream) {
-    const size_t smem = astar_smem_bytes(a.sub_capl);
+template <int K, bool kCount>
+static cudaError_t launch_one(const AstarArgs& a, int n_ctas, int team, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(astar_solve_kernel<K, kCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    astar_solve_kernel<K, kCount><<<n_ctas, team * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// Three launches (one per score-vector class); a class without blocks exits at once.
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t stream) {
+    const size_t smem = astar_smem_bytes(a.sub_capl, team);
     cudaError_t e;
     if (a.out_counters) {
-        e = cudaFuncSetAttribute(astar_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        astar_solve_kernel<true><<<n_ctas, kSolveWarps * 32, smem, stream>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(astar_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        astar_solve_kernel<false><<<n_ctas, kSolveWarps * 32, smem, stream>>>(a);
+        if ((e = launch_one<1, true>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
+        if ((e = launch_one<2, true>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
+        return launch_one<0, true>(a, n_ctas, team, smem, stream);
     }
-    return cudaGetLastError();
+    if ((e = launch_one<1, false>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
+    if ((e = launch_one<2, false>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
+    return launch_one<0, false>(a, n_ctas, team, smem, stream);
 }
 
 }  // namespace hp

@@ -32,25 +32,29 @@ __global__ void iota_kernel(uint32_t* p, uint32_t n) {
     if (i < n) p[i] = i;
 }
 
-// Largest-first processing order (LPT): blocks are binned by floor(log2(n_cells * min(n_var, 40))) so the
-// longest serial chains start first and the tail of the persistent kernel stays short.
+// Processing order: blocks are grouped by score-vector class (max reads per column <= 32 / <= 64 / more) and, inside
+// a class, binned largest-first (LPT) by floor(log2(n_cells * min(n_var, 40))) so the longest serial chains start
+// first and the tail of the persistent kernel stays short.
+__device__ __forceinline__ int order_bin(const BlkMeta& m) {
+    const uint64_t cost = (uint64_t)m.n_cells * min(m.n_var, 40u) + m.n_var;
+    const int cls = m.max_act <= 32 ? 0 : (m.max_act <= 64 ? 1 : 2);
+    return cls * 64 + (63 - (63 - __clzll((long long)(cost | 1ull))));
+}
 __global__ void order_count_kernel(const BlkMeta* meta, uint32_t n, uint32_t* bins) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t cost = (uint64_t)meta[i].n_cells * min(meta[i].n_var, 40u) + meta[i].n_var;
-    const int bin = 63 - __clzll((long long)(cost | 1ull));
-    atomicAdd(&bins[63 - bin], 1u);
+    if (i < n) atomicAdd(&bins[order_bin(meta[i])], 1u);
 }
-__global__ void order_scan_kernel(uint32_t* bins) {
+__global__ void order_scan_kernel(uint32_t* bins, uint32_t* class_info) {
     uint32_t run = 0;
-    for (int i = 0; i < 64; i++) { uint32_t x = bins[i]; bins[i] = run; run += x; }
+    for (int c = 0; c < 3; c++) {
+        class_info[4 + c] = run;
+        for (int i = 0; i < 64; i++) { uint32_t x = bins[c * 64 + i]; bins[c * 64 + i] = run; run += x; }
+        class_info[c] = run - class_info[4 + c];
+    }
 }
 __global__ void order_fill_kernel(const BlkMeta* meta, uint32_t n, uint32_t* bins, uint32_t* order) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t cost = (uint64_t)meta[i].n_cells * min(meta[i].n_var, 40u) + meta[i].n_var;
-    const int bin = 63 - __clzll((long long)(cost | 1ull));
-    order[atomicAdd(&bins[63 - bin], 1u)] = i;
+    if (i < n) order[atomicAdd(&bins[order_bin(meta[i])], 1u)] = i;
 }
 
 static int fail(hp_ctx* ctx, int code, const std::string& msg) {
@@ -87,19 +91,24 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     if (!ctx->meta.reserve(sizeof(BlkMeta) * (size_t)nb) || !ctx->rmeta.reserve(sizeof(ReadMeta) * (size_t)(n_reads + 1)) ||
         !ctx->planes.reserve(8ull * HP_PLANE_STRIDE * n_words) || !ctx->act_off.reserve(4 * n_vb) ||
         !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->col.reserve(4 * (n_cells + 130)) || !ctx->order.reserve(4ull * nb) ||
-        !ctx->heur.reserve(4 * n_vb) || !ctx->ticket.reserve(256 + 4 * 64))
+        !ctx->heur.reserve(4 * n_vb) || !ctx->ticket.reserve(512 + 4 * 192))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "workspace allocation failed");
 
-    int n_ctas = std::min<int>((nb + astar_solve_warps() - 1) / astar_solve_warps(), ctx->sm_count);
+    // team size: use otherwise idle warps for speculative sub-solves (exact, see astar_kernels.cu)
+    const int resident_warps = ctx->sm_count * astar_warps_per_sm();
+    int team = 1;
+    while (team * 2 <= astar_max_team() && (uint64_t)nb * team * 2 <= (uint64_t)resident_warps) team *= 2;
+    if (ctx->force_team > 0) team = std::min(ctx->force_team, astar_max_team());
+    int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)ctx->sm_count * (astar_warps_per_sm() / team));
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     const uint32_t hap_words = (max_block_vars + 63) / 64;
-    const uint64_t slab_bytes = astar_slab_bytes(ctx->qcap, hap_words);
-    if (!ctx->slabs.reserve(slab_bytes * (uint64_t)n_ctas * astar_solve_warps()))
+    const uint64_t slab_bytes = astar_slab_bytes(ctx->qcap, hap_words, ctx->sub_capl);
+    if (!ctx->slabs.reserve(slab_bytes * (uint64_t)n_ctas * team))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "queue slab allocation failed");
 
     HP_CUDA(ctx, cudaMemsetAsync(ctx->act_off.ptr, 0, 4 * n_vb, stream));
     HP_CUDA(ctx, cudaMemsetAsync(ctx->act_cur.ptr, 0, 4 * n_vb, stream));
-    HP_CUDA(ctx, cudaMemsetAsync(ctx->ticket.ptr, 0, 256 + 4 * 64, stream));
+    HP_CUDA(ctx, cudaMemsetAsync(ctx->ticket.ptr, 0, 512 + 4 * 192, stream));
 
     PrepArgs pa;
     pa.n_blocks = nb; pa.var_off = batch->var_off; pa.read_off = batch->read_off; pa.read_start = batch->read_start;
@@ -110,10 +119,11 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     HP_CUDA(ctx, launch_astar_prep(pa, stream));
     ctx->launches++;
 
-    uint32_t* bins = (uint32_t*)((uint8_t*)ctx->ticket.ptr + 256);
+    uint32_t* class_info = (uint32_t*)((uint8_t*)ctx->ticket.ptr + 256);
+    uint32_t* bins = (uint32_t*)((uint8_t*)ctx->ticket.ptr + 512);
     const int tb = 256, gb = (nb + tb - 1) / tb;
     order_count_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins);
-    order_scan_kernel<<<1, 1, 0, stream>>>(bins);
+    order_scan_kernel<<<1, 1, 0, stream>>>(bins, class_info);
     order_fill_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins, (uint32_t*)ctx->order.ptr);
     HP_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
@@ -122,7 +132,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     a.n_blocks = nb;
     a.alleles = batch->alleles; a.quals = batch->quals; a.ignored = batch->ignored; a.is_snv = batch->is_snv;
     a.meta = pa.meta; a.rmeta = pa.rmeta; a.planes = pa.planes; a.act_off = pa.act_off; a.act_idx = pa.act_idx; a.col = pa.col;
-    a.order = (uint32_t*)ctx->order.ptr;
+    a.order = (uint32_t*)ctx->order.ptr; a.class_info = class_info;
     a.heur = (uint32_t*)ctx->heur.ptr; a.ticket = (uint32_t*)ctx->ticket.ptr;
     a.slabs = (uint8_t*)ctx->slabs.ptr; a.slab_bytes = slab_bytes; a.qcap = ctx->qcap; a.hap_words = hap_words;
     a.min_queue_size = ctx->params.min_queue_size; a.queue_increment = ctx->params.queue_increment;
@@ -131,14 +141,14 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     a.out_heur = out->heuristic; a.out_counters = (uint64_t*)out->counters;
     a.dbg_cycles = nullptr;
     if (out->counters && ctx->want_dbg) {
-        if (!ctx->dbg.reserve(32ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
+        if (!ctx->dbg.reserve(64ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
         a.dbg_cycles = (uint64_t*)ctx->dbg.ptr; ctx->dbg_blocks = nb;
     }
 
     HP_CUDA(ctx, cudaEventRecord(ctx->ev0, stream));
-    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, stream));
+    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, team, stream));
     HP_CUDA(ctx, cudaEventRecord(ctx->ev1, stream));
-    ctx->launches++;
+    ctx->launches += 3;
     ctx->timing_pending = true;
     return HP_OK;
 }
@@ -180,7 +190,7 @@ int hp_ctx_create(const hp_params* params, int device, hp_ctx** out_ctx) {
     if (4 * max_visits + 2 >= (1u << 20)) return fail(nullptr, HP_ERR_UNSUPPORTED, "sub-solver visit budget exceeds the 20-bit node index");
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, HP_ERR_CUDA, "cudaSetDevice failed");
     const uint32_t capl = sub_capl_for(p);
-    if (astar_smem_bytes(capl) > (size_t)prop.sharedMemPerBlockOptin)
+    if (astar_smem_bytes(capl, astar_max_team()) > (size_t)prop.sharedMemPerBlockOptin)
         return fail(nullptr, HP_ERR_UNSUPPORTED, "sub-solver queue does not fit shared memory for these parameters");
 
     hp_ctx* ctx = new hp_ctx();
@@ -211,10 +221,11 @@ void hp_ctx_destroy(hp_ctx* ctx) {
 uint64_t hp_launch_count(const hp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // Not part of the public header: per-block phase cycles of the last counting run (profiling aid for bench/profiles).
+int hp_debug_set_team(hp_ctx* ctx, int team) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->force_team = team; return HP_OK; }
 int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
 int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
     if (!ctx || !out || n_blocks > ctx->dbg_blocks || !ctx->dbg.ptr) return HP_ERR_INVALID_INPUT;
-    if (cudaMemcpy(out, ctx->dbg.ptr, 32ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
+    if (cudaMemcpy(out, ctx->dbg.ptr, 64ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
     return HP_OK;
 }
 
@@ -357,7 +368,7 @@ int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out
         so.h1 = h1.data(); so.h2 = h2.data(); so.stats = stats.data(); so.status = status.data();
         so.heuristic = out->heuristic ? heur.data() : nullptr; so.counters = out->counters ? ctr.data() : nullptr;
         // keep the slab arena under ~24 GB
-        const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64) * astar_solve_warps();
+        const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64, ctx->sub_capl) * astar_max_team();
         int max_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>(ctx->sm_count, (24ull << 30) / std::max<uint64_t>(slab, 1)));
         rc = astar_host_once(ctx, &sb, &so, sub_max, max_ctas);
         if (rc != HP_OK) { ctx->qcap = qcap0; return rc; }

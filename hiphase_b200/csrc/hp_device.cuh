@@ -47,10 +47,11 @@ struct AstarArgs {
     const uint32_t* act_off;     // [n_vars + n_blocks] per block N+1 offsets (relative to cell_base) into act_idx
     const uint32_t* act_idx;     // [n_cells] block-relative read index of each (variant, covering read) pair
     const uint32_t* col;         // [n_cells] column record of the same pair: qual | allele<<8 | ends<<10 | carry<<16
-    const uint32_t* order;       // [n_blocks] processing order (largest first)
+    const uint32_t* order;       // [n_blocks] processing order: grouped by score-vector class, largest first inside a class
+    const uint32_t* class_info;  // [8]: class_count[0..2], pad, class_start[0..2], pad (class 0: K=1, 1: K=2, 2: K=0)
     // scratch
     uint32_t* heur;              // [n_vars + n_blocks] H[] per block (u32 is exact: total quals < 2^31 is enforced)
-    uint32_t* ticket;            // work-queue counter
+    uint32_t* ticket;            // work-queue counters, one per class
     uint8_t*  slabs;             // per-warp main-queue slabs
     uint64_t  slab_bytes;
     uint32_t  qcap;              // main-queue capacity per warp (entries, multiple of 32)
@@ -66,7 +67,7 @@ struct AstarArgs {
     int32_t*  out_status;        // [n_blocks]
     uint64_t* out_heur;          // optional [n_vars + n_blocks]
     uint64_t* out_counters;      // optional [n_blocks * 4]
-    uint64_t* dbg_cycles;        // optional [n_blocks * 4]: cycles in pre-pass, cycles in main loop, pops in each (counting variant)
+    uint64_t* dbg_cycles;        // optional [n_blocks * 8]: cycles pre-pass / main, pops pre-pass / main, rounds, barrier-wait cycles, team
 };
 
 // Arguments of astar_prep_kernel.

@@ -21,11 +21,12 @@ struct DevBuf {
 };
 
 // kernel launchers (astar_kernels.cu)
-size_t astar_smem_bytes(uint32_t sub_capl);
-int astar_solve_warps();
-uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words);
+size_t astar_smem_bytes(uint32_t sub_capl, int team);
+int astar_max_team();
+int astar_warps_per_sm();
+uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl);
 cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream);
-cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, cudaStream_t stream);
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t stream);
 
 }  // namespace hp
 
@@ -35,6 +36,7 @@ struct hp_ctx {
     int sm_count = 0;
     uint32_t sub_capl = 0;
     uint32_t qcap = 0;
+    int force_team = 0;                     // 0 = choose from the batch size; 1/2/4 = fixed team size
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;

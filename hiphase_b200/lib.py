@@ -89,6 +89,10 @@ class Context:
     def handle(self):
         return self._h
 
+    def set_team(self, team):
+        """Profiling / test aid: force the speculative team size of the A* kernel (0 = automatic, 1, 2 or 4)."""
+        self.check(lib().hp_debug_set_team(self._h, int(team)))
+
     def launch_count(self):
         return int(lib().hp_launch_count(self._h))
 

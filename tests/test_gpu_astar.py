@@ -47,6 +47,19 @@ def test_c2_subset(ctx):
     run_both(ctx, synth.config_c2(n_blocks=64))
 
 
+@pytest.mark.parametrize("team", [1, 2, 4])
+def test_speculative_teams_are_exact(team):
+    # warp i of a team solves variant v-i speculatively; whatever the team size, results equal the serial chain
+    c = lib.Context(device=0)
+    c.set_team(team)
+    for batch in (synth.config_c2(n_blocks=24), synth.config_c3(n_blocks=16),
+                  A.BlockBatch.from_blocks(_rand_blocks(31, 60, 1, 90, p_err=0.15))):
+        out = c.astar_solve_batch(batch, want_heuristic=True, want_counters=True)
+        ref = O.astar_solve(batch, threads=8)
+        assert_parity(batch, out, ref)
+    c.close()
+
+
 def test_c2_dense_subset(ctx):
     run_both(ctx, synth.config_c2_dense(n_blocks=6))
 
@@ -55,7 +68,7 @@ def test_c3_subset_mixed_sizes(ctx):
     run_both(ctx, synth.config_c3(n_blocks=48))
 
 
-def _rand_blocks(seed, n, nlo, nhi, smax_hi=14, p_err=0.05, p_amb=0.05, p_gap=0.03):
+def _rand_blocks(seed, n, nlo, nhi, smax_hi=14, p_err=0.05, p_amb=0.05, p_gap=0.03):   # noqa: E302
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n):
