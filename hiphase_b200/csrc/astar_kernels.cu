@@ -333,6 +333,9 @@ struct WarpCtx {
     uint32_t capl_s;        // of which in shared memory
     uint32_t lane;
     uint32_t h_floor;       // speculation: H[] entries below this index are not known yet and read as H[h_floor]
+    uint64_t* mq_hi;        // main queue: the first mq_cap_s keys of every stripe live in the CTA's shared memory
+    uint32_t* mq_idx;       //   (the sub-solver queues of the whole team are idle while warp 0 runs the main loop)
+    uint32_t mq_cap_s;
     // counters
     uint64_t evals, sum_lp, pops, cells;
     int status;
@@ -847,13 +850,13 @@ __device__ __forceinline__ MainKey wmin96(uint64_t hi, uint32_t idx) {
 }
 
 // warp-cooperative scan of stripe `owner` (cnt_o entries) -> its minimum and position; valid on every lane
-__device__ __forceinline__ void stripe_min(const Slab& s, uint32_t scap, int owner, uint32_t cnt_o, uint32_t lane,
+template <class HiAt, class IdxAt>
+__device__ __forceinline__ void stripe_min(HiAt khi_at, IdxAt kidx_at, int owner, uint32_t cnt_o, uint32_t lane,
                                            uint64_t& out_hi, uint32_t& out_idx, uint32_t& out_pos) {
     uint64_t bhi = ~0ull; uint32_t bidx = 0xffffffffu, bpos = 0;
-    const uint32_t b0 = owner * scap;
     for (uint32_t i = lane; i < cnt_o; i += 32) {
-        const uint64_t hi = s.khi[b0 + i];
-        const uint32_t idx = s.kidx[b0 + i];
+        const uint64_t hi = *khi_at(owner, i);
+        const uint32_t idx = *kidx_at(owner, i);
         if (key_less(hi, idx, bhi, bidx)) { bhi = hi; bidx = idx; bpos = i; }
     }
     const MainKey mk = wmin96(bhi, bidx);
@@ -878,6 +881,10 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     const uint32_t* col = a.col + m.cell_base;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
     const uint8_t* ign = a.ignored + m.var_base;
+    // key (hi, idx) of entry i of a stripe: shared memory for the first mq_cap_s entries, the slab beyond
+    uint64_t* const mq_hi = w.mq_hi; uint32_t* const mq_idx = w.mq_idx; const uint32_t mqs = w.mq_cap_s;
+    auto khi_at = [&](uint32_t stripe, uint32_t i) -> uint64_t* { return i < mqs ? mq_hi + stripe * mqs + i : s.khi + stripe * scap + i; };
+    auto kidx_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_idx + stripe * mqs + i : s.kidx + stripe * scap + i; };
 
     // tracker (PQueueHapTracker, :171-231): counts in the slab, totals in registers
     for (uint32_t i = lane; i <= N; i += 32) s.lencnt[i] = 0u;
@@ -910,7 +917,7 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint32_t e = lane * scap + cnt;
-                    s.khi[e] = cur_hi; s.kidx[e] = cur_idx; s.klen[e] = cur_len | (cur_ident ? 0x80000000u : 0u);
+                    *khi_at(lane, cnt) = cur_hi; *kidx_at(lane, cnt) = cur_idx; s.klen[e] = cur_len | (cur_ident ? 0x80000000u : 0u);
                     s.kfrozen[e] = cur_frozen; s.krec[e] = cur_rec;
                     if (key_less(cur_hi, cur_idx, c_hi, c_idx)) { c_hi = cur_hi; c_idx = cur_idx; c_pos = cnt; }
                     cnt++;
@@ -932,14 +939,14 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                 cnt--;
                 if (pos != cnt) {
                     const uint32_t last = owner * scap + cnt;
-                    s.khi[slot] = s.khi[last]; s.kidx[slot] = s.kidx[last]; s.klen[slot] = s.klen[last];
+                    *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt); s.klen[slot] = s.klen[last];
                     s.kfrozen[slot] = s.kfrozen[last]; s.krec[slot] = s.krec[last];
                 }
             }
             __syncwarp();
             {
                 uint64_t nhi; uint32_t nidx, npos;
-                stripe_min(s, scap, owner, cnt_o, lane, nhi, nidx, npos);
+                stripe_min(khi_at, kidx_at, owner, cnt_o, lane, nhi, nidx, npos);
                 if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
             }
             qmin = wmin96(c_hi, c_idx);
@@ -1062,7 +1069,7 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                     const uint32_t fr = cur_frozen + ((c == 0) ? fro[0] : (c == 1) ? fro[1] : (c == 2) ? fro[2] : fro[3]);
                     const uint32_t rc = (c == 0) ? crec[0] : (c == 1) ? crec[1] : (c == 2) ? crec[2] : crec[3];
                     const uint32_t e = lane * scap + cnt;
-                    s.khi[e] = hi; s.kidx[e] = ix; s.klen[e] = (L + 1) | cident; s.kfrozen[e] = fr; s.krec[e] = rc;
+                    *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = ix; s.klen[e] = (L + 1) | cident; s.kfrozen[e] = fr; s.krec[e] = rc;
                     if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = cnt; }
                     cnt++;
                 }
@@ -1076,7 +1083,7 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                         if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                         if (lane == target) {
                             const uint32_t e = lane * scap + cnt;
-                            s.khi[e] = khi[cc]; s.kidx[e] = kix[cc];
+                            *khi_at(lane, cnt) = khi[cc]; *kidx_at(lane, cnt) = kix[cc];
                             s.klen[e] = (L + 1) | ((cur_ident && cc >= 2u) ? 0x80000000u : 0u);
                             s.kfrozen[e] = cur_frozen + fro[cc]; s.krec[e] = crec[cc];
                             if (key_less(khi[cc], kix[cc], c_hi, c_idx)) { c_hi = khi[cc]; c_idx = kix[cc]; c_pos = cnt; }
@@ -1116,9 +1123,9 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                 const uint32_t b0 = lane * scap;
                 c_hi = ~0ull; c_idx = 0xffffffffu; c_pos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
-                    uint64_t hi = s.khi[b0 + i];
-                    const uint32_t ix = s.kidx[b0 + i];
-                    if ((s.klen[b0 + i] & 0x7fffffffu) < min_progress) { hi &= 0xffffffffull; s.khi[b0 + i] = hi; }
+                    uint64_t hi = *khi_at(lane, i);
+                    const uint32_t ix = *kidx_at(lane, i);
+                    if ((s.klen[b0 + i] & 0x7fffffffu) < min_progress) { hi &= 0xffffffffull; *khi_at(lane, i) = hi; }
                     if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = i; }
                 }
                 __syncwarp();
@@ -1305,10 +1312,15 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     w.h_floor = 0;
     w.evals = w.sum_lp = w.pops = w.cells = 0;
 
-    const uint32_t gwarp = blockIdx.x * team + warp;
-    uint8_t* my_slab = a.slabs + (uint64_t)gwarp * a.slab_bytes;
+    // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp
+    uint8_t* my_slab = a.slabs + (uint64_t)blockIdx.x * a.slab_bytes;
     const Slab slab = carve_slab(my_slab, a.qcap, a.hap_words);
-    w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)32 * (w.capl - w.capl_s) * sizeof(SubEntry));
+    const uint64_t spill_bytes = (uint64_t)32 * (w.capl - w.capl_s) * sizeof(SubEntry);
+    w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)(kMaxTeam - warp) * spill_bytes);
+    // main-queue keys reuse the whole team's sub-queue shared memory (12 B per key)
+    w.mq_cap_s = (uint32_t)(((size_t)team * w.capl_s * 32 * sizeof(SubEntry)) / (32 * 12));
+    w.mq_hi = (uint64_t*)smem_raw;
+    w.mq_idx = (uint32_t*)(smem_raw + (size_t)32 * w.mq_cap_s * 8);
 
     for (;;) {
         __syncthreads();
@@ -1358,7 +1370,7 @@ int astar_max_team() { return kMaxTeam; }
 int astar_warps_per_sm() { return 16; }
 uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl) {
     const uint32_t capl_s = std::min<uint32_t>(sub_capl, kSubCaplShared);
-    const uint64_t spill = (uint64_t)32 * (sub_capl - capl_s) * sizeof(SubEntry);
+    const uint64_t spill = (uint64_t)kMaxTeam * 32 * (sub_capl - capl_s) * sizeof(SubEntry);
     return ((slab_bytes_for(qcap, hap_words) + spill + 255) & ~255ull);
 }
 

@@ -103,7 +103,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     const uint32_t hap_words = (max_block_vars + 63) / 64;
     const uint64_t slab_bytes = astar_slab_bytes(ctx->qcap, hap_words, ctx->sub_capl);
-    if (!ctx->slabs.reserve(slab_bytes * (uint64_t)n_ctas * team))
+    if (!ctx->slabs.reserve(slab_bytes * (uint64_t)n_ctas))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "queue slab allocation failed");
 
     HP_CUDA(ctx, cudaMemsetAsync(ctx->act_off.ptr, 0, 4 * n_vb, stream));
@@ -368,7 +368,7 @@ int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out
         so.h1 = h1.data(); so.h2 = h2.data(); so.stats = stats.data(); so.status = status.data();
         so.heuristic = out->heuristic ? heur.data() : nullptr; so.counters = out->counters ? ctr.data() : nullptr;
         // keep the slab arena under ~24 GB
-        const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64, ctx->sub_capl) * astar_max_team();
+        const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64, ctx->sub_capl);
         int max_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>(ctx->sm_count, (24ull << 30) / std::max<uint64_t>(slab, 1)));
         rc = astar_host_once(ctx, &sb, &so, sub_max, max_ctas);
         if (rc != HP_OK) { ctx->qcap = qcap0; return rc; }
