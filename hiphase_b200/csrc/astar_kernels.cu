@@ -907,9 +907,12 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     bool cur_ident = true, have_cur = true;
     ExpCache<K> cache;
     cache.first_idx = 0xffffffffu; cache.present = 0;
+    long long tm_pop = 0, tm_exp = 0, tm_rest = 0, n_real = 0, t0 = 0;   // counting variant only
 
     for (;;) {
+        if (kCount) t0 = clock64();
         if (!have_cur || key_less(qmin.hi, qmin.idx, cur_hi, cur_idx)) {
+            n_real++;
             if (have_cur) {                                              // cur goes back to the queue
                 const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
                 if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
@@ -952,6 +955,7 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
             qmin = wmin96(c_hi, c_idx);
             have_cur = true;
         }
+        if (kCount) { const long long t1 = clock64(); tm_pop += t1 - t0; t0 = t1; }
         // ---- cur is the top ----
         const uint32_t L = cur_len;
         const uint32_t total = (uint32_t)(cur_hi >> 32);
@@ -1005,6 +1009,7 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         const uint32_t present = present_mask(bad_col, cur_ident);
         const uint32_t nchild = __popc(present);
         cache.first_idx = next_idx; cache.present = present;
+        if (kCount) { const long long t1 = clock64(); tm_exp += t1 - t0; t0 = t1; }
         if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
         if (bad_col && cur_frozen + tot[2] + heur != total) { w.status = HP_BLOCK_ASSERT; break; }   // :529
         if (qsize + nchild + 64 > a.qcap || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
@@ -1132,6 +1137,11 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                 qmin = wmin96(c_hi, c_idx);
             }
         }
+        if (kCount) { const long long t1 = clock64(); tm_rest += t1 - t0; t0 = t1; }
+    }
+    if (kCount && a.dbg_cycles && lane == 0) {
+        uint64_t* d = a.dbg_cycles + 16ull * blk;
+        d[8] = tm_pop; d[9] = tm_exp; d[10] = tm_rest; d[13] = n_real; d[14] = num_pruned; d[15] = qsize;
     }
     if (w.status != HP_BLOCK_OK) return;
 
@@ -1275,14 +1285,9 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
                                  ((uint64_t)__reduce_add_sync(HP_FULL_MASK, (uint32_t)(w.cells >> 32)) << 32);
             if (w.lane == 0) {
                 if (a.dbg_cycles) {
-                    a.dbg_cycles[8ull * blk + 0] = (uint64_t)(t_mid - t_start);
-                    a.dbg_cycles[8ull * blk + 1] = (uint64_t)(clock64() - t_mid);
-                    a.dbg_cycles[8ull * blk + 2] = ts.ctr[3];
-                    a.dbg_cycles[8ull * blk + 3] = w.pops;
-                    a.dbg_cycles[8ull * blk + 4] = n_rounds;
-                    a.dbg_cycles[8ull * blk + 5] = (uint64_t)t_wait;
-                    a.dbg_cycles[8ull * blk + 6] = team;
-                    a.dbg_cycles[8ull * blk + 7] = 0;
+                    uint64_t* d = a.dbg_cycles + 16ull * blk;
+                    d[0] = (uint64_t)(t_mid - t_start); d[1] = (uint64_t)(clock64() - t_mid); d[2] = ts.ctr[3]; d[3] = w.pops;
+                    d[4] = n_rounds; d[5] = team; d[6] = (uint64_t)t_wait;
                 }
                 ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;
             }

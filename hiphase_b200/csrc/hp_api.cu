@@ -141,7 +141,7 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     a.out_heur = out->heuristic; a.out_counters = (uint64_t*)out->counters;
     a.dbg_cycles = nullptr;
     if (out->counters && ctx->want_dbg) {
-        if (!ctx->dbg.reserve(64ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
+        if (!ctx->dbg.reserve(128ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
         a.dbg_cycles = (uint64_t*)ctx->dbg.ptr; ctx->dbg_blocks = nb;
     }
 
@@ -225,7 +225,7 @@ int hp_debug_set_team(hp_ctx* ctx, int team) { if (!ctx) return HP_ERR_INVALID_I
 int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
 int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
     if (!ctx || !out || n_blocks > ctx->dbg_blocks || !ctx->dbg.ptr) return HP_ERR_INVALID_INPUT;
-    if (cudaMemcpy(out, ctx->dbg.ptr, 64ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
+    if (cudaMemcpy(out, ctx->dbg.ptr, 128ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
     return HP_OK;
 }
 

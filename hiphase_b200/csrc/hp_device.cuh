@@ -67,7 +67,7 @@ struct AstarArgs {
     int32_t*  out_status;        // [n_blocks]
     uint64_t* out_heur;          // optional [n_vars + n_blocks]
     uint64_t* out_counters;      // optional [n_blocks * 4]
-    uint64_t* dbg_cycles;        // optional [n_blocks * 8]: cycles pre-pass / main, pops pre-pass / main, rounds, barrier-wait cycles, team
+    uint64_t* dbg_cycles;        // optional [n_blocks * 16]: per-block phase cycles / pops / rounds / team, main-loop split (counting variant)
 };
 
 // Arguments of astar_prep_kernel.

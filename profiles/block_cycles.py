@@ -24,7 +24,7 @@ print("main    : cycles/pop mean %.0f  cycles/block mean %.3g max %.3g" % ((d[:,
 tot = d[:, 0] + d[:, 1]
 print("sum pre-pass %.3g  sum main %.3g  slowest block %.3g cycles" % (d[:, 0].sum(), d[:, 1].sum(), tot.max()))
 print("5 slowest blocks: [total, pre-pass, main cycles | pops pre-pass, main | variants/round] then main split "
-      "[real-pop, expand, records, push, prune cycles | real pops, pruned, final queue]")
+      "[real-pop, expand, rest (records+push+prune) cycles | real pops, pruned, final queue]")
 for k in np.argsort(tot)[-5:]:
     print("  ", [int(tot[k]), int(d[k, 0]), int(d[k, 1])], [int(d[k, 2]), int(d[k, 3])], "%.2f" % (nvar[k] / d[k, 4]),
-          d[k, 8:13].astype(np.int64).tolist(), d[k, 13:16].astype(np.int64).tolist())
+          d[k, 8:11].astype(np.int64).tolist(), d[k, 13:16].astype(np.int64).tolist())
