@@ -325,6 +325,8 @@ struct __align__(16) SubEntry {
     uint32_t frozen, pad;
 };
 
+constexpr uint32_t kFreeStack = 192;   // free main-queue record slots kept in shared memory
+
 struct WarpCtx {
     SubEntry* sq;           // this warp's sub-solver queue: first capl_s entries of every stripe, in shared memory
     SubEntry* sq_spill;     // ... and the rest of every stripe in the warp's global slab (rarely touched)
@@ -335,7 +337,10 @@ struct WarpCtx {
     uint32_t h_floor;       // speculation: H[] entries below this index are not known yet and read as H[h_floor]
     uint64_t* mq_hi;        // main queue: the first mq_cap_s keys of every stripe live in the CTA's shared memory
     uint32_t* mq_idx;       //   (the sub-solver queues of the whole team are idle while warp 0 runs the main loop)
+    uint32_t* mq_len;       //   key = (hi, idx); len = length | identical flag << 31; rec = record slot of the node
+    uint32_t* mq_rec;
     uint32_t mq_cap_s;
+    uint32_t* free_stack;   // small stack of free record slots in shared memory (overflow: slab free list)
     // counters
     uint64_t evals, sum_lp, pops, cells;
     int status;
@@ -885,6 +890,10 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     uint64_t* const mq_hi = w.mq_hi; uint32_t* const mq_idx = w.mq_idx; const uint32_t mqs = w.mq_cap_s;
     auto khi_at = [&](uint32_t stripe, uint32_t i) -> uint64_t* { return i < mqs ? mq_hi + stripe * mqs + i : s.khi + stripe * scap + i; };
     auto kidx_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_idx + stripe * mqs + i : s.kidx + stripe * scap + i; };
+    uint32_t* const mq_len = w.mq_len; uint32_t* const mq_rec = w.mq_rec;
+    auto klen_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_len + stripe * mqs + i : s.klen + stripe * scap + i; };
+    auto krec_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_rec + stripe * mqs + i : s.krec + stripe * scap + i; };
+    // the frozen cost of a queued node lives at s.kfrozen[record slot] (stable while the entry moves inside its stripe)
 
     // tracker (PQueueHapTracker, :171-231): counts in the slab, totals in registers
     for (uint32_t i = lane; i <= N; i += 32) s.lencnt[i] = 0u;
@@ -896,6 +905,7 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     uint64_t num_pruned = 0;
     uint32_t next_idx = 1, rr = 0, qsize = 1;                            // qsize = pqueue.len() (cur included)
     uint32_t free_top = 0, rec_next = 1;                                 // record 0 = root
+    uint32_t fs_top = 0;                                                 // entries in the shared-memory free stack
     if (lane == 0) atomicAdd(s.lencnt + 0, 1u);
 
     // per-lane cached stripe minimum + warp-uniform queue minimum
@@ -905,6 +915,8 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     uint64_t cur_hi = ((uint64_t)Hg[0] << 32) | 0xffffffffull;
     uint32_t cur_idx = 0, cur_len = 0, cur_frozen = 0, cur_rec = 0;
     bool cur_ident = true, have_cur = true;
+    uint64_t cur_w1 = 0, cur_w2 = 0;                                     // lane wi: words wi of cur's h1 / h2 (when HW <= 32)
+    const bool regs_hap = HW <= 32;
     ExpCache<K> cache;
     cache.first_idx = 0xffffffffu; cache.present = 0;
     long long tm_pop = 0, tm_exp = 0, tm_rest = 0, n_real = 0, t0 = 0;   // counting variant only
@@ -919,9 +931,8 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                 uint32_t target = rr & 31u; rr++;
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
-                    const uint32_t e = lane * scap + cnt;
-                    *khi_at(lane, cnt) = cur_hi; *kidx_at(lane, cnt) = cur_idx; s.klen[e] = cur_len | (cur_ident ? 0x80000000u : 0u);
-                    s.kfrozen[e] = cur_frozen; s.krec[e] = cur_rec;
+                    *khi_at(lane, cnt) = cur_hi; *kidx_at(lane, cnt) = cur_idx; *klen_at(lane, cnt) = cur_len | (cur_ident ? 0x80000000u : 0u);
+                    *krec_at(lane, cnt) = cur_rec; s.kfrozen[cur_rec] = cur_frozen;
                     if (key_less(cur_hi, cur_idx, c_hi, c_idx)) { c_hi = cur_hi; c_idx = cur_idx; c_pos = cnt; }
                     cnt++;
                 }
@@ -931,19 +942,25 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
             if (qmin.hi == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }   // empty queue: the reference panics (:631)
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, c_hi == qmin.hi && c_idx == qmin.idx)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, c_pos, owner);
-            const uint32_t slot = owner * scap + pos;
             cur_hi = qmin.hi; cur_idx = qmin.idx;
-            const uint32_t lenf = s.klen[slot];
+            const uint32_t lenf = *klen_at(owner, pos);
             cur_len = lenf & 0x7fffffffu; cur_ident = (lenf >> 31) != 0;
-            cur_frozen = s.kfrozen[slot]; cur_rec = s.krec[slot];
+            cur_rec = *krec_at(owner, pos);
+            if (cur_len >= min_progress) {                                // a pruned node never needs its payload
+                cur_frozen = s.kfrozen[cur_rec];
+                if (regs_hap) {
+                    const uint64_t* r = s.recs + (uint64_t)cur_rec * 2 * HW;
+                    const bool own = lane < ((cur_len + 63) >> 6);
+                    cur_w1 = own ? r[lane] : 0ull; cur_w2 = own ? r[HW + lane] : 0ull;
+                }
+            }
             const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
             __syncwarp();
             if ((int)lane == owner) {
                 cnt--;
                 if (pos != cnt) {
-                    const uint32_t last = owner * scap + cnt;
-                    *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt); s.klen[slot] = s.klen[last];
-                    s.kfrozen[slot] = s.kfrozen[last]; s.krec[slot] = s.krec[last];
+                    *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt);
+                    *klen_at(owner, pos) = *klen_at(owner, cnt); *krec_at(owner, pos) = *krec_at(owner, cnt);
                 }
             }
             __syncwarp();
@@ -972,8 +989,8 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         if (L < min_progress) {                                           // :507-515
             if (num_pruned == 0) curr_thresh = a.min_queue_size;
             num_pruned++;
-            if (lane == 0) s.freelist[free_top] = cur_rec;
-            free_top++;
+            if (fs_top < kFreeStack) { if (lane == 0) w.free_stack[fs_top] = cur_rec; fs_top++; }
+            else { if (lane == 0) s.freelist[free_top] = cur_rec; free_top++; }
             have_cur = false;
             __syncwarp();
             continue;
@@ -1034,7 +1051,13 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         {
             const uint32_t nsib = nchild - 1;
             uint32_t mine = 0;
-            if (lane < nsib) mine = (lane < free_top) ? s.freelist[free_top - 1 - lane] : rec_next + (lane - min(free_top, nsib));
+            const uint32_t from_fs = min(nsib, fs_top);                   // shared-memory stack first, then the slab list, then fresh
+            const uint32_t from_gl = min(nsib - from_fs, free_top);
+            if (lane < nsib) {
+                if (lane < from_fs) mine = w.free_stack[fs_top - 1 - lane];
+                else if (lane - from_fs < from_gl) mine = s.freelist[free_top - 1 - (lane - from_fs)];
+                else mine = rec_next + (lane - from_fs - from_gl);
+            }
             uint32_t ordinal = 0;
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) {
@@ -1042,15 +1065,15 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                 crec[c] = sib ? __shfl_sync(HP_FULL_MASK, mine, ordinal & 31u) : cur_rec;
                 if (sib) ordinal++;
             }
-            const uint32_t from_free = min(nsib, free_top);
-            free_top -= from_free; rec_next += nsib - from_free;
+            fs_top -= from_fs; free_top -= from_gl; rec_next += nsib - from_fs - from_gl;
         }
         {
             const int wl = (int)(L >> 6);
             const uint64_t bit = bad_col ? 0ull : (1ull << (L & 63));
             for (int wi = lane; wi <= wl; wi += 32) {
                 uint64_t w1 = 0, w2 = 0;
-                if (wi < nwords) { w1 = prow[wi]; w2 = prow[HW + wi]; }
+                if (regs_hap) { w1 = cur_w1; w2 = cur_w2; }
+                else if (wi < nwords) { w1 = prow[wi]; w2 = prow[HW + wi]; }
 #pragma unroll
                 for (uint32_t c = 0; c < 4; c++) {
                     if (((present >> c) & 1u) && (c != best || wi == wl)) {   // best: only the word that changes
@@ -1073,8 +1096,8 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                     const uint32_t ix = (c == 0) ? kix[0] : (c == 1) ? kix[1] : (c == 2) ? kix[2] : kix[3];
                     const uint32_t fr = cur_frozen + ((c == 0) ? fro[0] : (c == 1) ? fro[1] : (c == 2) ? fro[2] : fro[3]);
                     const uint32_t rc = (c == 0) ? crec[0] : (c == 1) ? crec[1] : (c == 2) ? crec[2] : crec[3];
-                    const uint32_t e = lane * scap + cnt;
-                    *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = ix; s.klen[e] = (L + 1) | cident; s.kfrozen[e] = fr; s.krec[e] = rc;
+                    *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = ix; *klen_at(lane, cnt) = (L + 1) | cident;
+                    *krec_at(lane, cnt) = rc; s.kfrozen[rc] = fr;
                     if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = cnt; }
                     cnt++;
                 }
@@ -1087,10 +1110,9 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
                         uint32_t target = (rr + cc) & 31u;
                         if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                         if (lane == target) {
-                            const uint32_t e = lane * scap + cnt;
                             *khi_at(lane, cnt) = khi[cc]; *kidx_at(lane, cnt) = kix[cc];
-                            s.klen[e] = (L + 1) | ((cur_ident && cc >= 2u) ? 0x80000000u : 0u);
-                            s.kfrozen[e] = cur_frozen + fro[cc]; s.krec[e] = crec[cc];
+                            *klen_at(lane, cnt) = (L + 1) | ((cur_ident && cc >= 2u) ? 0x80000000u : 0u);
+                            *krec_at(lane, cnt) = crec[cc]; s.kfrozen[crec[cc]] = cur_frozen + fro[cc];
                             if (key_less(khi[cc], kix[cc], c_hi, c_idx)) { c_hi = khi[cc]; c_idx = kix[cc]; c_pos = cnt; }
                             cnt++;
                         }
@@ -1112,6 +1134,11 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
             const uint32_t bf = (best == 0) ? fro[0] : (best == 1) ? fro[1] : (best == 2) ? fro[2] : fro[3];
             cur_hi = khi[best]; cur_idx = kix[best]; cur_len = L + 1; cur_frozen += bf;
             cur_ident = cur_ident && best >= 2u;
+            if (regs_hap && !bad_col && lane == (L >> 6)) {
+                const uint64_t b = 1ull << (L & 63);
+                if (best == 1u || best == 3u) cur_w1 |= b;
+                if (best == 0u || best == 3u) cur_w2 |= b;
+            }
         }
         __syncwarp();
 
@@ -1125,12 +1152,11 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
             if (qsize > max_queue) {
                 // "full prune": every queued entry shorter than min_progress gets the cleared priority (cost 0);
                 // cur has length >= next_expected >= min_progress and is never affected
-                const uint32_t b0 = lane * scap;
                 c_hi = ~0ull; c_idx = 0xffffffffu; c_pos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
                     uint64_t hi = *khi_at(lane, i);
                     const uint32_t ix = *kidx_at(lane, i);
-                    if ((s.klen[b0 + i] & 0x7fffffffu) < min_progress) { hi &= 0xffffffffull; *khi_at(lane, i) = hi; }
+                    if ((*klen_at(lane, i) & 0x7fffffffu) < min_progress) { hi &= 0xffffffffull; *khi_at(lane, i) = hi; }
                     if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = i; }
                 }
                 __syncwarp();
@@ -1184,6 +1210,7 @@ struct TeamShared {
     int32_t final_status;
     unsigned long long ctr[4];       // accepted work counters (evals, cells, sum_lp, pops)
     uint32_t hring[64];
+    uint32_t free_stack[kFreeStack];
 };
 
 __device__ __forceinline__ uint64_t bad_window(const uint8_t* ign, uint32_t v, uint32_t N, uint32_t lane) {
@@ -1323,9 +1350,12 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     const uint64_t spill_bytes = (uint64_t)32 * (w.capl - w.capl_s) * sizeof(SubEntry);
     w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)(kMaxTeam - warp) * spill_bytes);
     // main-queue keys reuse the whole team's sub-queue shared memory (12 B per key)
-    w.mq_cap_s = (uint32_t)(((size_t)team * w.capl_s * 32 * sizeof(SubEntry)) / (32 * 12));
+    w.mq_cap_s = (uint32_t)(((size_t)team * w.capl_s * 32 * sizeof(SubEntry)) / (32 * 20));
     w.mq_hi = (uint64_t*)smem_raw;
     w.mq_idx = (uint32_t*)(smem_raw + (size_t)32 * w.mq_cap_s * 8);
+    w.mq_len = w.mq_idx + (size_t)32 * w.mq_cap_s;
+    w.mq_rec = w.mq_len + (size_t)32 * w.mq_cap_s;
+    w.free_stack = ts.free_stack;
 
     for (;;) {
         __syncthreads();
