@@ -1195,6 +1195,418 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
     if (top_total < Hg[0]) w.status = HP_BLOCK_ASSERT;                     // phase_stats.rs:163
 }
 
+// astar_solver main loop, register-resident fast path (K >= 1): the structure of sub_solve_fast (cur in registers,
+// packed-delta totals, child vectors pre-permuted into the next column's slot order, prefetched column records)
+// with the main loop's 96-bit keys, haplotype records, tracker and pruning rules (astar_phaser.rs:480-633).
+template <int K, bool kCount>
+__device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, const Slab& s, uint32_t blk,
+                                const uint32_t* Hg) {
+    const uint32_t lane = w.lane;
+    const uint32_t N = m.n_var;
+    const uint32_t HW = a.hap_words;
+    const uint32_t scap = a.qcap / 32;
+    const uint32_t* aoff = a.act_off + m.var_base + blk;
+    const uint32_t* aidx = a.act_idx + m.cell_base;
+    const uint32_t* col = a.col + m.cell_base;
+    const ReadMeta* rmeta = a.rmeta + m.read_base;
+    const uint8_t* ign = a.ignored + m.var_base;
+    constexpr uint32_t kEmpty = 0xffff0000u;
+    uint64_t* const mq_hi = w.mq_hi; uint32_t* const mq_idx = w.mq_idx; const uint32_t mqs = w.mq_cap_s;
+    uint32_t* const mq_len = w.mq_len; uint32_t* const mq_rec = w.mq_rec;
+    auto khi_at = [&](uint32_t stripe, uint32_t i) -> uint64_t* { return i < mqs ? mq_hi + stripe * mqs + i : s.khi + stripe * scap + i; };
+    auto kidx_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_idx + stripe * mqs + i : s.kidx + stripe * scap + i; };
+    auto klen_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_len + stripe * mqs + i : s.klen + stripe * scap + i; };
+    auto krec_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_rec + stripe * mqs + i : s.krec + stripe * scap + i; };
+
+    for (uint32_t i = lane; i <= N; i += 32) s.lencnt[i] = 0u;
+    __syncwarp();
+    uint32_t trk_total = 1, trk_thresh = 0;                              // root counted (:488)
+    uint32_t curr_thresh = a.min_queue_size;
+    const uint32_t max_queue = 10u * a.min_queue_size;                   // :457
+    uint32_t min_progress = 0, next_expected = 0;
+    uint64_t num_pruned = 0;
+    uint32_t next_idx = 1, rr = 0, qsize = 1;                            // qsize = pqueue.len() (cur included)
+    uint32_t free_top = 0, rec_next = 1, fs_top = 0;                     // record 0 = root
+    if (lane == 0) atomicAdd(s.lencnt + 0, 1u);
+
+    uint64_t c_hi = ~0ull; uint32_t c_idx = 0xffffffffu, c_pos = 0, cnt = 0;
+    MainKey qmin; qmin.hi = ~0ull; qmin.idx = 0xffffffffu;
+    // current top (root, :485-487)
+    uint32_t cur_total = Hg[0], cur_nh = 0xffffffffu, cur_idx = 0, cur_len = 0, cur_frozen = 0, cur_rec = 0;
+    bool cur_ident = true, have_cur = true;
+    int cur_src = SRC_ROOT;
+    uint32_t cur_x1 = 0, cur_x2 = 0;
+    uint32_t heur_p = cur_total;                                         // heuristic term inside cur_total
+    uint64_t cur_w1 = 0, cur_w2 = 0;                                     // lane wi: words wi of cur's h1 / h2 (HW <= 32)
+    const bool regs_hap = HW <= 32;
+    uint32_t nA0[K], nA1[K], nB0[K], nB1[K], nW[K];
+    uint32_t cache_first = 0xffffffffu, cache_present = 0;
+    uint32_t o_p = __ldg(aoff + 0), o_p1 = __ldg(aoff + 1);
+    uint32_t colc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        nA0[k] = nA1[k] = nB0[k] = nB1[k] = nW[k] = 0;
+        colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+    }
+
+    for (;;) {
+        if (!have_cur || key_less(qmin.hi, qmin.idx, ((uint64_t)cur_total << 32) | cur_nh, cur_idx)) {
+            if (have_cur) {                                              // cur goes back to the queue
+                const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
+                if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+                uint32_t target = rr & 31u; rr++;
+                if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                if (lane == target) {
+                    const uint64_t hi = ((uint64_t)cur_total << 32) | cur_nh;
+                    *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = cur_idx; *klen_at(lane, cnt) = cur_len | (cur_ident ? 0x80000000u : 0u);
+                    *krec_at(lane, cnt) = cur_rec; s.kfrozen[cur_rec] = cur_frozen;
+                    if (key_less(hi, cur_idx, c_hi, c_idx)) { c_hi = hi; c_idx = cur_idx; c_pos = cnt; }
+                    cnt++;
+                }
+                __syncwarp();
+            }
+            // ---- real pop ----
+            if (qmin.hi == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }   // empty queue: the reference panics (:631)
+            const int owner = __ffs(__ballot_sync(HP_FULL_MASK, c_hi == qmin.hi && c_idx == qmin.idx)) - 1;
+            const uint32_t pos = __shfl_sync(HP_FULL_MASK, c_pos, owner);
+            cur_total = (uint32_t)(qmin.hi >> 32); cur_nh = (uint32_t)qmin.hi; cur_idx = qmin.idx;
+            const uint32_t lenf = *klen_at(owner, pos);
+            cur_len = lenf & 0x7fffffffu; cur_ident = (lenf >> 31) != 0;
+            cur_rec = *krec_at(owner, pos);
+            if (cur_len >= min_progress && cur_len < N) {                 // pruned / final nodes never need the payload
+                cur_frozen = s.kfrozen[cur_rec];
+                if (regs_hap) {
+                    const uint64_t* r = s.recs + (uint64_t)cur_rec * 2 * HW;
+                    const bool own = lane < ((cur_len + 63) >> 6);
+                    cur_w1 = own ? r[lane] : 0ull; cur_w2 = own ? r[HW + lane] : 0ull;
+                }
+                // re-seat the column state
+                const uint32_t d = cur_idx - cache_first;
+                if (cur_len == 0u) cur_src = SRC_ROOT;
+                else if (d < (uint32_t)__popc(cache_present)) {
+                    const uint32_t cs = slot_of_ordinal(cache_present, d);
+                    cur_src = SRC_CACHE; cur_x1 = cs & 1u; cur_x2 = (0x9u >> cs) & 1u;
+                } else cur_src = SRC_PLANES;
+                heur_p = Hg[cur_len];
+                o_p = __ldg(aoff + cur_len); o_p1 = __ldg(aoff + cur_len + 1);
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+            }
+            const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
+            __syncwarp();
+            if ((int)lane == owner) {
+                cnt--;
+                if (pos != cnt) {
+                    *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt);
+                    *klen_at(owner, pos) = *klen_at(owner, cnt); *krec_at(owner, pos) = *krec_at(owner, cnt);
+                }
+            }
+            __syncwarp();
+            {
+                uint64_t nhi; uint32_t nidx, npos;
+                stripe_min(khi_at, kidx_at, owner, cnt_o, lane, nhi, nidx, npos);
+                if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
+            }
+            qmin = wmin96(c_hi, c_idx);
+            have_cur = true;
+        }
+        // ---- cur is the top ----
+        const uint32_t L = cur_len;
+        if (L >= N) break;                                                // :492
+        qsize--;
+        if (lane == 0) atomicAdd(s.lencnt + L, 0xffffffffu);              // hap_tracker.remove_hap (:495)
+        if (L >= trk_thresh) trk_total--;
+        w.pops++;
+        if (L == next_expected) {                                         // :497-504
+            next_expected++;
+            if (num_pruned == 0) curr_thresh += a.queue_increment;
+        }
+        if (L < min_progress) {                                           // :507-515
+            if (num_pruned == 0) curr_thresh = a.min_queue_size;
+            num_pruned++;
+            if (fs_top < kFreeStack) { if (lane == 0) w.free_stack[fs_top] = cur_rec; fs_top++; }
+            else { if (lane == 0) s.freelist[free_top] = cur_rec; free_top++; }
+            have_cur = false;
+            __syncwarp();
+            continue;
+        }
+
+        // ---- expand column p = L ----
+        const uint32_t p = L;
+        const uint32_t a_cur = o_p1 - o_p;
+        const bool has_next = p + 1 < N;
+        const uint32_t o_p2 = has_next ? __ldg(aoff + p + 2) : o_p1;
+        uint32_t coln[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col + o_p1 + lane + 32u * k) : kEmpty;
+        const uint32_t heur = Hg[p + 1];
+        const bool bad_col = __ldg(ign + p) != 0;
+        const bool ident = cur_ident;
+
+        uint32_t s1[K], s2[K], wv[K];
+        if (cur_src == SRC_CACHE) {
+#pragma unroll
+            for (int k = 0; k < K; k++) { s1[k] = cur_x1 ? nA1[k] : nA0[k]; s2[k] = cur_x2 ? nB1[k] : nB0[k]; wv[k] = nW[k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) { s1[k] = 0; s2[k] = 0; wv[k] = 0; }
+            if (cur_src == SRC_PLANES) {
+                const uint64_t* prow = s.recs + (uint64_t)cur_rec * 2 * HW;
+                const int nwords = (int)((L + 63) >> 6);
+                auto hap = [&](int which, int i0) -> uint64_t {           // 64 bits from haplotype position i0 >= 0
+                    const uint64_t* hw = prow + (which ? HW : 0);
+                    const int wi = i0 >> 6, sh = i0 & 63;
+                    uint64_t x = (wi < nwords) ? (hw[wi] >> sh) : 0ull;
+                    if (sh && wi + 1 < nwords) x |= hw[wi + 1] << (64 - sh);
+                    return x;
+                };
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const uint32_t j = lane + 32u * k;
+                    if (j < a_cur) {
+                        const ReadMeta rm = rmeta[__ldg(aidx + o_p + j)];
+                        score_planes(a, m, rm, -(int)rm.start, (int)L, hap, s1[k], s2[k]);
+                        wv[k] = p - rm.start;
+                    }
+                }
+            }
+        }
+        uint32_t A0[K], A1[K], B0[K], B1[K];
+        uint32_t pk0 = 0, pk1 = 0, e01 = 0, e10 = 0, e00 = 0, e11 = 0;
+        bool anyend = false;
+        uint64_t cells = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t c = colc[k];
+            const uint32_t q = bad_col ? 0u : (c & 0xffu);
+            const uint32_t al = (c >> 8) & 3u;
+            const uint32_t q0 = (al != 0u) ? q : 0u, q1 = (al != 1u) ? q : 0u;
+            A0[k] = s1[k] + q0; A1[k] = s1[k] + q1; B0[k] = s2[k] + q0; B1[k] = s2[k] + q1;
+            const uint32_t base = min(s1[k], s2[k]);
+            const uint32_t c01 = min(A0[k], B1[k]), c10 = min(A1[k], B0[k]), c00 = min(A0[k], B0[k]), c11 = min(A1[k], B1[k]);
+            pk0 += (c01 - base) | ((c10 - base) << 16);
+            pk1 += (c00 - base) | ((c11 - base) << 16);
+            if ((c >> 10) & 1u) { anyend = true; e01 += c01; e10 += c10; e00 += c00; e11 += c11; }
+            if (kCount) { wv[k] += 1; if (lane + 32u * k < a_cur) cells += wv[k]; }
+        }
+        const uint32_t r0 = wsum(pk0), r1 = wsum(pk1);
+        uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+        if (__ballot_sync(HP_FULL_MASK, anyend)) { f0 = wsum(e01); f1 = wsum(e10); f2 = wsum(e00); f3 = wsum(e11); }
+        const uint32_t present = present_mask(bad_col, ident);
+        const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
+        if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
+        if (qsize + nchild + 64 > a.qcap || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+
+        // candidate keys: total_c = cur_total - H[p] + H[p+1] + delta_c; hi_c = total_c << 32 | (~hets_c); idx in creation
+        // order.  (~hets) is smaller for the heterozygous candidates 0,1, so ties on the total go to the lowest slot.
+        const uint32_t tb = cur_total - heur_p + heur;
+        const uint32_t t0 = bad_col ? 0xffffffffu : tb + (r0 & 0xffffu);
+        const uint32_t t1 = (bad_col || ident) ? 0xffffffffu : tb + (r0 >> 16);
+        const uint32_t t2 = tb + (r1 & 0xffffu);
+        const uint32_t t3 = bad_col ? 0xffffffffu : tb + (r1 >> 16);
+        if (bad_col && t2 != cur_total) { w.status = HP_BLOCK_ASSERT; break; }              // :529
+        const uint32_t nh_het = cur_nh - 1u;                               // hets + 1
+        const uint32_t i0 = next_idx, i1 = next_idx + 1u;
+        const uint32_t i2 = next_idx + (bad_col ? 0u : (ident ? 1u : 2u)), i3 = i2 + 1u;
+        const uint32_t tmin = min(min(t0, t1), min(t2, t3));
+        const uint32_t best = (t0 == tmin) ? 0u : (t1 == tmin) ? 1u : (t2 == tmin) ? 2u : 3u;
+
+        // ---- children vectors into the next column's slot order ----
+        {
+            const uint32_t a_next = o_p2 - o_p1;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t cn = (lane + 32u * k < a_next) ? coln[k] : kEmpty;
+                const uint32_t carry = cn >> 16, sl = carry & 31u;
+                uint32_t g0 = __shfl_sync(HP_FULL_MASK, A0[0], sl), g1 = __shfl_sync(HP_FULL_MASK, A1[0], sl);
+                uint32_t g2 = __shfl_sync(HP_FULL_MASK, B0[0], sl), g3 = __shfl_sync(HP_FULL_MASK, B1[0], sl);
+                uint32_t gw = kCount ? __shfl_sync(HP_FULL_MASK, wv[0], sl) : 0u;
+#pragma unroll
+                for (int kk = 1; kk < K; kk++) {
+                    const uint32_t u0 = __shfl_sync(HP_FULL_MASK, A0[kk], sl), u1 = __shfl_sync(HP_FULL_MASK, A1[kk], sl);
+                    const uint32_t u2 = __shfl_sync(HP_FULL_MASK, B0[kk], sl), u3 = __shfl_sync(HP_FULL_MASK, B1[kk], sl);
+                    const uint32_t uw = kCount ? __shfl_sync(HP_FULL_MASK, wv[kk], sl) : 0u;
+                    if ((carry >> 5) == (uint32_t)kk) { g0 = u0; g1 = u1; g2 = u2; g3 = u3; gw = uw; }
+                }
+                const bool has = carry != 0xffffu;
+                nA0[k] = has ? g0 : 0u; nA1[k] = has ? g1 : 0u; nB0[k] = has ? g2 : 0u; nB1[k] = has ? g3 : 0u;
+                nW[k] = has ? gw : 0u;
+                colc[k] = cn;
+            }
+            o_p = o_p1; o_p1 = o_p2;
+        }
+        cache_first = next_idx; cache_present = present;
+
+        // ---- records: siblings get copies of the parent's words + their allele bit; the best child takes the parent's
+        //      record in place ----
+        const uint32_t c_mine = (lane - rr) & 31u;                         // this lane's candidate (pushes), if < 4
+        const bool mine = c_mine < 4u && ((present >> c_mine) & 1u) && c_mine != best;
+        uint32_t my_rec = 0;
+        {
+            const uint32_t nsib = nchild - 1;
+            // sibling ordinal of candidate c = number of present non-best candidates below it
+            const uint32_t sibmask = present & ~(1u << best);
+            const uint32_t my_ord = __popc(sibmask & ((1u << (c_mine & 31u)) - 1u));
+            const uint32_t from_fs = min(nsib, fs_top);                   // shared-memory stack first, then the slab list, then fresh
+            const uint32_t from_gl = min(nsib - from_fs, free_top);
+            if (mine) {
+                if (my_ord < from_fs) my_rec = w.free_stack[fs_top - 1 - my_ord];
+                else if (my_ord - from_fs < from_gl) my_rec = s.freelist[free_top - 1 - (my_ord - from_fs)];
+                else my_rec = rec_next + (my_ord - from_fs - from_gl);
+            }
+            fs_top -= from_fs; free_top -= from_gl; rec_next += nsib - from_fs - from_gl;
+            // haplotype words
+            const uint32_t wl = L >> 6;
+            const uint64_t bit = bad_col ? 0ull : (1ull << (L & 63));
+            if (regs_hap) {
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if ((present >> cc) & 1u) {
+                        const uint32_t rc = (cc == best) ? cur_rec : __shfl_sync(HP_FULL_MASK, my_rec, (rr + cc) & 31u);
+                        if (lane <= wl && (cc != best || lane == wl)) {
+                            uint64_t* crow = s.recs + (uint64_t)rc * 2 * HW;
+                            crow[lane] = (lane == wl && (cc & 1u)) ? (cur_w1 | bit) : cur_w1;
+                            crow[HW + lane] = (lane == wl && ((0x9u >> cc) & 1u)) ? (cur_w2 | bit) : cur_w2;
+                        }
+                    }
+                }
+            } else {
+                const uint64_t* prow = s.recs + (uint64_t)cur_rec * 2 * HW;
+                const uint32_t nwords = (L + 63) >> 6;
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if ((present >> cc) & 1u) {
+                        const uint32_t rc = (cc == best) ? cur_rec : __shfl_sync(HP_FULL_MASK, my_rec, (rr + cc) & 31u);
+                        uint64_t* crow = s.recs + (uint64_t)rc * 2 * HW;
+                        for (uint32_t wi = lane; wi <= wl; wi += 32) {
+                            if (cc != best || wi == wl) {
+                                const uint64_t w1 = wi < nwords ? prow[wi] : 0ull, w2 = wi < nwords ? prow[HW + wi] : 0ull;
+                                crow[wi] = (wi == wl && (cc & 1u)) ? (w1 | bit) : w1;
+                                crow[HW + wi] = (wi == wl && ((0x9u >> cc) & 1u)) ? (w2 | bit) : w2;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        // ---- push the siblings (one lane each) ----
+        {
+            const uint32_t mt = (c_mine == 0u) ? t0 : (c_mine == 1u) ? t1 : (c_mine == 2u) ? t2 : t3;
+            const uint32_t mi = (c_mine == 0u) ? i0 : (c_mine == 1u) ? i1 : (c_mine == 2u) ? i2 : i3;
+            const uint32_t mf = cur_frozen + ((c_mine == 0u) ? f0 : (c_mine == 1u) ? f1 : (c_mine == 2u) ? f2 : f3);
+            const uint64_t mhi = ((uint64_t)mt << 32) | ((c_mine < 2u && !bad_col) ? nh_het : cur_nh);
+            const uint32_t mlen = (L + 1) | ((cur_ident && c_mine >= 2u) ? 0x80000000u : 0u);
+            const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= scap);
+            if (fullmask == 0) {
+                if (mine) {
+                    *khi_at(lane, cnt) = mhi; *kidx_at(lane, cnt) = mi; *klen_at(lane, cnt) = mlen; *krec_at(lane, cnt) = my_rec;
+                    s.kfrozen[my_rec] = mf;
+                    if (key_less(mhi, mi, c_hi, c_idx)) { c_hi = mhi; c_idx = mi; c_pos = cnt; }
+                    cnt++;
+                }
+            } else {                                                      // rare: a target stripe is full
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if (((present >> cc) & 1u) && cc != best) {
+                        const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
+                        if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+                        const uint32_t src_lane = (rr + cc) & 31u;
+                        uint32_t target = src_lane;
+                        if (!((room >> target) & 1u)) target = __ffs(room) - 1;
+                        const uint64_t xhi = __shfl_sync(HP_FULL_MASK, mhi, src_lane);
+                        const uint32_t xi = __shfl_sync(HP_FULL_MASK, mi, src_lane), xl = __shfl_sync(HP_FULL_MASK, mlen, src_lane);
+                        const uint32_t xr = __shfl_sync(HP_FULL_MASK, my_rec, src_lane), xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
+                        if (lane == target) {
+                            *khi_at(lane, cnt) = xhi; *kidx_at(lane, cnt) = xi; *klen_at(lane, cnt) = xl; *krec_at(lane, cnt) = xr;
+                            s.kfrozen[xr] = xf;
+                            if (key_less(xhi, xi, c_hi, c_idx)) { c_hi = xhi; c_idx = xi; c_pos = cnt; }
+                            cnt++;
+                        }
+                    }
+                }
+            }
+            rr += 4;
+        }
+        if (w.status != HP_BLOCK_OK) break;
+        // queue minimum now includes the siblings
+        {
+            const uint64_t h0 = ((uint64_t)t0 << 32) | nh_het, h1 = ((uint64_t)t1 << 32) | nh_het;
+            const uint64_t h2 = ((uint64_t)t2 << 32) | cur_nh, h3 = ((uint64_t)t3 << 32) | cur_nh;
+            if (best != 0u && t0 != 0xffffffffu && key_less(h0, i0, qmin.hi, qmin.idx)) { qmin.hi = h0; qmin.idx = i0; }
+            if (best != 1u && t1 != 0xffffffffu && key_less(h1, i1, qmin.hi, qmin.idx)) { qmin.hi = h1; qmin.idx = i1; }
+            if (best != 2u && key_less(h2, i2, qmin.hi, qmin.idx)) { qmin.hi = h2; qmin.idx = i2; }
+            if (best != 3u && t3 != 0xffffffffu && key_less(h3, i3, qmin.hi, qmin.idx)) { qmin.hi = h3; qmin.idx = i3; }
+        }
+        next_idx += nchild; qsize += nchild;
+        if (lane == 0) atomicAdd(s.lencnt + L + 1, nchild);               // tracker.add_hap(L+1) x nchild (:531, :558)
+        if (L + 1 >= trk_thresh) trk_total += nchild;
+        // ---- the best child is the new cur (record inherited in place) ----
+        cur_total = tmin;
+        cur_nh = (best < 2u && !bad_col) ? nh_het : cur_nh;
+        cur_idx = (best == 0u) ? i0 : (best == 1u) ? i1 : (best == 2u) ? i2 : i3;
+        cur_frozen += (best == 0u) ? f0 : (best == 1u) ? f1 : (best == 2u) ? f2 : f3;
+        cur_len = L + 1;
+        cur_ident = cur_ident && best >= 2u;
+        cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
+        cur_src = SRC_CACHE;
+        heur_p = heur;
+        if (regs_hap && !bad_col && lane == (L >> 6)) {
+            const uint64_t b = 1ull << (L & 63);
+            if (cur_x1) cur_w1 |= b;
+            if (cur_x2) cur_w2 |= b;
+        }
+        __syncwarp();
+
+        // ---- pruning bookkeeping (:564-585) ----
+        while (trk_total > curr_thresh && min_progress < next_expected) {
+            min_progress++;
+            uint32_t dropped = 0;
+            if (lane == 0) dropped = atomicAdd(s.lencnt + min_progress - 1, 0u);
+            dropped = __shfl_sync(HP_FULL_MASK, dropped, 0);
+            trk_total -= dropped; trk_thresh = min_progress;
+            if (qsize > max_queue) {
+                // "full prune": every queued entry shorter than min_progress gets the cleared priority (cost 0);
+                // cur has length >= next_expected >= min_progress and is never affected
+                c_hi = ~0ull; c_idx = 0xffffffffu; c_pos = 0;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    uint64_t hi = *khi_at(lane, i);
+                    const uint32_t ix = *kidx_at(lane, i);
+                    if ((*klen_at(lane, i) & 0x7fffffffu) < min_progress) { hi &= 0xffffffffull; *khi_at(lane, i) = hi; }
+                    if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = i; }
+                }
+                __syncwarp();
+                qmin = wmin96(c_hi, c_idx);
+            }
+        }
+    }
+    if (w.status != HP_BLOCK_OK) return;
+
+    // ---- final node (:588-628) ----
+    const uint32_t top_total = cur_total;
+    const uint64_t* frow = s.recs + (uint64_t)cur_rec * 2 * HW;
+    uint32_t phased = 0, phased_snv = 0, skipped = 0;
+    const uint8_t* snv = a.is_snv + m.var_base;
+    __syncwarp();
+    for (uint32_t i = lane; i < N; i += 32) {
+        uint32_t b1 = (uint32_t)(frow[i >> 6] >> (i & 63)) & 1u;
+        uint32_t b2 = (uint32_t)(frow[HW + (i >> 6)] >> (i & 63)) & 1u;
+        if (__ldg(ign + i)) { b1 = 2; b2 = 2; skipped++; }
+        else if (b1 != b2) { phased++; if (__ldg(snv + i)) phased_snv++; }
+        a.out_h1[m.var_base + i] = (uint8_t)b1;
+        a.out_h2[m.var_base + i] = (uint8_t)b2;
+    }
+    phased = wsum(phased); phased_snv = wsum(phased_snv); skipped = wsum(skipped);
+    if (lane == 0) {
+        uint64_t* st = a.out_stats + (uint64_t)blk * 7;
+        st[0] = num_pruned;
+        st[1] = Hg[0];
+        st[2] = top_total;
+        st[3] = phased; st[4] = phased_snv; st[5] = N - phased - skipped; st[6] = skipped;
+    }
+    if (top_total < Hg[0]) w.status = HP_BLOCK_ASSERT;                     // phase_stats.rs:163
+}
+
 // ---- team: the warps of one CTA work on one phase block ---------------------------------------------------------
 // The heuristic pre-pass is a chain: sub-solve v needs H[v+1..v+40] and the clip size left by sub-solve v+1.  But
 // H[v] == H[v+1] for most variants, so warp i of the team solves variant v_hi - i SPECULATIVELY, reading every not yet
@@ -1304,7 +1716,10 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
     // ---- main loop: one warp ----
     if (warp == 0) {
         w.evals = w.sum_lp = w.pops = w.cells = 0;
-        if (w.status == HP_BLOCK_OK) main_solve<K, kCount>(a, m, w, slab, blk, Hg);
+        if (w.status == HP_BLOCK_OK) {
+            if constexpr (K == 0) main_solve<K, kCount>(a, m, w, slab, blk, Hg);
+            else main_solve_fast<K, kCount>(a, m, w, slab, blk, Hg);
+        }
         w.status = __shfl_sync(HP_FULL_MASK, w.status, 0);
         if (w.lane == 0) ts.final_status = w.status;
         if (kCount) {
