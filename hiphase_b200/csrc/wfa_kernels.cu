@@ -17,6 +17,7 @@
 #include <cstring>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hp_host.h"
@@ -47,6 +48,7 @@ struct WfaJob {
 struct WfaArgs {
     uint32_t n_jobs;
     const WfaJob* jobs;
+    const uint32_t* order;         // processing order: longest reads first (shorter tail of the persistent kernel)
     const WfaNode* nodes;
     const uint32_t* child_off;     // CSR rows per job: n_nodes + 1 entries starting at node_base + job index
     const uint32_t* child_idx;     // job-relative node ids
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
         if (lane == 0) j = atomicAdd(a.ticket, 1u);
         j = __shfl_sync(HP_FULL_MASK, j, 0);
         if (j >= a.n_jobs) break;
+        j = a.order[j];
         const WfaJob job = a.jobs[j];
         int status = job.status;
         uint32_t score = 0;
@@ -574,7 +577,7 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     const uint32_t sw_max = (max_nodes + 63) / 64;
 
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t in_bytes = al(sizeof(WfaJob) * nj) + al(sizeof(WfaNode) * fg.nodes.size()) + al(4 * fg.child_off.size()) +
+    const size_t in_bytes = al(sizeof(WfaJob) * nj) + al(4ull * nj) + al(sizeof(WfaNode) * fg.nodes.size()) + al(4 * fg.child_off.size()) +
                             al(4 * fg.child_idx.size()) + al(4 * fg.amap_off.size()) + al(4 * fg.amap.size()) + al(in.n_reference) +
                             al(in.n_allele_bytes) + al(in.n_seq_pool) + al(in.n_read_bytes) + al(in.n_vtype) + 4096;
     if (!ctx->wfa_in.reserve(in_bytes)) return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA input staging allocation failed");
@@ -587,6 +590,10 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     WfaArgs a;
     a.n_jobs = nj;
     a.jobs = (const WfaJob*)up(fg.jobs.data(), sizeof(WfaJob) * nj);
+    std::vector<uint32_t> order(nj);
+    for (uint32_t i = 0; i < nj; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return fg.jobs[x].read_len > fg.jobs[y].read_len; });
+    a.order = (const uint32_t*)up(order.data(), 4ull * nj);
     a.nodes = (const WfaNode*)up(fg.nodes.data(), sizeof(WfaNode) * fg.nodes.size());
     a.child_off = (const uint32_t*)up(fg.child_off.data(), 4 * fg.child_off.size());
     a.child_idx = (const uint32_t*)up(fg.child_idx.data(), 4 * fg.child_idx.size());
@@ -686,22 +693,57 @@ int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
     for (uint32_t j = 0; j < b->n_jobs; j++) ids[j] = j;
     uint32_t cap = ctx->wfa_table_cap;
     for (int attempt = 0; attempt < 4 && !ids.empty(); attempt++) {
-        FlatGraphs fg;
-        fg.jobs.reserve(ids.size());
-        uint64_t rows = 0;
-        for (uint32_t j : ids) {
-            WfaJob job{};
-            job.read_off = b->read_off[j]; job.read_len = (uint32_t)(b->read_off[j + 1] - b->read_off[j]);
-            job.row_off = rows; job.row_len = b->het_hi[j] - b->het_lo[j]; job.het_lo = b->het_lo[j];
-            rows += job.row_len;
-            job.status = HP_WFA_OK;
-            if (job.row_len == 0) { job.status = HP_WFA_SKIPPED; job.node_base = fg.nodes.size(); job.n_nodes = 0; }   // read_parsing.rs:703-712
-            else if (!build_job_graph(b, j, fg, job)) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "graph construction failed for job " + std::to_string(j) + " (the reference unwrap()s this, read_parsing.rs:777)");
-            if (job.status != HP_WFA_OK) {            // keep the CSR row layout: one (empty) row per job
-                fg.child_off.push_back((uint32_t)fg.child_idx.size());
-                fg.amap_off.push_back((uint32_t)fg.amap.size());
+        // graph construction is per job and independent: build chunks on host threads, then concatenate
+        const size_t n_ids = ids.size();
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(hw, n_ids / 64));
+        std::vector<FlatGraphs> parts(n_chunks);
+        std::vector<int> part_fail(n_chunks, -1);
+        auto build_chunk = [&](size_t c) {
+            const size_t lo = n_ids * c / n_chunks, hi = n_ids * (c + 1) / n_chunks;
+            FlatGraphs& pg = parts[c];
+            pg.jobs.reserve(hi - lo);
+            for (size_t q = lo; q < hi; q++) {
+                const uint32_t j = ids[q];
+                WfaJob job{};
+                job.read_off = b->read_off[j]; job.read_len = (uint32_t)(b->read_off[j + 1] - b->read_off[j]);
+                job.row_len = b->het_hi[j] - b->het_lo[j]; job.het_lo = b->het_lo[j];
+                job.status = HP_WFA_OK;
+                if (job.row_len == 0) { job.status = HP_WFA_SKIPPED; job.node_base = pg.nodes.size(); job.n_nodes = 0; }   // read_parsing.rs:703-712
+                else if (!build_job_graph(b, j, pg, job)) { part_fail[c] = (int)j; return; }
+                if (job.status != HP_WFA_OK) {            // keep the CSR row layout: one (empty) row per job
+                    pg.child_off.push_back((uint32_t)pg.child_idx.size());
+                    pg.amap_off.push_back((uint32_t)pg.amap.size());
+                }
+                pg.jobs.push_back(job);
             }
-            fg.jobs.push_back(job);
+        };
+        if (n_chunks == 1) build_chunk(0);
+        else {
+            std::vector<std::thread> pool;
+            for (size_t c = 0; c < n_chunks; c++) pool.emplace_back(build_chunk, c);
+            for (auto& t : pool) t.join();
+        }
+        for (size_t c = 0; c < n_chunks; c++)
+            if (part_fail[c] >= 0)
+                return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "graph construction failed for job " + std::to_string(part_fail[c]) + " (the reference unwrap()s this, read_parsing.rs:777)");
+        FlatGraphs fg;
+        uint64_t rows = 0;
+        {
+            size_t tn = 0, tc = 0, ta = 0, tj = 0, to = 0;
+            for (const FlatGraphs& pg : parts) { tn += pg.nodes.size(); tc += pg.child_idx.size(); ta += pg.amap.size(); tj += pg.jobs.size(); to += pg.child_off.size(); }
+            fg.nodes.reserve(tn); fg.child_idx.reserve(tc); fg.amap.reserve(ta); fg.jobs.reserve(tj); fg.child_off.reserve(to); fg.amap_off.reserve(to);
+            for (FlatGraphs& pg : parts) {
+                const uint64_t nb0 = fg.nodes.size();
+                const uint32_t cb0 = (uint32_t)fg.child_idx.size(), ab0 = (uint32_t)fg.amap.size();
+                for (WfaJob job : pg.jobs) { job.node_base += nb0; job.row_off = rows; rows += job.row_len; fg.jobs.push_back(job); }
+                fg.nodes.insert(fg.nodes.end(), pg.nodes.begin(), pg.nodes.end());
+                fg.child_idx.insert(fg.child_idx.end(), pg.child_idx.begin(), pg.child_idx.end());
+                fg.amap.insert(fg.amap.end(), pg.amap.begin(), pg.amap.end());
+                for (uint32_t x : pg.child_off) fg.child_off.push_back(x + cb0);
+                for (uint32_t x : pg.amap_off) fg.amap_off.push_back(x + ab0);
+                pg = FlatGraphs();
+            }
         }
         // slabs: full occupancy on the first attempt, fewer and larger afterwards
         int max_ctas = 0;
