@@ -322,7 +322,7 @@ __device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((ui
 // One sub-solver queue entry (32 B = two 128-bit shared-memory transactions).
 struct __align__(16) SubEntry {
     uint64_t key, h1, h2;
-    uint32_t frozen, pad;
+    uint32_t frozen, tag;
 };
 
 constexpr uint32_t kFreeStack = 192;   // free main-queue record slots kept in shared memory
@@ -351,10 +351,12 @@ struct WarpCtx {
     __device__ __forceinline__ uint32_t H(uint32_t idx) const { return hring[max(idx, h_floor) & 63u]; }
 };
 
-__device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1, uint64_t h2, uint32_t frozen) {
+// tag 0xff: h1/h2 are the node's own haplotypes; tag < 4: h1/h2 are the PARENT's and tag is the node's candidate
+// slot -- its allele bit is applied when the node is popped (saves the per-sibling bit fiddling in the dive loop).
+__device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1, uint64_t h2, uint32_t frozen, uint32_t tag = 0xffu) {
     uint4* p = reinterpret_cast<uint4*>(e);
     p[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
-    p[1] = make_uint4((uint32_t)h2, (uint32_t)(h2 >> 32), frozen, 0u);
+    p[1] = make_uint4((uint32_t)h2, (uint32_t)(h2 >> 32), frozen, tag);
 }
 
 // astar_subsolver (astar_phaser.rs:311-405).  Returns est in .x, solved depth in .y (both warp-uniform).
@@ -546,6 +548,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     const uint32_t* aoff = a.act_off + m.var_base + blk;
     const uint32_t* aidx = a.act_idx + m.cell_base;
     const uint32_t* col = a.col + m.cell_base;
+    const uint32_t* col_lane = col + lane;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
     constexpr uint32_t kEmpty = 0xffff0000u;      // column record of an unused slot: no carry, quality 0
 
@@ -593,6 +596,14 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const SubEntry* e = w.ent(owner, pos);
             cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
             cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
+            {
+                const uint32_t tag = e->tag;
+                if (tag < 4u) {                                          // parent's haplotypes + this node's candidate slot
+                    const uint32_t lb = (cur_lo & 63u) - 1u;
+                    cur_h1 |= (uint64_t)(tag & 1u) << lb;
+                    cur_h2 |= (uint64_t)((0x9u >> tag) & 1u) << lb;
+                }
+            }
             __syncwarp();
             if ((int)lane == owner) {                                    // remove + rescan own stripe
                 cnt--;
@@ -644,7 +655,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         const uint32_t o_p2 = has_next ? __ldg(aoff + p + 2) : o_p1;
         uint32_t coln[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col + o_p1 + lane + 32u * k) : kEmpty;
+        for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
         const uint32_t heur = w.H(p + 1);
         const bool bad_col = (badwin >> L) & 1ull;
         const bool ident = (cur_h1 == cur_h2);
@@ -705,8 +716,9 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         const uint32_t t3 = bad_col ? 0xffffffffu : tb + (r1 >> 16);
         if (bad_col && t2 != cur_total) { w.status = HP_BLOCK_ASSERT; break; }             // :360
         const uint32_t lo_base = (cur_lo & 0xfc000000u) | (next_idx << 6) | (L + 1);
-        const uint32_t lo0 = lo_base - (1u << 26), lo1 = lo0 + 64u;
-        const uint32_t lo2 = lo_base + (bad_col ? 0u : (ident ? 64u : 128u)), lo3 = lo2 + 64u;
+        // lo of candidate c = (c < 2 ? lo0 : lo2) + ((c & 1) << 6)
+        const uint32_t lo0 = lo_base - (1u << 26);
+        const uint32_t lo2 = lo_base + (bad_col ? 0u : (ident ? 64u : 128u));
         const uint32_t tmin = min(min(t0, t1), min(t2, t3));
         const uint32_t best = (t0 == tmin) ? 0u : (t1 == tmin) ? 1u : (t2 == tmin) ? 2u : 3u;
 
@@ -736,19 +748,19 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         }
         cache_first = next_idx; cache_present = present;
 
-        // ---- push the siblings of the best child (one lane each, round-robin over the stripes) ----
-        const uint64_t bit = bad_col ? 0ull : (1ull << L);
+        // ---- push the siblings of the best child: candidate c is handled by lane (rr + c) & 31, into its own stripe.
+        //      The entry keeps the PARENT's haplotypes and the candidate slot as a tag. ----
         {
             const uint32_t c = (lane - rr) & 31u;
             const bool mine = c < 4u && ((present >> c) & 1u) && c != best;
-            const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl);
-            const uint32_t mt = (c == 0u) ? t0 : (c == 1u) ? t1 : (c == 2u) ? t2 : t3;
-            const uint32_t ml = (c == 0u) ? lo0 : (c == 1u) ? lo1 : (c == 2u) ? lo2 : lo3;
+            const uint32_t rsel = (c & 2u) ? r1 : r0;
+            const uint32_t mt = tb + ((c & 1u) ? (rsel >> 16) : (rsel & 0xffffu));
+            const uint32_t ml = ((c & 2u) ? lo2 : lo0) + ((c & 1u) << 6);
             const uint32_t mf = cur_frozen + ((c == 0u) ? f0 : (c == 1u) ? f1 : (c == 2u) ? f2 : f3);
-            if (fullmask == 0) {
+            if (__ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl) == 0) {
                 if (mine) {
                     const uint64_t k = mk64(mt, ml);
-                    sub_store(w.ent(lane, cnt), k, cur_h1 | ((c & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> c) & 1u) ? bit : 0ull), mf);
+                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, mf, c);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -764,7 +776,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                         const uint32_t xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
                         if (lane == target) {
                             const uint64_t k = mk64(xt, xl);
-                            sub_store(w.ent(lane, cnt), k, cur_h1 | ((cc & 1u) ? bit : 0ull), cur_h2 | (((0x9u >> cc) & 1u) ? bit : 0ull), xf);
+                            sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, xf, cc);
                             if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
@@ -773,22 +785,27 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             }
             rr += 4;
         }
-        // queue minimum now includes the siblings
+        // queue minimum now includes the siblings: fold in the smallest sibling key (second best candidate)
         {
-            const uint64_t k0 = (best == 0u) ? ~0ull : mk64(t0, lo0), k1 = (best == 1u) ? ~0ull : mk64(t1, lo1);
-            const uint64_t k2 = (best == 2u) ? ~0ull : mk64(t2, lo2), k3 = (best == 3u) ? ~0ull : mk64(t3, lo3);
-            const uint64_t ka = k0 < k1 ? k0 : k1, kb = k2 < k3 ? k2 : k3;
-            const uint64_t kc = ka < kb ? ka : kb;
-            qmin = kc < qmin ? kc : qmin;
+            const uint32_t u0 = (best == 0u) ? 0xffffffffu : t0, u1 = (best == 1u) ? 0xffffffffu : t1;
+            const uint32_t u2 = (best == 2u) ? 0xffffffffu : t2, u3 = (best == 3u) ? 0xffffffffu : t3;
+            const uint32_t m2 = min(min(u0, u1), min(u2, u3));
+            if (m2 != 0xffffffffu) {
+                const uint32_t c2 = (u0 == m2) ? 0u : (u1 == m2) ? 1u : (u2 == m2) ? 2u : 3u;
+                const uint64_t k2 = mk64(m2, ((c2 & 2u) ? lo2 : lo0) + ((c2 & 1u) << 6));
+                qmin = k2 < qmin ? k2 : qmin;
+            }
         }
         next_idx += nchild;
         // ---- the best child is the new cur ----
         cur_total = tmin;
-        cur_lo = (best == 0u) ? lo0 : (best == 1u) ? lo1 : (best == 2u) ? lo2 : lo3;
+        cur_lo = ((best & 2u) ? lo2 : lo0) + ((best & 1u) << 6);
         cur_frozen += (best == 0u) ? f0 : (best == 1u) ? f1 : (best == 2u) ? f2 : f3;
         cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
-        cur_h1 |= cur_x1 ? bit : 0ull;
-        cur_h2 |= cur_x2 ? bit : 0ull;
+        if (!bad_col) {
+            cur_h1 |= (uint64_t)cur_x1 << L;
+            cur_h2 |= (uint64_t)cur_x2 << L;
+        }
         cur_src = SRC_CACHE;
         heur_p = heur;
         __syncwarp();
