@@ -88,6 +88,10 @@ class hp_wfa_out(C.Structure):
                 ("traversed", u64p), ("trav_words", C.c_uint32), ("counters", C.POINTER(hp_wfa_counters))]
 
 
+class hp_post_out(C.Structure):
+    _fields_ = [("span_counts", u32p), ("block_tags", u64p), ("read_haplotag", u8p), ("read_tag", u64p)]
+
+
 STATS_DTYPE = np.dtype([(n, "<u8") for n, _ in hp_phase_stats._fields_])
 COUNTERS_DTYPE = np.dtype([(n, "<u8") for n, _ in hp_astar_counters._fields_])
 WFA_COUNTERS_DTYPE = np.dtype([(n, "<u8") for n, _ in hp_wfa_counters._fields_])
@@ -257,3 +261,16 @@ class WfaOut:
                           ptr(self.n_nodes, u32p), ptr(self.traversed, u64p), self.trav_words,
                           self.counters.ctypes.data_as(C.POINTER(hp_wfa_counters)) if self.counters is not None
                           else C.POINTER(hp_wfa_counters)())
+
+
+class PostOut:
+    """Host-side result buffers of hp_post_solve_batch (span counts, block tags, read haplotags)."""
+
+    def __init__(self, batch):
+        self.span_counts = np.zeros(batch.n_vars, np.uint32)
+        self.block_tags = np.zeros(batch.n_vars, np.uint64)
+        self.read_haplotag = np.full(batch.n_reads, 255, np.uint8)
+        self.read_tag = np.zeros(batch.n_reads, np.uint64)
+
+    def as_struct(self):
+        return hp_post_out(ptr(self.span_counts, u32p), ptr(self.block_tags, u64p), ptr(self.read_haplotag, u8p), ptr(self.read_tag, u64p))

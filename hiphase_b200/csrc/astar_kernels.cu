@@ -565,12 +565,14 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     uint32_t nA0[K], nA1[K], nB0[K], nB1[K], nW[K];
     uint32_t cache_first = 0xffffffffu, cache_present = 0;
     // column records of the current column p (slot = lane + 32k) and the offsets of p and p+1
-    uint32_t o_p = __ldg(aoff + v), o_p1 = __ldg(aoff + v + 1);
-    uint32_t colc[K];
+    // column records two columns ahead are always in flight (the small L1 next to 196 KB of shared memory misses often)
+    uint32_t o_p = __ldg(aoff + v), o_p1 = __ldg(aoff + v + 1), o_p2 = (v + 2 <= N) ? __ldg(aoff + v + 2) : o_p1;
+    uint32_t colc[K], coln[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
         nA0[k] = nA1[k] = nB0[k] = nB1[k] = nW[k] = 0;
         colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+        coln[k] = (v + 1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
     uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 0;
     const uint32_t max_visits = a.min_queue_size / 10 + a.queue_increment * clip;    // :266, :333
@@ -631,10 +633,12 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             } else cur_src = SRC_PLANES;
             heur_p = w.H(Lp == 0u ? v + 1 : pp);
             if (pp < N) {
-                o_p = __ldg(aoff + pp); o_p1 = __ldg(aoff + pp + 1);
+                o_p = __ldg(aoff + pp); o_p1 = __ldg(aoff + pp + 1); o_p2 = (pp + 2 <= N) ? __ldg(aoff + pp + 2) : o_p1;
 #pragma unroll
-                for (int k = 0; k < K; k++)
+                for (int k = 0; k < K; k++) {
                     colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+                    coln[k] = (pp + 1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
+                }
             }
         }
         // ---- cur is the top of the queue (peek) ----
@@ -651,11 +655,10 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         const uint32_t p = v + L;
         const uint32_t a_cur = o_p1 - o_p;
         // ---- prefetch the next column's records (addresses are known; validity is masked once o_p2 arrives) ----
-        const bool has_next = p + 1 < N;
-        const uint32_t o_p2 = has_next ? __ldg(aoff + p + 2) : o_p1;
-        uint32_t coln[K];
+        const uint32_t o_p3 = (p + 3 <= N) ? __ldg(aoff + p + 3) : o_p2;
+        uint32_t colnn[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
+        for (int k = 0; k < K; k++) colnn[k] = (p + 2 < N) ? __ldg(col_lane + o_p2 + 32u * k) : kEmpty;
         const uint32_t heur = w.H(p + 1);
         const bool bad_col = (badwin >> L) & 1ull;
         const bool ident = (cur_h1 == cur_h2);
@@ -743,8 +746,9 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 nA0[k] = has ? g0 : 0u; nA1[k] = has ? g1 : 0u; nB0[k] = has ? g2 : 0u; nB1[k] = has ? g3 : 0u;
                 nW[k] = has ? gw : 0u;
                 colc[k] = cn;
+                coln[k] = colnn[k];
             }
-            o_p = o_p1; o_p1 = o_p2;
+            o_p = o_p1; o_p1 = o_p2; o_p2 = o_p3;
         }
         cache_first = next_idx; cache_present = present;
 
@@ -1258,12 +1262,14 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     const bool regs_hap = HW <= 32;
     uint32_t nA0[K], nA1[K], nB0[K], nB1[K], nW[K];
     uint32_t cache_first = 0xffffffffu, cache_present = 0;
-    uint32_t o_p = __ldg(aoff + 0), o_p1 = __ldg(aoff + 1);
-    uint32_t colc[K];
+    const uint32_t* col_lane = col + lane;
+    uint32_t o_p = __ldg(aoff + 0), o_p1 = __ldg(aoff + 1), o_p2 = (2 <= N) ? __ldg(aoff + 2) : o_p1;
+    uint32_t colc[K], coln[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
         nA0[k] = nA1[k] = nB0[k] = nB1[k] = nW[k] = 0;
         colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+        coln[k] = (1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
 
     for (;;) {
@@ -1306,9 +1312,12 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 } else cur_src = SRC_PLANES;
                 heur_p = Hg[cur_len];
                 o_p = __ldg(aoff + cur_len); o_p1 = __ldg(aoff + cur_len + 1);
+                o_p2 = (cur_len + 2 <= N) ? __ldg(aoff + cur_len + 2) : o_p1;
 #pragma unroll
-                for (int k = 0; k < K; k++)
+                for (int k = 0; k < K; k++) {
                     colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
+                    coln[k] = (cur_len + 1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
+                }
             }
             const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
             __syncwarp();
@@ -1352,11 +1361,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         // ---- expand column p = L ----
         const uint32_t p = L;
         const uint32_t a_cur = o_p1 - o_p;
-        const bool has_next = p + 1 < N;
-        const uint32_t o_p2 = has_next ? __ldg(aoff + p + 2) : o_p1;
-        uint32_t coln[K];
+        const uint32_t o_p3 = (p + 3 <= N) ? __ldg(aoff + p + 3) : o_p2;
+        uint32_t colnn[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) coln[k] = has_next ? __ldg(col + o_p1 + lane + 32u * k) : kEmpty;
+        for (int k = 0; k < K; k++) colnn[k] = (p + 2 < N) ? __ldg(col_lane + o_p2 + 32u * k) : kEmpty;
         const uint32_t heur = Hg[p + 1];
         const bool bad_col = __ldg(ign + p) != 0;
         const bool ident = cur_ident;
@@ -1450,8 +1458,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 nA0[k] = has ? g0 : 0u; nA1[k] = has ? g1 : 0u; nB0[k] = has ? g2 : 0u; nB1[k] = has ? g3 : 0u;
                 nW[k] = has ? gw : 0u;
                 colc[k] = cn;
+                coln[k] = colnn[k];
             }
-            o_p = o_p1; o_p1 = o_p2;
+            o_p = o_p1; o_p1 = o_p2; o_p2 = o_p3;
         }
         cache_first = next_idx; cache_present = present;
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(CSRC, "libhiphase_b200.so")
 
 EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
-           "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align")
+           "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch")
 
 _LIB = None
 
@@ -54,6 +54,7 @@ def lib():
         L.hp_last_kernel_ms.restype = C.c_float
         L.hp_last_kernel_ms.argtypes = [C.c_void_p]
         L.hp_wfa_align_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_wfa_batch), C.POINTER(A.hp_wfa_out)]
+        L.hp_post_solve_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), A.i64p, A.u8p, A.u8p, C.POINTER(A.hp_post_out)]
         L.hp_wfa_graph_align.argtypes = [C.c_void_p, C.c_uint32, A.u8p, A.u64p, A.u32p, A.u64p, A.u8p, C.c_uint64,
                                          C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), A.u64p]
         _LIB = L
@@ -105,6 +106,15 @@ class Context:
         out = A.AstarOut(batch, want_heuristic, want_counters)
         bs, os_ = batch.as_struct(), out.as_struct()
         self.check(lib().hp_astar_solve_batch(self._h, C.byref(bs), C.byref(os_)))
+        return out
+
+    # ---- post-solve (span counts, block tags, haplotags) ----
+    def post_solve_batch(self, batch, var_pos, h1, h2):
+        import numpy as np
+        var_pos = np.ascontiguousarray(var_pos, np.int64); h1 = np.ascontiguousarray(h1, np.uint8); h2 = np.ascontiguousarray(h2, np.uint8)
+        out = A.PostOut(batch)
+        bs, os_ = batch.as_struct(), out.as_struct()
+        self.check(lib().hp_post_solve_batch(self._h, C.byref(bs), A.ptr(var_pos, A.i64p), A.ptr(h1, A.u8p), A.ptr(h2, A.u8p), C.byref(os_)))
         return out
 
     # ---- graph-WFA ----

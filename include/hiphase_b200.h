@@ -166,6 +166,21 @@ int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads,
                        const uint8_t* ignored, const uint8_t* is_snv,
                        uint8_t* h1, uint8_t* h2, hp_phase_stats* stats);
 
+
+/* ---- post-solve: span counts, block splitting and haplotagging ------------------------
+ *      replaces get_solution_span_counts (src/phaser.rs:350-388), the block_split / block_tags loop
+ *      (src/phaser.rs:546-569) and haplotag_reads (src/phaser.rs:714-750) ------------------------------------ */
+typedef struct hp_post_out {
+    uint32_t* span_counts;   /* [n_vars]  block b: N-1 junction counts at var_off[b] .. (last entry of a block unused, 0)   */
+    uint64_t* block_tags;    /* [n_vars]  PhaseResult::block_ids: position of the first variant of the variant's sub-block  */
+    uint8_t*  read_haplotag; /* [n_reads] 0 / 1, or 2 = unassigned (equal scores: the read gets no entry in the reference)   */
+    uint64_t* read_tag;      /* [n_reads] phase block tag of the read (valid when read_haplotag < 2)                         */
+} hp_post_out;
+
+/* Host buffers in / out.  var_pos[n_vars] = Variant::position(); h1 / h2 = the haplotypes returned by the A* entry. */
+int hp_post_solve_batch(hp_ctx* ctx, const hp_block_batch* batch, const int64_t* var_pos,
+                        const uint8_t* h1, const uint8_t* h2, hp_post_out* out);
+
 /* Number of kernel launches this context has issued so far (for bench.py's gpu_launches). */
 uint64_t hp_launch_count(const hp_ctx* ctx);
 /* Device time (ms, CUDA events on the launching stream) of the dominant kernel in the last _device / _batch call. */

@@ -55,6 +55,9 @@ int hpo_astar_solve_batch(const hp_params* params, const hp_block_batch* batch, 
 int hpo_astar_subsolver(const hp_params* params, const hp_block_batch* one_block, uint64_t problem_offset,
                         uint64_t problem_size, const uint64_t* H, uint64_t* max_cost, uint64_t* solved);
 
+/* ---- post-solve (src/phaser.rs:350-388, 546-569, 714-750) ---- */
+int hpo_post_solve_batch(const hp_block_batch* batch, const int64_t* var_pos, const uint8_t* h1, const uint8_t* h2, hp_post_out* out);
+
 /* ---- WFA graph (src/wfa_graph.rs) ---- */
 typedef struct hpo_graph hpo_graph;
 hpo_graph* hpo_graph_new(uint64_t max_edit_distance);

@@ -54,6 +54,7 @@ def lib():
         L.hpo_tracker_script.argtypes = [C.c_uint32, C.c_uint32, A.u8p, A.u32p, A.u64p]
         L.hpo_collapse.argtypes = [C.c_uint32, C.c_uint64, A.u8p, A.u8p, A.u8p, A.u8p, A.u64p, A.u64p]
         L.hpo_read_segment_region.argtypes = [A.u8p, C.c_uint64, A.u64p, A.u64p]
+        L.hpo_post_solve_batch.argtypes = [C.POINTER(A.hp_block_batch), A.i64p, A.u8p, A.u8p, C.POINTER(A.hp_post_out)]
         L.hpo_wfa_align_batch.argtypes = [C.POINTER(A.hp_params), C.POINTER(A.hp_wfa_batch), C.POINTER(A.hp_wfa_out),
                                           C.c_int]
         _LIB = L
@@ -158,4 +159,12 @@ def wfa_align(batch, params=None, threads=1, trav_words=0, want_counters=False):
     out = A.WfaOut(batch, trav_words, want_counters)
     bs, os_ = batch.as_struct(), out.as_struct()
     out.failures = lib().hpo_wfa_align_batch(C.byref(params), C.byref(bs), C.byref(os_), int(threads))
+    return out
+
+
+def post_solve(batch, var_pos, h1, h2):
+    var_pos = np.ascontiguousarray(var_pos, np.int64); h1 = u8(h1); h2 = u8(h2)
+    out = A.PostOut(batch)
+    bs, os_ = batch.as_struct(), out.as_struct()
+    out.rc = lib().hpo_post_solve_batch(C.byref(bs), A.ptr(var_pos, A.i64p), A.ptr(h1, A.u8p), A.ptr(h2, A.u8p), C.byref(os_))
     return out
