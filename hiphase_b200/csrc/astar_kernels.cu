@@ -325,6 +325,14 @@ struct __align__(16) SubEntry {
     uint32_t frozen, tag;
 };
 
+#ifndef HP_DEAD_POOL
+#define HP_DEAD_POOL 1
+#endif
+constexpr bool kDeadPool = HP_DEAD_POOL != 0;
+#ifndef HP_SWEEP_MIN_QUEUE
+#define HP_SWEEP_MIN_QUEUE 4096
+#endif
+constexpr uint32_t kSweepMinQueue = HP_SWEEP_MIN_QUEUE;   // dead entries are swept into the pool only while the queue is this large
 constexpr uint32_t kFreeStack = 192;   // free main-queue record slots kept in shared memory
 
 struct WarpCtx {
@@ -341,6 +349,10 @@ struct WarpCtx {
     uint32_t* mq_rec;
     uint32_t mq_cap_s;
     uint32_t* free_stack;   // small stack of free record slots in shared memory (overflow: slab free list)
+    uint32_t* free_ctr;     // shared-memory cursors into the slab free list / the dead pool while a sweep runs
+    uint32_t* pool_ctr;
+    uint32_t* lencnt_s;     // PQueueHapTracker::length_counts in shared memory (blocks with <= lencnt_cap_s variants)
+    uint32_t lencnt_cap_s;
     // counters
     uint64_t evals, sum_lp, pops, cells;
     int status;
@@ -834,11 +846,13 @@ struct Slab {
     uint32_t* krec;      // [qcap] record slot
     uint32_t* freelist;  // [qcap]
     uint32_t* lencnt;    // [hap_words*64 + 2] PQueueHapTracker::length_counts
+    uint64_t* pool_hi;   // [qcap] dead pool (entries shorter than min_progress, waiting to be popped and discarded)
+    uint32_t* pool_idx;  // [qcap]
     uint64_t* recs;      // [qcap][2*hap_words]
 };
 
 __host__ __device__ inline uint64_t slab_bytes_for(uint32_t qcap, uint32_t hap_words) {
-    uint64_t b = (uint64_t)qcap * (8 + 4 * 5) + (uint64_t)(hap_words * 64 + 2) * 4;
+    uint64_t b = (uint64_t)qcap * (8 + 4 * 5 + 8 + 4) + (uint64_t)(hap_words * 64 + 2) * 4;
     b = (b + 15) & ~15ull;
     b += (uint64_t)qcap * 2 * hap_words * 8;
     return (b + 255) & ~255ull;
@@ -847,11 +861,13 @@ __host__ __device__ inline uint64_t slab_bytes_for(uint32_t qcap, uint32_t hap_w
 __device__ __forceinline__ Slab carve_slab(uint8_t* p, uint32_t qcap, uint32_t hap_words) {
     Slab s;
     s.khi = (uint64_t*)p; p += (uint64_t)qcap * 8;
+    s.pool_hi = (uint64_t*)p; p += (uint64_t)qcap * 8;
     s.kidx = (uint32_t*)p; p += (uint64_t)qcap * 4;
     s.klen = (uint32_t*)p; p += (uint64_t)qcap * 4;
     s.kfrozen = (uint32_t*)p; p += (uint64_t)qcap * 4;
     s.krec = (uint32_t*)p; p += (uint64_t)qcap * 4;
     s.freelist = (uint32_t*)p; p += (uint64_t)qcap * 4;
+    s.pool_idx = (uint32_t*)p; p += (uint64_t)qcap * 4;
     s.lencnt = (uint32_t*)p; p += (uint64_t)(hap_words * 64 + 2) * 4;
     p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     s.recs = (uint64_t*)p;
@@ -1239,8 +1255,15 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     auto klen_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_len + stripe * mqs + i : s.klen + stripe * scap + i; };
     auto krec_at = [&](uint32_t stripe, uint32_t i) -> uint32_t* { return i < mqs ? mq_rec + stripe * mqs + i : s.krec + stripe * scap + i; };
 
-    for (uint32_t i = lane; i <= N; i += 32) s.lencnt[i] = 0u;
+    // tracker length counts: only lane 0 touches them (plain read-modify-write, program order)
+    uint32_t* const lc = (N + 1 <= w.lencnt_cap_s) ? w.lencnt_s : s.lencnt;
+    for (uint32_t i = lane; i <= N; i += 32) lc[i] = 0u;
     __syncwarp();
+    // dead pool: entries that fell below min_progress leave their stripe at once (keys only, records freed); they are
+    // "popped" (counted) in key order as the live pops pass them
+    uint64_t* const pool_hi = s.pool_hi; uint32_t* const pool_idx = s.pool_idx;
+    uint32_t pool_n = 0;
+    MainKey pool_min; pool_min.hi = ~0ull; pool_min.idx = 0xffffffffu;
     uint32_t trk_total = 1, trk_thresh = 0;                              // root counted (:488)
     uint32_t curr_thresh = a.min_queue_size;
     const uint32_t max_queue = 10u * a.min_queue_size;                   // :457
@@ -1248,7 +1271,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     uint64_t num_pruned = 0;
     uint32_t next_idx = 1, rr = 0, qsize = 1;                            // qsize = pqueue.len() (cur included)
     uint32_t free_top = 0, rec_next = 1, fs_top = 0;                     // record 0 = root
-    if (lane == 0) atomicAdd(s.lencnt + 0, 1u);
+    if (lane == 0) lc[0] = 1u;
 
     uint64_t c_hi = ~0ull; uint32_t c_idx = 0xffffffffu, c_pos = 0, cnt = 0;
     MainKey qmin; qmin.hi = ~0ull; qmin.idx = 0xffffffffu;
@@ -1258,6 +1281,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     int cur_src = SRC_ROOT;
     uint32_t cur_x1 = 0, cur_x2 = 0;
     uint32_t heur_p = cur_total;                                         // heuristic term inside cur_total
+    // H[p+1] and ignored[p] of cur's column p are loaded one expansion ahead (L2 latency off the dive's critical path)
+    uint32_t heur_c = Hg[1 <= N ? 1 : 0];
+    bool bad_c = N > 0 && __ldg(ign) != 0;
     uint64_t cur_w1 = 0, cur_w2 = 0;                                     // lane wi: words wi of cur's h1 / h2 (HW <= 32)
     const bool regs_hap = HW <= 32;
     uint32_t nA0[K], nA1[K], nB0[K], nB1[K], nW[K];
@@ -1272,8 +1298,11 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         coln[k] = (1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
 
+    long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0;   // counting variant only
     for (;;) {
+        if (kCount) tq0 = clock64();
         if (!have_cur || key_less(qmin.hi, qmin.idx, ((uint64_t)cur_total << 32) | cur_nh, cur_idx)) {
+            if (kCount) n_real++;
             if (have_cur) {                                              // cur goes back to the queue
                 const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
                 if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
@@ -1292,8 +1321,8 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             if (qmin.hi == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }   // empty queue: the reference panics (:631)
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, c_hi == qmin.hi && c_idx == qmin.idx)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, c_pos, owner);
-            cur_total = (uint32_t)(qmin.hi >> 32); cur_nh = (uint32_t)qmin.hi; cur_idx = qmin.idx;
             const uint32_t lenf = *klen_at(owner, pos);
+            cur_total = (uint32_t)(qmin.hi >> 32); cur_nh = (uint32_t)qmin.hi; cur_idx = qmin.idx;
             cur_len = lenf & 0x7fffffffu; cur_ident = (lenf >> 31) != 0;
             cur_rec = *krec_at(owner, pos);
             if (cur_len >= min_progress && cur_len < N) {                 // pruned / final nodes never need the payload
@@ -1311,6 +1340,8 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                     cur_src = SRC_CACHE; cur_x1 = cs & 1u; cur_x2 = (0x9u >> cs) & 1u;
                 } else cur_src = SRC_PLANES;
                 heur_p = Hg[cur_len];
+                heur_c = Hg[cur_len + 1];
+                bad_c = __ldg(ign + cur_len) != 0;
                 o_p = __ldg(aoff + cur_len); o_p1 = __ldg(aoff + cur_len + 1);
                 o_p2 = (cur_len + 2 <= N) ? __ldg(aoff + cur_len + 2) : o_p1;
 #pragma unroll
@@ -1337,11 +1368,38 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             qmin = wmin96(c_hi, c_idx);
             have_cur = true;
         }
-        // ---- cur is the top ----
+        // ---- cur is the top of the live entries: the reference first pops and discards every dead entry with a smaller
+        //      key, one by one, and nothing else happens in between (:507-515) ----
+        if (pool_n != 0 && key_less(pool_min.hi, pool_min.idx, ((uint64_t)cur_total << 32) | cur_nh, cur_idx)) {
+            const uint64_t k_hi = ((uint64_t)cur_total << 32) | cur_nh;
+            uint32_t base = 0;
+            uint64_t m_hi = ~0ull; uint32_t m_idx = 0xffffffffu;
+            for (uint32_t c0 = 0; c0 < pool_n; c0 += 32) {
+                const uint32_t i = c0 + lane;
+                const bool in = i < pool_n;
+                uint64_t hi = ~0ull; uint32_t ix = 0xffffffffu;
+                if (in) { hi = pool_hi[i]; ix = pool_idx[i]; }
+                const bool keep = in && !key_less(hi, ix, k_hi, cur_idx);
+                const uint32_t km = __ballot_sync(HP_FULL_MASK, keep);
+                if (keep) {
+                    const uint32_t d = base + __popc(km & ((1u << lane) - 1u));
+                    pool_hi[d] = hi; pool_idx[d] = ix;
+                    if (key_less(hi, ix, m_hi, m_idx)) { m_hi = hi; m_idx = ix; }
+                }
+                base += __popc(km);
+            }
+            __syncwarp();
+            const uint32_t k = pool_n - base;
+            pool_n = base;
+            pool_min = wmin96(m_hi, m_idx);
+            if (num_pruned == 0) curr_thresh = a.min_queue_size;          // :508-510 (k >= 1 here)
+            num_pruned += k; qsize -= k; w.pops += k;
+            if (kCount) n_swept += k;
+        }
         const uint32_t L = cur_len;
         if (L >= N) break;                                                // :492
         qsize--;
-        if (lane == 0) atomicAdd(s.lencnt + L, 0xffffffffu);              // hap_tracker.remove_hap (:495)
+        if (lane == 0) lc[L] -= 1u;                                       // hap_tracker.remove_hap (:495)
         if (L >= trk_thresh) trk_total--;
         w.pops++;
         if (L == next_expected) {                                         // :497-504
@@ -1355,8 +1413,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             else { if (lane == 0) s.freelist[free_top] = cur_rec; free_top++; }
             have_cur = false;
             __syncwarp();
+            if (kCount) tm_pop += clock64() - tq0;
             continue;
         }
+        if (kCount) { const long long t1 = clock64(); tm_pop += t1 - tq0; tq0 = t1; }
 
         // ---- expand column p = L ----
         const uint32_t p = L;
@@ -1365,9 +1425,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         uint32_t colnn[K];
 #pragma unroll
         for (int k = 0; k < K; k++) colnn[k] = (p + 2 < N) ? __ldg(col_lane + o_p2 + 32u * k) : kEmpty;
-        const uint32_t heur = Hg[p + 1];
-        const bool bad_col = __ldg(ign + p) != 0;
+        const uint32_t heur = heur_c;
+        const bool bad_col = bad_c;
         const bool ident = cur_ident;
+        if (p + 1 < N) { heur_c = Hg[p + 2]; bad_c = __ldg(ign + p + 1) != 0; }
 
         uint32_t s1[K], s2[K], wv[K];
         if (cur_src == SRC_CACHE) {
@@ -1420,6 +1481,11 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         if (__ballot_sync(HP_FULL_MASK, anyend)) { f0 = wsum(e01); f1 = wsum(e10); f2 = wsum(e00); f3 = wsum(e11); }
         const uint32_t present = present_mask(bad_col, ident);
         const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
+        if (kCount) {
+            const long long t1 = clock64(); tm_exp += t1 - tq0;
+            if (cur_src == SRC_PLANES) { tm_planes += t1 - tq0; n_planes++; }
+            tq0 = t1;
+        }
         if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
         if (qsize + nchild + 64 > a.qcap || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
 
@@ -1565,7 +1631,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             if (best != 3u && t3 != 0xffffffffu && key_less(h3, i3, qmin.hi, qmin.idx)) { qmin.hi = h3; qmin.idx = i3; }
         }
         next_idx += nchild; qsize += nchild;
-        if (lane == 0) atomicAdd(s.lencnt + L + 1, nchild);               // tracker.add_hap(L+1) x nchild (:531, :558)
+        if (lane == 0) lc[L + 1] += nchild;                               // tracker.add_hap(L+1) x nchild (:531, :558)
         if (L + 1 >= trk_thresh) trk_total += nchild;
         // ---- the best child is the new cur (record inherited in place) ----
         cur_total = tmin;
@@ -1587,13 +1653,70 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         // ---- pruning bookkeeping (:564-585) ----
         while (trk_total > curr_thresh && min_progress < next_expected) {
             min_progress++;
+            const uint32_t dl = min_progress - 1;                          // entries of exactly this length die now
             uint32_t dropped = 0;
-            if (lane == 0) dropped = atomicAdd(s.lencnt + min_progress - 1, 0u);
+            if (lane == 0) dropped = lc[dl];
             dropped = __shfl_sync(HP_FULL_MASK, dropped, 0);
             trk_total -= dropped; trk_thresh = min_progress;
-            if (qsize > max_queue) {
-                // "full prune": every queued entry shorter than min_progress gets the cleared priority (cost 0);
-                // cur has length >= next_expected >= min_progress and is never affected
+            // sweep policy: any subset of the dead entries may move to the pool at any time (dead pops commute); entries
+            // left in their stripe are discarded by the ordinary pop path when they surface
+            if (kDeadPool && dropped != 0 && qsize > kSweepMinQueue) {
+                if (lane == 0) { *w.free_ctr = free_top; *w.pool_ctr = pool_n; }
+                __syncwarp();
+                uint32_t j = 0;
+                uint64_t m_hi = ~0ull; uint32_t m_idx = 0xffffffffu;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t ln = *klen_at(lane, i);
+                    if ((ln & 0x7fffffffu) <= dl) {
+                        const uint64_t hi = *khi_at(lane, i); const uint32_t ix = *kidx_at(lane, i);
+                        const uint32_t ps = atomicAdd(w.pool_ctr, 1u);
+                        pool_hi[ps] = hi; pool_idx[ps] = ix;
+                        s.freelist[atomicAdd(w.free_ctr, 1u)] = *krec_at(lane, i);
+                        if (key_less(hi, ix, m_hi, m_idx)) { m_hi = hi; m_idx = ix; }
+                    } else {
+                        if (j != i) {
+                            *khi_at(lane, j) = *khi_at(lane, i); *kidx_at(lane, j) = *kidx_at(lane, i);
+                            *klen_at(lane, j) = ln; *krec_at(lane, j) = *krec_at(lane, i);
+                        }
+                        j++;
+                    }
+                }
+                if (j != cnt) {                                            // this stripe lost entries: new cached minimum
+                    cnt = j;
+                    c_hi = ~0ull; c_idx = 0xffffffffu; c_pos = 0;
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const uint64_t hi = *khi_at(lane, i); const uint32_t ix = *kidx_at(lane, i);
+                        if (key_less(hi, ix, c_hi, c_idx)) { c_hi = hi; c_idx = ix; c_pos = i; }
+                    }
+                }
+                __syncwarp();
+                free_top = *w.free_ctr; pool_n = *w.pool_ctr;
+                __syncwarp();
+                if (have_cur && cur_len <= dl) {                           // the node in registers dies as well
+                    const uint64_t hi = ((uint64_t)cur_total << 32) | cur_nh;
+                    if (lane == 0) { pool_hi[pool_n] = hi; pool_idx[pool_n] = cur_idx; s.freelist[free_top] = cur_rec; }
+                    pool_n++; free_top++;
+                    if (key_less(hi, cur_idx, m_hi, m_idx)) { m_hi = hi; m_idx = cur_idx; }
+                    have_cur = false;
+                    __syncwarp();
+                }
+                const MainKey nm = wmin96(m_hi, m_idx);
+                if (key_less(nm.hi, nm.idx, pool_min.hi, pool_min.idx)) pool_min = nm;
+                qmin = wmin96(c_hi, c_idx);
+            }
+            if (kDeadPool && qsize > max_queue) {
+                // "full prune": every dead entry gets the cleared priority (cost 0)
+                uint64_t m_hi = ~0ull; uint32_t m_idx = 0xffffffffu;
+                for (uint32_t i = lane; i < pool_n; i += 32) {
+                    const uint64_t hi = pool_hi[i] & 0xffffffffull; const uint32_t ix = pool_idx[i];
+                    pool_hi[i] = hi;
+                    if (key_less(hi, ix, m_hi, m_idx)) { m_hi = hi; m_idx = ix; }
+                }
+                __syncwarp();
+                pool_min = wmin96(m_hi, m_idx);
+            }
+            if (qsize > max_queue) {                                       // ... including the ones still in their stripe
+                if (have_cur && cur_len < min_progress) cur_total = 0;     // and the node held in registers
                 c_hi = ~0ull; c_idx = 0xffffffffu; c_pos = 0;
                 for (uint32_t i = 0; i < cnt; i++) {
                     uint64_t hi = *khi_at(lane, i);
@@ -1605,6 +1728,12 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 qmin = wmin96(c_hi, c_idx);
             }
         }
+        if (kCount) tm_rest += clock64() - tq0;
+    }
+    if (kCount && a.dbg_cycles && lane == 0) {
+        uint64_t* d = a.dbg_cycles + 16ull * blk;
+        d[8] = tm_pop; d[9] = tm_exp; d[10] = tm_rest; d[11] = n_planes; d[12] = tm_planes;
+        d[13] = n_real; d[14] = num_pruned; d[15] = qsize; d[7] = n_swept;
     }
     if (w.status != HP_BLOCK_OK) return;
 
@@ -1649,6 +1778,7 @@ struct TeamShared {
     unsigned long long ctr[4];       // accepted work counters (evals, cells, sum_lp, pops)
     uint32_t hring[64];
     uint32_t free_stack[kFreeStack];
+    uint32_t free_ctr, pool_ctr;
 };
 
 __device__ __forceinline__ uint64_t bad_window(const uint8_t* ign, uint32_t v, uint32_t N, uint32_t lane) {
@@ -1764,7 +1894,10 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
     __syncthreads();
 }
 
-constexpr int kSubCaplShared = 12;    // sub-solver queue entries per stripe kept in shared memory (rest: global spill)
+#ifndef HP_SUB_CAPL_S
+#define HP_SUB_CAPL_S 8
+#endif
+constexpr int kSubCaplShared = HP_SUB_CAPL_S;    // sub-solver queue entries per stripe kept in shared memory (rest: global spill)
 
 // One kernel per score-vector class K (1: <= 32 reads per column, 2: <= 64, 0: any) keeps the register footprint of the
 // common class small.  Class c owns order[class_start[c] .. +class_count[c]) and ticket[c].
@@ -1791,12 +1924,19 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     const uint64_t spill_bytes = (uint64_t)32 * (w.capl - w.capl_s) * sizeof(SubEntry);
     w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)(kMaxTeam - warp) * spill_bytes);
     // main-queue keys reuse the whole team's sub-queue shared memory (12 B per key)
-    w.mq_cap_s = (uint32_t)(((size_t)team * w.capl_s * 32 * sizeof(SubEntry)) / (32 * 20));
+    // ... minus a 4 KB tail for the tracker's length counts
+    const size_t team_smem = (size_t)team * w.capl_s * 32 * sizeof(SubEntry);
+    const size_t lencnt_bytes = team_smem >= 8192 ? 4096 : 0;
+    w.lencnt_s = (uint32_t*)(smem_raw + team_smem - lencnt_bytes);
+    w.lencnt_cap_s = (uint32_t)(lencnt_bytes / 4);
+    w.mq_cap_s = (uint32_t)((team_smem - lencnt_bytes) / (32 * 20));
     w.mq_hi = (uint64_t*)smem_raw;
     w.mq_idx = (uint32_t*)(smem_raw + (size_t)32 * w.mq_cap_s * 8);
     w.mq_len = w.mq_idx + (size_t)32 * w.mq_cap_s;
     w.mq_rec = w.mq_len + (size_t)32 * w.mq_cap_s;
     w.free_stack = ts.free_stack;
+    w.free_ctr = &ts.free_ctr;
+    w.pool_ctr = &ts.pool_ctr;
 
     for (;;) {
         __syncthreads();

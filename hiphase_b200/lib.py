@@ -9,7 +9,8 @@ import subprocess
 from . import _abi as A
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libhiphase_b200.so")
+# HP_B200_LIB: kernel-development override (A/B builds of the same ABI); the product path is the in-tree .so
+LIB_PATH = os.environ.get("HP_B200_LIB") or os.path.join(CSRC, "libhiphase_b200.so")
 
 EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",

@@ -23,8 +23,11 @@ print("pre-pass: cycles/pop mean %.0f  cycles/block mean %.3g max %.3g" % ((d[:,
 print("main    : cycles/pop mean %.0f  cycles/block mean %.3g max %.3g" % ((d[:, 1] / np.maximum(d[:, 3], 1)).mean(), d[:, 1].mean(), d[:, 1].max()))
 tot = d[:, 0] + d[:, 1]
 print("sum pre-pass %.3g  sum main %.3g  slowest block %.3g cycles" % (d[:, 0].sum(), d[:, 1].sum(), tot.max()))
+mp = d[:, 8:11].sum(0)
+print("main split (all blocks): real-pop %.3g  expand %.3g  rest %.3g cycles | real pops %d  pruned %d  plane-rescored expansions %d (%.3g cycles)"
+      % (mp[0], mp[1], mp[2], d[:, 13].sum(), d[:, 14].sum(), d[:, 11].sum(), d[:, 12].sum()))
 print("5 slowest blocks: [total, pre-pass, main cycles | pops pre-pass, main | variants/round] then main split "
       "[real-pop, expand, rest (records+push+prune) cycles | real pops, pruned, final queue]")
 for k in np.argsort(tot)[-5:]:
     print("  ", [int(tot[k]), int(d[k, 0]), int(d[k, 1])], [int(d[k, 2]), int(d[k, 3])], "%.2f" % (nvar[k] / d[k, 4]),
-          d[k, 8:11].astype(np.int64).tolist(), d[k, 13:16].astype(np.int64).tolist())
+          d[k, 8:11].astype(np.int64).tolist(), d[k, 13:16].astype(np.int64).tolist(), "planes", d[k, 11:13].astype(np.int64).tolist())
