@@ -274,3 +274,82 @@ class PostOut:
 
     def as_struct(self):
         return hp_post_out(ptr(self.span_counts, u32p), ptr(self.block_tags, u64p), ptr(self.read_haplotag, u8p), ptr(self.read_tag, u64p))
+
+
+# ---- local realignment (src/read_parsing.rs:121-503) ------------------------------------------
+HP_LOCAL_OK, HP_LOCAL_UNHANDLED_TYPE, HP_LOCAL_BAD_SLICE, HP_LOCAL_ALLELE_TOO_LONG = 0, 1, 2, 3
+HP_LOCAL_OVERLAPS, HP_LOCAL_EXACT = 1, 2
+
+
+class hp_local_batch(C.Structure):
+    _fields_ = [("n_jobs", C.c_uint32), ("variants", hp_variant_table), ("prefix_len", u32p), ("postfix_len", u32p),
+                ("var_lo", u32p), ("var_hi", u32p), ("read_pos", i64p), ("seg_off", u64p), ("seg_ref_start", i64p),
+                ("seg_read_start", u32p), ("seg_len", u32p), ("read_bytes", u8p), ("read_quals", u8p),
+                ("read_off", u64p), ("row_off", u64p)]
+
+
+class hp_local_out(C.Structure):
+    _fields_ = [("alleles", u8p), ("quals", u8p), ("match_class", u8p), ("edit_distance", u32p), ("status", i32p)]
+
+
+class LocalBatch:
+    """numpy side of hp_local_batch.  variants: dict of arrays as for WfaBatch (FULL alleles) + prefix_len/postfix_len;
+    jobs: per read mapping var_lo/var_hi, read_pos, aligned segments (seg_off CSR), read bytes and base qualities."""
+
+    def __init__(self, variants, var_lo, var_hi, read_pos, seg_off, seg_ref_start, seg_read_start, seg_len,
+                 read_bytes, read_quals, read_off):
+        v = variants
+        self.position = _np(v["position"], np.int64)
+        self.ref_len = _np(v["ref_len"], np.uint32)
+        self.allele0_off = _np(v["allele0_off"], np.uint64)
+        self.allele0_len = _np(v["allele0_len"], np.uint32)
+        self.allele1_off = _np(v["allele1_off"], np.uint64)
+        self.allele1_len = _np(v["allele1_len"], np.uint32)
+        self.index_allele0 = _np(v.get("index_allele0", np.zeros(len(self.position))), np.uint8)
+        self.vtype = _np(v["vtype"], np.uint8)
+        self.ignored = _np(v["ignored"], np.uint8)
+        self.allele_bytes = _np(v["allele_bytes"], np.uint8)
+        self.prefix_len = _np(v["prefix_len"], np.uint32)
+        self.postfix_len = _np(v["postfix_len"], np.uint32)
+        self.var_lo = _np(var_lo, np.uint32)
+        self.var_hi = _np(var_hi, np.uint32)
+        self.read_pos = _np(read_pos, np.int64)
+        self.seg_off = _np(seg_off, np.uint64)
+        self.seg_ref_start = _np(seg_ref_start, np.int64)
+        self.seg_read_start = _np(seg_read_start, np.uint32)
+        self.seg_len = _np(seg_len, np.uint32)
+        self.read_bytes = _np(read_bytes, np.uint8)
+        self.read_quals = _np(read_quals, np.uint8)
+        self.read_off = _np(read_off, np.uint64)
+        self.n_jobs = len(self.var_lo)
+        row_len = self.var_hi.astype(np.int64) - self.var_lo.astype(np.int64)
+        self.row_off = np.concatenate([[0], np.cumsum(row_len)]).astype(np.uint64)
+
+    @property
+    def n_variants(self):
+        return len(self.position)
+
+    def as_struct(self):
+        vt = hp_variant_table(self.n_variants, ptr(self.position, i64p), ptr(self.ref_len, u32p),
+                              ptr(self.allele0_off, u64p), ptr(self.allele0_len, u32p), ptr(self.allele1_off, u64p),
+                              ptr(self.allele1_len, u32p), ptr(self.index_allele0, u8p), ptr(self.vtype, u8p),
+                              ptr(self.ignored, u8p), ptr(self.allele_bytes, u8p), len(self.allele_bytes))
+        return hp_local_batch(self.n_jobs, vt, ptr(self.prefix_len, u32p), ptr(self.postfix_len, u32p),
+                              ptr(self.var_lo, u32p), ptr(self.var_hi, u32p), ptr(self.read_pos, i64p),
+                              ptr(self.seg_off, u64p), ptr(self.seg_ref_start, i64p), ptr(self.seg_read_start, u32p),
+                              ptr(self.seg_len, u32p), ptr(self.read_bytes, u8p), ptr(self.read_quals, u8p),
+                              ptr(self.read_off, u64p), ptr(self.row_off, u64p))
+
+
+class LocalOut:
+    def __init__(self, batch):
+        n = int(batch.row_off[-1])
+        self.alleles = np.full(n, 255, np.uint8)
+        self.quals = np.full(n, 255, np.uint8)
+        self.match_class = np.full(n, 255, np.uint8)
+        self.edit_distance = np.zeros(2 * n, np.uint32)
+        self.status = np.full(batch.n_jobs, -1, np.int32)
+
+    def as_struct(self):
+        return hp_local_out(ptr(self.alleles, u8p), ptr(self.quals, u8p), ptr(self.match_class, u8p),
+                            ptr(self.edit_distance, u32p), ptr(self.status, i32p))

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("HP_B200_LIB") or os.path.join(CSRC, "libhiphase_b200.
 
 EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
-           "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch")
+           "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch",
+           "hp_local_realign_batch", "hp_edit_distance_batch")
 
 _LIB = None
 
@@ -58,6 +59,8 @@ def lib():
         L.hp_post_solve_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), A.i64p, A.u8p, A.u8p, C.POINTER(A.hp_post_out)]
         L.hp_wfa_graph_align.argtypes = [C.c_void_p, C.c_uint32, A.u8p, A.u64p, A.u32p, A.u64p, A.u8p, C.c_uint64,
                                          C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), A.u64p]
+        L.hp_local_realign_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_local_batch), C.POINTER(A.hp_local_out)]
+        L.hp_edit_distance_batch.argtypes = [C.c_void_p, C.c_uint32, A.u8p, C.c_uint64, A.u64p, A.u32p, A.u64p, A.u32p, A.u32p]
         _LIB = L
     return _LIB
 
@@ -142,6 +145,30 @@ class Context:
                                             C.byref(st), C.byref(sc), A.ptr(trav, A.u64p)))
         nodes = [i for i in range(n) if (int(trav[i // 64]) >> (i % 64)) & 1]
         return st.value, sc.value, nodes
+
+    # ---- local realignment ----
+    def local_realign_batch(self, batch):
+        """Host buffers in / out: local_realignment (read_parsing.rs:121-503) for a batch of read mappings.  Returns a LocalOut."""
+        out = A.LocalOut(batch)
+        bs, os_ = batch.as_struct(), out.as_struct()
+        self.check(lib().hp_local_realign_batch(self._h, C.byref(bs), C.byref(os_)))
+        return out
+
+    def edit_distance_batch(self, pairs):
+        """sequence_alignment::edit_distance (sequence_alignment.rs:6-38) for a list of (a, b) byte sequences."""
+        import numpy as np
+        seqs, a_off, a_len, b_off, b_len, pos = [], [], [], [], [], 0
+        for x, y in pairs:
+            for off, ln, z in ((a_off, a_len, x), (b_off, b_len, y)):
+                z = np.asarray(list(z), np.uint8)
+                off.append(pos); ln.append(len(z)); seqs.append(z); pos += len(z)
+        blob = np.concatenate(seqs) if pos else np.zeros(1, np.uint8)
+        a_off = np.asarray(a_off, np.uint64); b_off = np.asarray(b_off, np.uint64)
+        a_len = np.asarray(a_len, np.uint32); b_len = np.asarray(b_len, np.uint32)
+        dist = np.zeros(len(pairs), np.uint32)
+        self.check(lib().hp_edit_distance_batch(self._h, len(pairs), A.ptr(blob, A.u8p), pos, A.ptr(a_off, A.u64p), A.ptr(a_len, A.u32p),
+                                                A.ptr(b_off, A.u64p), A.ptr(b_len, A.u32p), A.ptr(dist, A.u32p)))
+        return dist
 
     def astar_solve_device(self, dev_batch_struct, n_vars, n_reads, n_cells, max_block_vars, dev_out_struct, stream):
         self.check(lib().hp_astar_solve_device(self._h, C.byref(dev_batch_struct), n_vars, n_reads, n_cells,

@@ -322,3 +322,158 @@ def blocks_from_wfa_rows(batch, out, job_block, meta, min_set=2):
         start = int(batch.het_lo[j]) - m["het_base"] + lo
         blocks[job_block[j]]["reads"].append((start, a[lo:hi].copy(), q[lo:hi].copy()))
     return BlockBatch.from_blocks(blocks)
+
+
+# ---- local realignment jobs ---------------------------------------------------------------------
+def extend_with_reference(variants, ref, reference_buffer=15):
+    """Reference prefix / postfix of the het variants exactly as load_variant_calls does it (src/phaser.rs:236-296):
+    up to `reference_buffer` bases either side, the previous variant's postfix truncated where two variants crowd."""
+    previous_het_end = 0
+    for i, v in enumerate(variants):
+        pos, ref_len = v.position(), v.get_ref_len()
+        ref_prefix_start = pos - reference_buffer if pos > reference_buffer else 0
+        ref_postfix_start = pos + ref_len
+        if ref_prefix_start < previous_het_end:
+            prev = variants[i - 1]
+            current_end = prev.position() + prev.get_ref_len() + prev.get_postfix_len()
+            prev.truncate_reference_postfix(min(max(current_end - pos, 0), prev.get_postfix_len()))
+            ref_prefix_start = min(previous_het_end, pos)
+        v.add_reference_prefix(ref[ref_prefix_start:pos].tobytes())
+        v.add_reference_postfix(ref[ref_postfix_start:ref_postfix_start + reference_buffer].tobytes())
+        previous_het_end = pos + ref_len
+
+
+def gen_local_block(rng, window=30000, n_var=40, n_reads=60, read_lo=4000, read_hi=15000, err=0.003, sv_max=1500,
+                    reference_buffer=15, p_ignored=0.02):
+    """One block for local realignment: reference window, het variants (with reference prefix / postfix), reads sampled
+    from the two haplotypes and their alignments (gap-free aligned segments, the M/=/X runs of a CIGAR).
+    Returns dict(variants=[Variant], jobs=[(var_lo, var_hi, read_pos, segs[(ref, read, len)], seq, quals)])."""
+    from .variants import Variant
+    ref = _rand_seq(rng, window)
+    pos = np.sort(rng.choice(np.arange(100, window - sv_max - 300), n_var, replace=False))
+    vs, phase = [], []
+    for p in (int(x) for x in pos):
+        u = rng.random()
+        if u < 0.6:
+            alt = _BASES[(int(np.searchsorted(_BASES, ref[p])) + int(rng.integers(1, 4))) % 4]
+            v = Variant(0, _VT_SNV, p, 1, ref[p:p + 1].tobytes(), bytes([alt]))
+        elif u < 0.8:
+            kind, k = int(rng.integers(0, 3)), int(rng.integers(1, 21))
+            if kind == 0:
+                v = Variant(0, _VT_INS, p, 1, ref[p:p + 1].tobytes(), ref[p:p + 1].tobytes() + _rand_seq(rng, k).tobytes())
+            elif kind == 1:
+                v = Variant(0, _VT_DEL, p, k + 1, ref[p:p + k + 1].tobytes(), ref[p:p + 1].tobytes())
+            else:
+                r = int(rng.integers(2, 11))
+                v = Variant(0, _VT_INDEL, p, r, ref[p:p + r].tobytes(), ref[p:p + 1].tobytes() + _rand_seq(rng, int(rng.integers(1, 10))).tobytes())
+        elif u < 0.85:     # multi-allelic indel, both alleles ALT
+            r = int(rng.integers(2, 8))
+            v = Variant(0, _VT_INDEL, p, r, ref[p:p + 1].tobytes() + _rand_seq(rng, int(rng.integers(1, 6))).tobytes(),
+                        ref[p:p + 1].tobytes() + _rand_seq(rng, int(rng.integers(6, 12))).tobytes(), 1, 2)
+        elif u < 0.92:
+            motif, L = _rand_seq(rng, int(rng.integers(2, 7))), int(rng.integers(10, 60))
+            exp = np.tile(motif, 40)[: int(rng.integers(10, 201))]
+            v = Variant(0, _VT_TR, p, L, ref[p:p + L].tobytes(), ref[p:p + L].tobytes() + exp.tobytes())
+        else:
+            L = int(rng.integers(50, sv_max + 1))
+            if rng.random() < 0.5:
+                v = Variant(0, _VT_SVINS, p, 1, ref[p:p + 1].tobytes(), ref[p:p + 1].tobytes() + _rand_seq(rng, L).tobytes())
+            else:
+                v = Variant(0, _VT_SVDEL, p, L + 1, ref[p:p + L + 1].tobytes(), ref[p:p + 1].tobytes())
+        vs.append(v); phase.append(int(rng.integers(0, 2)))
+    raw = [(v.get_allele0(), v.get_allele1()) for v in vs]      # alleles before the reference extension
+    extend_with_reference(vs, ref, reference_buffer)
+    for v in vs:
+        if rng.random() < p_ignored:
+            v.set_ignored()
+    vpos = np.array([v.position() for v in vs])
+
+    jobs = []
+    for _ in range(n_reads):
+        h = int(rng.integers(0, 2))
+        ln = int(rng.integers(read_lo, read_hi + 1))
+        s = int(rng.integers(0, max(1, window - ln)))
+        e = min(window, s + ln)
+        seq, segs = [], []
+        rd = 0                          # read cursor
+        run = None                      # open aligned run [ref_start, read_start, len]
+
+        def close():
+            nonlocal run
+            if run is not None and run[2] > 0:
+                segs.append(tuple(run))
+            run = None
+
+        def emit_match(lo, hi):
+            nonlocal rd, run
+            n = hi - lo
+            if n <= 0:
+                return
+            r = rng.random(n)
+            for i in range(n):
+                x = r[i]
+                if x < err / 3:                      # deletion error: reference base without a read base
+                    close()
+                    continue
+                if x < 2 * err / 3:                  # insertion error before this base
+                    close()
+                    seq.append(int(_BASES[rng.integers(0, 4)])); rd += 1
+                if run is None:
+                    run = [lo + i, rd, 0]
+                run[2] += 1
+                seq.append(int(ref[lo + i])); rd += 1
+
+        cur = s
+        for k, v in enumerate(vs):
+            p, rl = v.position(), v.get_ref_len()
+            if p < cur or p + rl > e:
+                continue
+            emit_match(cur, p)
+            al = np.frombuffer(raw[k][1] if phase[k] == h else raw[k][0], np.uint8)
+            m = min(len(al), rl)
+            if run is None:
+                run = [p, rd, 0]
+            run[2] += m
+            seq.extend(int(x) for x in al[:m]); rd += m
+            if len(al) > m:                          # insertion
+                close()
+                seq.extend(int(x) for x in al[m:]); rd += len(al) - m
+            elif rl > m:                             # deletion
+                close()
+            cur = p + rl
+        emit_match(cur, e)
+        close()
+        if not segs:
+            continue
+        seq = np.array(seq, np.uint8)
+        sub = rng.random(len(seq)) < err / 3
+        seq[sub] = _BASES[rng.integers(0, 4, int(sub.sum()))]
+        q = rng.integers(15, 60, len(seq)).astype(np.uint8)
+        low = rng.random(len(seq)) < 0.03
+        q[low] = rng.integers(0, 10, int(low.sum()))
+        jobs.append((int(np.searchsorted(vpos, s)), int(np.searchsorted(vpos, e)), segs[0][0], segs, seq, q))
+    return dict(variants=vs, jobs=jobs, reference=ref)
+
+
+def config_local(n_blocks=8, first_block=0, full_rows=False, **kw):
+    """Local-realignment batch over n_blocks blocks.  full_rows=True gives every job the block's whole variant list (the
+    reference calls local_realignment with all variants of the block, read_parsing.rs:568)."""
+    from ._abi import LocalBatch
+    from .variants import variant_table
+    allv, var_lo, var_hi, read_pos, seg_off, sr, sd, sl, reads, quals = [], [], [], [], [0], [], [], [], [], []
+    for b in range(first_block, first_block + n_blocks):
+        rng = np.random.default_rng(block_seed(6, b))
+        blk = gen_local_block(rng, **kw)
+        base = len(allv)
+        allv.extend(blk["variants"])
+        for (lo, hi, rp, segs, seq, q) in blk["jobs"]:
+            var_lo.append(base if full_rows else base + lo)
+            var_hi.append(base + len(blk["variants"]) if full_rows else base + hi)
+            read_pos.append(rp)
+            for (a, r, n) in segs:
+                sr.append(a); sd.append(r); sl.append(n)
+            seg_off.append(len(sr))
+            reads.append(seq); quals.append(q)
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])])
+    return LocalBatch(variant_table(allv), var_lo, var_hi, read_pos, seg_off, sr, sd, sl,
+                      np.concatenate(reads), np.concatenate(quals), read_off)

@@ -268,6 +268,69 @@ int hp_wfa_graph_align(hp_ctx* ctx, uint32_t n_nodes, const uint8_t* seq, const 
                        uint64_t prune_distance /* UINT64_MAX = off */, uint32_t max_edit_distance,
                        int32_t* status, uint32_t* score, uint64_t* traversed);
 
+
+/* ---- local realignment: replaces local_realignment (src/read_parsing.rs:121-503),
+ *      Variant::match_allele / closest_allele_clip (src/data_types/variants.rs:598-641) and
+ *      sequence_alignment::edit_distance (src/sequence_alignment.rs:6-38).  This is the path every read takes when
+ *      graph-WFA reports MaxEditDistance or global realignment is switched off for a block (read_parsing.rs:564-600). -- */
+
+/* per-job status written to hp_local_out.status */
+#define HP_LOCAL_OK                0
+#define HP_LOCAL_UNHANDLED_TYPE    1   /* a reachable variant is SvDuplication / SvInversion / SvBreakend / Unknown:  */
+                                       /* the reference panics (read_parsing.rs:320-322, 452-454)                   */
+#define HP_LOCAL_BAD_SLICE         2   /* start index after end index in the read: the reference panics on the slice */
+#define HP_LOCAL_ALLELE_TOO_LONG   3   /* an inexact comparison with BOTH sequences longer than 16384 bases: outside  */
+                                       /* the kernel's range                                                        */
+
+/* bits of hp_local_out.match_class (the per-variant inputs of ReadStats, read_parsing.rs:457-477) */
+#define HP_LOCAL_OVERLAPS  1           /* overlaps_allele                                                           */
+#define HP_LOCAL_EXACT     2           /* exact_allele                                                              */
+
+/*
+ * Job j = one read mapping (bam::Record) against the variants [var_lo[j], var_hi[j]) of the table.
+ *   variants      the FULL alleles (Variant::get_allele0/1: reference prefix + allele + reference postfix, as built by
+ *                 src/phaser.rs:236-296) with prefix_len[] / postfix_len[] = get_prefix_len() / get_postfix_len()
+ *   read_pos[j]   bam::Record::pos()
+ *   segments      the gap-free runs of rust_htslib aligned_pairs() (CIGAR M/=/X): segment s maps reference
+ *                 [seg_ref_start[s], +seg_len[s]) onto read [seg_read_start[s], +seg_len[s]); ascending, non-overlapping
+ *   read bytes / base qualities at read_bytes[read_off[j] ..], read_quals[read_off[j] ..]
+ * Output row j has var_hi-var_lo cells at row_off[j].
+ */
+typedef struct hp_local_batch {
+    uint32_t         n_jobs;
+    hp_variant_table variants;        /* index_allele0 is not used by this path and may be NULL                     */
+    const uint32_t*  prefix_len;      /* [n_variants]                                                               */
+    const uint32_t*  postfix_len;     /* [n_variants]                                                               */
+    const uint32_t*  var_lo;          /* [n_jobs]                                                                   */
+    const uint32_t*  var_hi;          /* [n_jobs]                                                                   */
+    const int64_t*   read_pos;        /* [n_jobs]                                                                   */
+    const uint64_t*  seg_off;         /* [n_jobs+1]                                                                 */
+    const int64_t*   seg_ref_start;   /* [n_segs]                                                                   */
+    const uint32_t*  seg_read_start;  /* [n_segs]                                                                   */
+    const uint32_t*  seg_len;         /* [n_segs]                                                                   */
+    const uint8_t*   read_bytes;
+    const uint8_t*   read_quals;
+    const uint64_t*  read_off;        /* [n_jobs+1]                                                                 */
+    const uint64_t*  row_off;         /* [n_jobs+1]                                                                 */
+} hp_local_batch;
+
+typedef struct hp_local_out {
+    uint8_t*  alleles;        /* [row_off[n_jobs]] HP_ALLELE_*                                                      */
+    uint8_t*  quals;          /* [row_off[n_jobs]]                                                                  */
+    uint8_t*  match_class;    /* optional [row_off[n_jobs]] HP_LOCAL_OVERLAPS | HP_LOCAL_EXACT                      */
+    uint32_t* edit_distance;  /* optional [row_off[n_jobs]*2] (d0, d1) of closest_allele_clip where it ran, else 0,0 */
+    int32_t*  status;         /* [n_jobs] HP_LOCAL_*                                                                */
+} hp_local_out;
+
+/* Host buffers in / out. */
+int hp_local_realign_batch(hp_ctx* ctx, const hp_local_batch* batch, hp_local_out* out);
+
+/* sequence_alignment::edit_distance for n_pairs pairs: a = bytes[a_off[i] .. +a_len[i]), b likewise.  Host buffers.
+ * dist[i] = UINT32_MAX when both sequences are longer than 16384 bases (outside the kernel's range). */
+int hp_edit_distance_batch(hp_ctx* ctx, uint32_t n_pairs, const uint8_t* bytes, uint64_t n_bytes,
+                           const uint64_t* a_off, const uint32_t* a_len, const uint64_t* b_off, const uint32_t* b_len,
+                           uint32_t* dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,13 +3,14 @@
  *
  * TEST INFRASTRUCTURE ONLY.  This directory is a from-scratch CPU restatement of the reference algorithm
  * (PacificBiosciences/HiPhase v1.5.0, src/astar_phaser.rs, src/wfa_graph.rs, src/data_types/read_segments.rs,
- * src/read_parsing.rs:790-851).  It exists to CHECK the CUDA path and to be timed as the CPU baseline.
+ * src/read_parsing.rs:121-503 and 790-851, src/sequence_alignment.rs).  It exists to CHECK the CUDA path and to be timed as the CPU baseline.
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * Nothing under hiphase_b200/ links, imports or calls it.
  *
  * Parity pinning:
  *   - ReadSegment (clip / score / partial score / collapse), AstarNode costs+priorities, PQueueHapTracker and all
- *     19 WFA tests of the reference are transcribed as data in tests/golden/ and checked against this oracle.
+ *     19 WFA tests of the reference, plus edit_distance (sequence_alignment.rs:45-76) and match_allele /
+ *     closest_allele (variants.rs:668-846), are transcribed as data in tests/golden/ and checked against this oracle.
  *   - astar_solver / astar_subsolver / calculate_astar_heuristic have NO known-answer test in the reference
  *     (SURVEY.md section 8c): for those three functions parity is UNPINNED -- the oracle follows the code text of
  *     src/astar_phaser.rs:246-633 and is cross-checked against an independent pure-Python restatement
@@ -57,6 +58,13 @@ int hpo_astar_subsolver(const hp_params* params, const hp_block_batch* one_block
 
 /* ---- post-solve (src/phaser.rs:350-388, 546-569, 714-750) ---- */
 int hpo_post_solve_batch(const hp_block_batch* batch, const int64_t* var_pos, const uint8_t* h1, const uint8_t* h2, hp_post_out* out);
+
+/* ---- local realignment (src/read_parsing.rs:121-503, src/sequence_alignment.rs:6-38, variants.rs:598-641) ---- */
+uint64_t hpo_edit_distance(const uint8_t* a, uint64_t la, const uint8_t* b, uint64_t lb);
+uint8_t  hpo_match_allele(const hp_local_batch* batch, uint32_t variant, const uint8_t* seq, uint64_t n);
+uint8_t  hpo_closest_allele_clip(const hp_local_batch* batch, uint32_t variant, const uint8_t* seq, uint64_t n,
+                                 uint64_t head_clip, uint64_t tail_clip, uint64_t* d0, uint64_t* d1);
+int      hpo_local_realign_batch(const hp_local_batch* batch, hp_local_out* out);
 
 /* ---- WFA graph (src/wfa_graph.rs) ---- */
 typedef struct hpo_graph hpo_graph;

@@ -57,6 +57,14 @@ def lib():
         L.hpo_post_solve_batch.argtypes = [C.POINTER(A.hp_block_batch), A.i64p, A.u8p, A.u8p, C.POINTER(A.hp_post_out)]
         L.hpo_wfa_align_batch.argtypes = [C.POINTER(A.hp_params), C.POINTER(A.hp_wfa_batch), C.POINTER(A.hp_wfa_out),
                                           C.c_int]
+        L.hpo_edit_distance.restype = C.c_uint64
+        L.hpo_edit_distance.argtypes = [A.u8p, C.c_uint64, A.u8p, C.c_uint64]
+        L.hpo_match_allele.restype = C.c_uint8
+        L.hpo_match_allele.argtypes = [C.POINTER(A.hp_local_batch), C.c_uint32, A.u8p, C.c_uint64]
+        L.hpo_closest_allele_clip.restype = C.c_uint8
+        L.hpo_closest_allele_clip.argtypes = [C.POINTER(A.hp_local_batch), C.c_uint32, A.u8p, C.c_uint64, C.c_uint64,
+                                              C.c_uint64, A.u64p, A.u64p]
+        L.hpo_local_realign_batch.argtypes = [C.POINTER(A.hp_local_batch), C.POINTER(A.hp_local_out)]
         _LIB = L
     return _LIB
 
@@ -167,4 +175,29 @@ def post_solve(batch, var_pos, h1, h2):
     out = A.PostOut(batch)
     bs, os_ = batch.as_struct(), out.as_struct()
     out.rc = lib().hpo_post_solve_batch(C.byref(bs), A.ptr(var_pos, A.i64p), A.ptr(h1, A.u8p), A.ptr(h2, A.u8p), C.byref(os_))
+    return out
+
+
+def edit_distance(a, b):
+    a, b = u8(list(a)), u8(list(b))
+    return int(lib().hpo_edit_distance(A.ptr(a, A.u8p), len(a), A.ptr(b, A.u8p), len(b)))
+
+
+def match_allele(local_batch, variant, seq):
+    s = u8(list(seq)); bs = local_batch.as_struct()
+    return int(lib().hpo_match_allele(C.byref(bs), variant, A.ptr(s, A.u8p), len(s)))
+
+
+def closest_allele_clip(local_batch, variant, seq, head=0, tail=0):
+    """(allele, min distance, other distance) like Variant::closest_allele_clip (variants.rs:624-641)."""
+    s = u8(list(seq)); bs = local_batch.as_struct()
+    d0, d1 = C.c_uint64(), C.c_uint64()
+    a = int(lib().hpo_closest_allele_clip(C.byref(bs), variant, A.ptr(s, A.u8p), len(s), head, tail, C.byref(d0), C.byref(d1)))
+    return a, min(d0.value, d1.value), max(d0.value, d1.value)
+
+
+def local_realign(batch):
+    out = A.LocalOut(batch)
+    bs, os_ = batch.as_struct(), out.as_struct()
+    out.rc = lib().hpo_local_realign_batch(C.byref(bs), C.byref(os_))
     return out

@@ -144,3 +144,123 @@ def astar_solver(block, min_q=1000, inc=3):
         else:
             st["homozygous_variants"] += 1
     return h1, h2, st, H
+
+
+# ---- independent restatement of local_realignment (src/read_parsing.rs:121-503) in plain Python ----------------------
+def py_edit_distance(a, b):
+    """sequence_alignment.rs:6-38"""
+    prev = list(range(len(a) + 1))
+    for i, cb in enumerate(b):
+        row = [i + 1] + [0] * len(a)
+        for j, ca in enumerate(a):
+            row[j + 1] = min(prev[j + 1] + 1, row[j] + 1, prev[j] + (0 if ca == cb else 1))
+        prev = row
+    return prev[len(a)]
+
+
+def _as_u8(f):
+    if f != f or f <= 0.0:
+        return 0
+    return 255 if f >= 255.0 else int(f)
+
+
+def _rmin(a, b):      # f64::min: the non-NaN operand wins
+    return b if a != a else (a if b != b else min(a, b))
+
+
+def _rmax(a, b):
+    return b if a != a else (a if b != b else max(a, b))
+
+
+def py_local_realignment(variants, read_pos, segs, seq, quals):
+    """variants: list of dict(pos, ref_len, prefix_len, postfix_len, a0, a1 (bytes, full alleles), vtype, ignored);
+    segs: [(ref_start, read_start, len)].  Returns (alleles, quals, match_class, status)."""
+    lookup, max_position = {}, read_pos
+    for (r, d, n) in segs:
+        for i in range(n):
+            lookup[r + i] = d + i
+            max_position = max(max_position, r + i)
+    lo, hi = read_pos, max_position + 1
+    out_a, out_q, out_c, status = [], [], [], 0
+    last_deletion_end = 0
+    for v in variants:
+        pos, vt = v["pos"], v["vtype"]
+        allele, qual, exact, overlaps = 3, 0, False, False
+        if v["ignored"]:
+            pass
+        elif pos < last_deletion_end:
+            allele, overlaps = 2, True
+        elif vt in (0, 1, 2, 3, 4, 9):
+            pl, ql, rl = v["prefix_len"], v["postfix_len"], v["ref_len"]
+            first_start, last_start, first_end, last_end = pos - pl, pos + 1, pos + rl, pos + rl + ql + 1
+            cs = next((lookup[c] for c in range(last_start - 1, first_start - 1, -1) if c in lookup), None)
+            ce = next((lookup[c] for c in range(first_end, last_end) if c in lookup), None)
+            ss = se = None
+            start_clip = end_clip = 0
+            if cs is not None and ce is not None:
+                for sc in range(first_start, last_start):
+                    start_clip += 1
+                    if sc in lookup:
+                        if cs - lookup[sc] > 2 * pl:
+                            continue
+                        ss = lookup[sc]
+                        for ec in range(last_end - 1, first_end - 1, -1):
+                            end_clip += 1
+                            if ec in lookup:
+                                if lookup[ec] - ce > 2 * ql:
+                                    continue
+                                se = lookup[ec]
+                                break
+                        break
+            if ss is not None:
+                overlaps = True
+                if se is not None:
+                    obs = bytes(seq[ss:se])
+                    if obs == v["a0"]:
+                        allele, exact = 0, True
+                    elif obs == v["a1"]:
+                        allele, exact = 1, True
+                    else:
+                        h, t = start_clip - 1, end_clip - 1
+                        d0 = py_edit_distance(obs, v["a0"][h:len(v["a0"]) - t])
+                        d1 = py_edit_distance(obs, v["a1"][h:len(v["a1"]) - t])
+                        allele = 0 if d0 < d1 else (1 if d0 > d1 else 2)
+                    s = 0.0
+                    for q in quals[ss:se]:
+                        s += (1.0 / float(q)) if q else float("inf")
+                    n = float(se - ss)
+                    harmonic = (n / s) if s != 0.0 else float("nan")     # 0/0 (empty slice)
+                    factor = _rmin(harmonic / 40.0, 1.0)
+                    base = {0: 80.0, 9: 40.0, 4: 20.0}.get(vt, 10.0)
+                    qual = _as_u8(_rmax(base * factor, 1.0))
+                else:
+                    allele = 2
+            elif lo <= pos < hi:
+                allele, overlaps = 2, True
+        elif vt == 5:
+            if lo <= pos < hi:
+                overlaps, allele = True, 2
+                last_start, first_end = pos + 1, pos + v["ref_len"]
+                if lo <= first_end < hi:
+                    expected = first_end - last_start
+                    sa = last_start
+                    while sa not in lookup:
+                        if sa <= lo:
+                            break
+                        sa -= 1
+                    ea = first_end
+                    while ea not in lookup:
+                        ea += 1
+                        if ea >= hi:
+                            break
+                    deleted = sum(1 for c in range(sa, ea) if c not in lookup)
+                    ratio = (deleted / expected) if expected else (float("nan") if deleted == 0 else float("inf"))
+                    if ratio < 0.33:
+                        allele, qual, exact = 0, _as_u8(_rmax(20.0 * (1.0 - ratio), 1.0)), ratio == 0.0
+                    elif abs(1.0 - ratio) < 0.33:
+                        allele, qual, exact = 1, _as_u8(_rmax(20.0 * (1.0 - abs(1.0 - ratio)), 1.0)), ratio == 1.0
+                        last_deletion_end = first_end
+        else:
+            status = 1
+        out_a.append(allele); out_q.append(qual); out_c.append((1 if overlaps else 0) | (2 if exact else 0))
+    return out_a, out_q, out_c, status
