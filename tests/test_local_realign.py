@@ -231,3 +231,22 @@ def test_gpu_local_realign_sv_heavy(ctx):
     """Many SV insertions / deletions: long x long edit distances (warp-systolic path) and deletion masking."""
     batch = synth.config_local(3, full_rows=True, n_var=60, sv_max=3000, err=0.01)
     _same(ctx.local_realign_batch(batch), O.local_realign(batch))
+
+
+@pytest.mark.gpu
+def test_gpu_local_realignment_mirror():
+    """read_parsing.local_realignment(read, variants) with the reference's argument order; a CIGAR-described read."""
+    from hiphase_b200.read_parsing import AlignedRead, local_realignment
+    ref = b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"
+    snv = Variant(0, 0, 10, 1, b"G", b"T")
+    snv.add_reference_prefix(ref[7:10]); snv.add_reference_postfix(ref[11:14])
+    svd = Variant(0, 5, 20, 10, ref[20:30], ref[20:21])
+    inner = Variant(0, 0, 25, 1, b"C", b"A")
+    read = AlignedRead.from_cigar(0, [("S", 2), ("M", 21), ("D", 9), ("M", 10)], b"TT" + ref[:21] + ref[30:], [40] * 33)
+    assert read.segments == [(0, 2, 21), (30, 23, 10)]
+    alleles, quals, stats = local_realignment(read, [snv, svd, inner])
+    assert alleles == [0, 1, 2] and quals == [80, 20, 0]
+    assert stats.exact_matches[0] == 1 and stats.exact_matches[5] == 1 and stats.failed_matches[0] == 1
+    assert stats.allele0_matches[0] == 1 and stats.allele1_matches[5] == 1 and stats.num_alleles == 2 and stats.local_aligned == 1
+    with pytest.raises(RuntimeError):
+        local_realignment(read, [Variant(0, 6, 10, 1, b"G", b"GG")])
