@@ -212,7 +212,7 @@ void hp_ctx_destroy(hp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->meta, &ctx->rmeta, &ctx->planes, &ctx->act_off, &ctx->act_cur, &ctx->act_idx, &ctx->col, &ctx->order,
-                      &ctx->heur, &ctx->ticket, &ctx->dbg, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out})
+                      &ctx->heur, &ctx->ticket, &ctx->dbg, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out, &ctx->wfa_graph})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -223,6 +223,8 @@ uint64_t hp_launch_count(const hp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // Not part of the public header: per-block phase cycles of the last counting run (profiling aid for bench/profiles).
 int hp_debug_set_team(hp_ctx* ctx, int team) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->force_team = team; return HP_OK; }
+// bit 0: build the WFA graphs on the host (A/B aid); bit 1: no workspace hint (exercises the regrow path)
+int hp_debug_wfa_build_mode(hp_ctx* ctx, int mode) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->wfa_host_build = (mode & 1) != 0; ctx->wfa_no_hint = (mode & 2) != 0; return HP_OK; }
 int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
 int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
     if (!ctx || !out || n_blocks > ctx->dbg_blocks || !ctx->dbg.ptr) return HP_ERR_INVALID_INPUT;

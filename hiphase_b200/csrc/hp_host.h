@@ -49,7 +49,9 @@ struct hp_ctx {
     hp::DevBuf dbg;
     hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, slabs, stage_in, stage_out;
     // WFA workspaces
-    hp::DevBuf wfa_ws, wfa_in, wfa_out;
+    hp::DevBuf wfa_ws, wfa_in, wfa_out, wfa_graph;
+    bool wfa_no_hint = false;               // test aid: start with an unsized graph workspace (exercises the regrow path)
+    bool wfa_host_build = false;            // debug / A-B aid: build the graphs on the host instead of on the device
     uint32_t wfa_table_cap = 1u << 15;      // (node, diagonal) hash slots per warp; grown 8x on overflow
     std::vector<int32_t> wfa_h_status;
     std::vector<uint32_t> wfa_h_score, wfa_h_nodes;

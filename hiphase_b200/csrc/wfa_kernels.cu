@@ -454,6 +454,157 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// graph construction on the device: from_reference_variants_with_hom (wfa_graph.rs:119-284),
+// one thread per job, two passes -- count (nodes / edges / allele tags per job), then fill into exactly sized slices.
+// Node order, edges and the allele map are those of the host builder below (and of the reference): variants by
+// position (hets before homs on ties), ALT node(s) before the reference node of a locus, allele0 shares the next
+// backbone node unless it is itself an ALT (index_allele0 != 0), ALT nodes rejoin the backbone at pos + ref_len.
+// ---------------------------------------------------------------------------------------------------------------
+struct BuildArgs {
+    uint32_t n_sel;                // jobs of this run
+    const uint32_t* ids;           // their indices in the caller's batch
+    // variant table
+    const int64_t* position;
+    const uint32_t* ref_len;
+    const uint64_t* a0_off;
+    const uint32_t* a0_len;
+    const uint64_t* a1_off;
+    const uint32_t* a1_len;
+    const uint8_t* index_allele0;
+    const uint8_t* ignored;
+    // job windows
+    const uint64_t* ref_start;
+    const uint64_t* ref_end;
+    const uint32_t* het_lo;
+    const uint32_t* het_hi;
+    const uint32_t* hom_lo;
+    const uint32_t* hom_hi;
+    uint64_t n_reference;
+    // pass 1 output: per selected job {n_nodes, n_edges, n_amap, status}
+    uint32_t* counts;
+    // pass 2: exactly sized slices
+    const WfaJob* jobs;            // node_base set by the host from the counts
+    const uint64_t* edge_base;     // [n_sel]
+    const uint64_t* amap_base;     // [n_sel]
+    WfaNode* nodes;
+    uint32_t* child_off;
+    uint32_t* child_idx;
+    uint32_t* amap_off;
+    uint32_t* amap;
+    uint32_t* e_parent;            // scratch: edges in creation order (child ascending)
+    uint32_t* e_child;
+};
+
+constexpr int kBuildCap = 64;      // open ALT branches / parents of one node / pending allele-0 tags
+constexpr uint32_t kBuildOk = 0, kBuildInvalid = 1, kBuildOverflow = 2;
+
+template <bool kFill>
+__global__ void __launch_bounds__(128) wfa_graph_build_kernel(BuildArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_sel) return;
+    const uint32_t j = a.ids[slot];
+    const uint32_t het_lo = a.het_lo[j];
+    uint32_t hi = het_lo, he = a.het_hi[j], mi = a.hom_lo[j], me = a.hom_hi[j];
+    const uint64_t w0 = a.ref_start[j], w1 = a.ref_end[j];
+    uint32_t n_nodes = 0, n_edges = 0, n_amap = 0, status = kBuildOk;
+    uint64_t node_base = 0, ebase = 0, mbase = 0, row = 0;
+    if (kFill) {
+        if (a.counts[4 * slot + 3] != kBuildOk || (he == het_lo)) return;
+        node_base = a.jobs[slot].node_base; ebase = a.edge_base[slot]; mbase = a.amap_base[slot];
+        row = node_base + slot;                               // CSR rows: n_nodes + 1 entries per job
+    }
+    if (he == het_lo) {                                        // skipped job (read_parsing.rs:703-712): no graph
+        if (!kFill) { a.counts[4 * slot] = 0; a.counts[4 * slot + 1] = 0; a.counts[4 * slot + 2] = 0; a.counts[4 * slot + 3] = kBuildOk; }
+        return;
+    }
+    uint64_t cursor = w0;
+    uint32_t attach[kBuildCap]; int n_attach = 0;              // parents of the next backbone node
+    uint32_t pend[kBuildCap]; int n_pend = 0;                  // allele-0 tags waiting for the next backbone node
+    uint64_t rpos[kBuildCap]; uint32_t rnode[kBuildCap]; int n_rej = 0;   // open ALT branches: (rejoin position, node)
+    if (w1 > a.n_reference || w0 > w1) status = kBuildInvalid;
+
+    auto add = [&](uint32_t src, uint64_t off, uint32_t len) -> uint32_t {      // parents = attach[]
+        const uint32_t id = n_nodes++;
+        if (kFill) {
+            WfaNode nd; nd.seq_off = off; nd.len = len; nd.src = src;
+            a.nodes[node_base + id] = nd;
+            a.amap_off[row + id] = (uint32_t)(mbase + n_amap);
+            for (int q = 0; q < n_attach; q++) { a.e_parent[ebase + n_edges + q] = attach[q]; a.e_child[ebase + n_edges + q] = id; }
+        }
+        n_edges += (uint32_t)n_attach;
+        return id;
+    };
+    auto tag = [&](uint32_t t) { if (kFill) a.amap[mbase + n_amap] = t; n_amap++; };
+    auto backbone_to = [&](uint64_t upto) -> uint32_t {                           // emits reference[cursor, upto)
+        const uint32_t id = add(0u, cursor, (uint32_t)(upto - cursor));
+        for (int q = 0; q < n_pend; q++) tag(pend[q]);
+        n_pend = 0;
+        cursor = upto;
+        return id;
+    };
+    auto drain = [&](uint64_t limit) {                                            // ALT nodes rejoining at positions <= limit
+        while (status == kBuildOk && n_rej > 0) {
+            uint64_t at = rpos[0];
+            for (int q = 1; q < n_rej; q++) at = rpos[q] < at ? rpos[q] : at;
+            if (at > limit) break;
+            if (!(at > cursor)) { status = kBuildInvalid; break; }
+            const uint32_t bb = backbone_to(at);
+            attach[0] = bb; n_attach = 1;
+            for (int q = 0; q < n_rej;) {
+                if (rpos[q] == at) {
+                    if (n_attach >= kBuildCap) { status = kBuildOverflow; break; }
+                    attach[n_attach++] = rnode[q];
+                    rpos[q] = rpos[n_rej - 1]; rnode[q] = rnode[n_rej - 1]; n_rej--;
+                } else q++;
+            }
+        }
+    };
+    while (status == kBuildOk && (hi < he || mi < me)) {
+        uint32_t k; int het;
+        if (hi < he && (mi >= me || a.position[hi] <= a.position[mi])) { k = hi; het = (int)(hi - het_lo); hi++; }
+        else { k = mi; het = -1; mi++; }
+        if (a.ignored[k] || a.position[k] < 0) continue;
+        const uint64_t pos = (uint64_t)a.position[k], rl = a.ref_len[k];
+        if (pos < w0 || pos + rl > w1) continue;
+        drain(pos);
+        if (status != kBuildOk) break;
+        if (cursor < pos || n_nodes == 0) {
+            const uint32_t bb = backbone_to(pos);
+            attach[0] = bb; n_attach = 1;
+        } else if (cursor != pos) { status = kBuildInvalid; break; }
+        if (n_rej + 2 > kBuildCap || n_pend + 1 > kBuildCap) { status = kBuildOverflow; break; }
+        if (a.index_allele0[k] != 0) {                          // allele0 is an ALT of a multi-allelic site
+            const uint32_t alt = add(1u, a.a0_off[k], a.a0_len[k]);
+            if (het >= 0) tag(((uint32_t)het << 1) | 0u);
+            rpos[n_rej] = pos + rl; rnode[n_rej] = alt; n_rej++;
+        } else if (het >= 0) pend[n_pend++] = ((uint32_t)het << 1) | 0u;
+        const uint32_t alt = add(1u, a.a1_off[k], a.a1_len[k]);
+        if (het >= 0) tag(((uint32_t)het << 1) | 1u);
+        rpos[n_rej] = pos + rl; rnode[n_rej] = alt; n_rej++;
+    }
+    if (status == kBuildOk) drain(UINT64_MAX);
+    if (status == kBuildOk && cursor > w1) status = kBuildInvalid;
+    if (status == kBuildOk) {
+        backbone_to(w1);
+        if (n_pend != 0) status = kBuildInvalid;                // cannot happen: backbone_to consumes the pending tags
+    }
+    if (!kFill) {
+        a.counts[4 * slot] = n_nodes; a.counts[4 * slot + 1] = n_edges; a.counts[4 * slot + 2] = n_amap; a.counts[4 * slot + 3] = status;
+        return;
+    }
+    // children CSR: counting sort of the edges by parent (children stay in ascending order)
+    a.amap_off[row + n_nodes] = (uint32_t)(mbase + n_amap);
+    uint32_t* coff = a.child_off + row;
+    for (uint32_t i = 0; i <= n_nodes; i++) coff[i] = 0;
+    for (uint32_t e = 0; e < n_edges; e++) coff[a.e_parent[ebase + e] + 1]++;
+    for (uint32_t i = 1; i <= n_nodes; i++) coff[i] += coff[i - 1];
+    for (uint32_t i = 0; i <= n_nodes; i++) coff[i] += (uint32_t)ebase;
+    for (uint32_t e = 0; e < n_edges; e++) a.child_idx[coff[a.e_parent[ebase + e]]++] = a.e_child[ebase + e];
+    for (uint32_t i = n_nodes; i >= 1; i--) coff[i] = coff[i - 1];      // undo the fill cursors
+    coff[0] = (uint32_t)ebase;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side: graph flattening (from_reference_variants_with_hom) and the API
 // ---------------------------------------------------------------------------------------------------------------
 struct FlatGraphs {
@@ -557,6 +708,14 @@ static int wfa_fail(hp_ctx* ctx, int code, const std::string& msg) { if (ctx) ct
         if (e_ != cudaSuccess) { cudaGetLastError(); return wfa_fail(ctx, HP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
     } while (0)
 
+// Graphs (and byte pools) already resident on the device (built by wfa_graph_build_kernel).
+struct DevBuilt {
+    const WfaJob* jobs = nullptr;
+    const WfaNode* nodes = nullptr;
+    const uint32_t *child_off = nullptr, *child_idx = nullptr, *amap_off = nullptr, *amap = nullptr;
+    const uint8_t *reference = nullptr, *allele_bytes = nullptr, *read_bytes = nullptr, *vtype = nullptr;
+};
+
 struct WfaHostInputs {
     const uint8_t* reference; uint64_t n_reference;
     const uint8_t* allele_bytes; uint64_t n_allele_bytes;
@@ -568,7 +727,7 @@ struct WfaHostInputs {
 // Uploads the flattened graphs + byte pools, runs the kernel, downloads the outputs.  `sel` (optional) restricts the
 // run to a subset of jobs (retry path); outputs are written at the original job indices.
 static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, uint64_t prune, uint32_t max_ed,
-                   uint64_t n_rows, hp_wfa_out* out, uint32_t table_cap, int max_ctas) {
+                   uint64_t n_rows, hp_wfa_out* out, uint32_t table_cap, int max_ctas, const DevBuilt* dev = nullptr) {
     const uint32_t nj = (uint32_t)fg.jobs.size();
     if (nj == 0) return HP_OK;
     cudaStream_t st = ctx->stream;
@@ -577,7 +736,8 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     const uint32_t sw_max = (max_nodes + 63) / 64;
 
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t in_bytes = al(sizeof(WfaJob) * nj) + al(4ull * nj) + al(sizeof(WfaNode) * fg.nodes.size()) + al(4 * fg.child_off.size()) +
+    const size_t in_bytes = dev ? al(4ull * nj) + 4096
+                          : al(sizeof(WfaJob) * nj) + al(4ull * nj) + al(sizeof(WfaNode) * fg.nodes.size()) + al(4 * fg.child_off.size()) +
                             al(4 * fg.child_idx.size()) + al(4 * fg.amap_off.size()) + al(4 * fg.amap.size()) + al(in.n_reference) +
                             al(in.n_allele_bytes) + al(in.n_seq_pool) + al(in.n_read_bytes) + al(in.n_vtype) + 4096;
     if (!ctx->wfa_in.reserve(in_bytes)) return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA input staging allocation failed");
@@ -589,21 +749,28 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     };
     WfaArgs a;
     a.n_jobs = nj;
-    a.jobs = (const WfaJob*)up(fg.jobs.data(), sizeof(WfaJob) * nj);
     std::vector<uint32_t> order(nj);
     for (uint32_t i = 0; i < nj; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return fg.jobs[x].read_len > fg.jobs[y].read_len; });
-    a.order = (const uint32_t*)up(order.data(), 4ull * nj);
-    a.nodes = (const WfaNode*)up(fg.nodes.data(), sizeof(WfaNode) * fg.nodes.size());
-    a.child_off = (const uint32_t*)up(fg.child_off.data(), 4 * fg.child_off.size());
-    a.child_idx = (const uint32_t*)up(fg.child_idx.data(), 4 * fg.child_idx.size());
-    a.amap_off = (const uint32_t*)up(fg.amap_off.data(), 4 * fg.amap_off.size());
-    a.amap = (const uint32_t*)up(fg.amap.data(), 4 * fg.amap.size());
-    a.reference = up(in.reference, in.n_reference);
-    a.allele_bytes = up(in.allele_bytes, in.n_allele_bytes);
-    a.seq_pool = up(in.seq_pool, in.n_seq_pool);
-    a.read_bytes = up(in.read_bytes, in.n_read_bytes);
-    a.vtype = up(in.vtype, in.n_vtype);
+    if (dev) {
+        a.jobs = dev->jobs; a.nodes = dev->nodes; a.child_off = dev->child_off; a.child_idx = dev->child_idx;
+        a.amap_off = dev->amap_off; a.amap = dev->amap;
+        a.reference = dev->reference; a.allele_bytes = dev->allele_bytes; a.seq_pool = nullptr; a.read_bytes = dev->read_bytes; a.vtype = dev->vtype;
+        a.order = (const uint32_t*)up(order.data(), 4ull * nj);
+    } else {
+        a.jobs = (const WfaJob*)up(fg.jobs.data(), sizeof(WfaJob) * nj);
+        a.order = (const uint32_t*)up(order.data(), 4ull * nj);
+        a.nodes = (const WfaNode*)up(fg.nodes.data(), sizeof(WfaNode) * fg.nodes.size());
+        a.child_off = (const uint32_t*)up(fg.child_off.data(), 4 * fg.child_off.size());
+        a.child_idx = (const uint32_t*)up(fg.child_idx.data(), 4 * fg.child_idx.size());
+        a.amap_off = (const uint32_t*)up(fg.amap_off.data(), 4 * fg.amap_off.size());
+        a.amap = (const uint32_t*)up(fg.amap.data(), 4 * fg.amap.size());
+        a.reference = up(in.reference, in.n_reference);
+        a.allele_bytes = up(in.allele_bytes, in.n_allele_bytes);
+        a.seq_pool = up(in.seq_pool, in.n_seq_pool);
+        a.read_bytes = up(in.read_bytes, in.n_read_bytes);
+        a.vtype = up(in.vtype, in.n_vtype);
+    }
     a.prune_distance = prune; a.max_edit_distance = max_ed;
 
     int n_ctas = std::min<int>((nj + kWfaWarps - 1) / kWfaWarps, ctx->sm_count * 2);
@@ -650,6 +817,132 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     return HP_OK;
 }
 
+// Builds the graphs of jobs `ids` on the device (two passes: count, then fill exactly sized slices).  On return
+// fg.jobs holds the host copy of the job table (node counts, row layout) and `dev` the device pointers.
+// The batch-constant inputs (variant table, windows, byte pools) are uploaded once per hp_wfa_align_batch call.
+struct DevInputs {
+    bool ready = false;
+    BuildArgs b{};
+    DevBuilt pools;
+    size_t used = 0;               // bytes of ctx->wfa_graph taken by the batch-constant inputs
+};
+
+static int wfa_upload_batch(hp_ctx* ctx, const hp_wfa_batch* b, DevInputs& di, size_t graph_bytes_hint) {
+    const hp_variant_table& vt = b->variants;
+    const uint32_t nj = b->n_jobs, nv = vt.n_variants;
+    const uint64_t n_read = b->read_off[nj];
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t bytes = al(8ull * nv) * 3 + al(4ull * nv) * 3 + al(nv) * 3 + al(vt.n_allele_bytes) + al(b->n_reference) + al(n_read) +
+                         al(8ull * nj) * 2 + al(4ull * nj) * 4 + 4096;
+    if (!ctx->wfa_graph.reserve(bytes + graph_bytes_hint)) return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA graph workspace allocation failed");
+    cudaStream_t st = ctx->stream;
+    uint8_t* p = (uint8_t*)ctx->wfa_graph.ptr;
+    bool ok = true;
+    auto up = [&](const void* src, size_t n) -> uint8_t* { uint8_t* d = p; p += al(n); if (n) ok &= cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, st) == cudaSuccess; return d; };
+    BuildArgs& a = di.b;
+    a.position = (const int64_t*)up(vt.position, 8ull * nv); a.ref_len = (const uint32_t*)up(vt.ref_len, 4ull * nv);
+    a.a0_off = (const uint64_t*)up(vt.allele0_off, 8ull * nv); a.a0_len = (const uint32_t*)up(vt.allele0_len, 4ull * nv);
+    a.a1_off = (const uint64_t*)up(vt.allele1_off, 8ull * nv); a.a1_len = (const uint32_t*)up(vt.allele1_len, 4ull * nv);
+    a.index_allele0 = up(vt.index_allele0, nv); a.ignored = up(vt.ignored, nv);
+    di.pools.vtype = up(vt.vtype, nv);
+    di.pools.allele_bytes = up(vt.allele_bytes, vt.n_allele_bytes);
+    di.pools.reference = up(b->reference, b->n_reference);
+    di.pools.read_bytes = up(b->read_bytes, n_read);
+    a.ref_start = (const uint64_t*)up(b->ref_start, 8ull * nj); a.ref_end = (const uint64_t*)up(b->ref_end, 8ull * nj);
+    a.het_lo = (const uint32_t*)up(b->het_lo, 4ull * nj); a.het_hi = (const uint32_t*)up(b->het_hi, 4ull * nj);
+    a.hom_lo = (const uint32_t*)up(b->hom_lo, 4ull * nj); a.hom_hi = (const uint32_t*)up(b->hom_hi, 4ull * nj);
+    a.n_reference = b->n_reference;
+    if (!ok) { cudaGetLastError(); return wfa_fail(ctx, HP_ERR_CUDA, "WFA batch upload failed"); }
+    di.used = (size_t)(p - (uint8_t*)ctx->wfa_graph.ptr);
+    di.ready = true;
+    return HP_OK;
+}
+
+static int wfa_build_on_device(hp_ctx* ctx, const hp_wfa_batch* b, const std::vector<uint32_t>& ids, DevInputs& di,
+                               FlatGraphs& fg, DevBuilt& dev, uint64_t& rows) {
+    const uint32_t ns = (uint32_t)ids.size();
+    cudaStream_t st = ctx->stream;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    // pass 1 needs ids + counts: carve them behind the batch-constant inputs
+    size_t need = di.used + al(4ull * ns) + al(16ull * ns) + 4096;
+    if (ctx->wfa_graph.cap < need) return wfa_fail(ctx, HP_ERR_INTERNAL, "WFA graph workspace too small for the count pass");
+    uint8_t* base = (uint8_t*)ctx->wfa_graph.ptr + di.used;
+    uint32_t* d_ids = (uint32_t*)base;
+    uint32_t* d_counts = (uint32_t*)(base + al(4ull * ns));
+    BuildArgs a = di.b;
+    a.n_sel = ns; a.ids = d_ids; a.counts = d_counts;
+    WFA_CUDA(ctx, cudaMemcpyAsync(d_ids, ids.data(), 4ull * ns, cudaMemcpyHostToDevice, st));
+    const int grid = (int)((ns + 127) / 128);
+    wfa_graph_build_kernel<false><<<grid, 128, 0, st>>>(a);
+    WFA_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    std::vector<uint32_t> counts(4ull * ns);
+    WFA_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_counts, 16ull * ns, cudaMemcpyDeviceToHost, st));
+    WFA_CUDA(ctx, cudaStreamSynchronize(st));
+    // job table + slice bases
+    fg = FlatGraphs();
+    fg.jobs.resize(ns);
+    std::vector<uint64_t> edge_base(ns), amap_base(ns);
+    uint64_t tn = 0, te = 0, ta = 0;
+    rows = 0;
+    for (uint32_t k = 0; k < ns; k++) {
+        const uint32_t j = ids[k];
+        WfaJob& job = fg.jobs[k];
+        job = WfaJob{};
+        job.read_off = b->read_off[j]; job.read_len = (uint32_t)(b->read_off[j + 1] - b->read_off[j]);
+        job.row_len = b->het_hi[j] - b->het_lo[j]; job.het_lo = b->het_lo[j];
+        job.row_off = rows; rows += job.row_len;
+        job.node_base = tn; job.n_nodes = counts[4ull * k];
+        job.status = HP_WFA_OK;
+        if (job.row_len == 0) job.status = HP_WFA_SKIPPED;                               // read_parsing.rs:703-712
+        else if (counts[4ull * k + 3] == kBuildInvalid)
+            return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "graph construction failed for job " + std::to_string(j) + " (the reference unwrap()s this, read_parsing.rs:777)");
+        else if (counts[4ull * k + 3] == kBuildOverflow) { job.status = HP_WFA_WORKSPACE_OVERFLOW; job.n_nodes = 0; }
+        edge_base[k] = te; amap_base[k] = ta;
+        if (job.status == HP_WFA_OK) { tn += job.n_nodes; te += counts[4ull * k + 1]; ta += counts[4ull * k + 2]; }
+    }
+    if (te + ns >= 0xffffffffull || ta + ns >= 0xffffffffull || tn + ns >= 0xffffffffull) return wfa_fail(ctx, HP_ERR_UNSUPPORTED, "WFA batch too large (32-bit CSR offsets)");
+    // pass 2 slices
+    const size_t fill_bytes = al(sizeof(WfaJob) * ns) + al(8ull * ns) * 2 + al(sizeof(WfaNode) * (tn + 1)) + al(4ull * (tn + ns + 1)) * 2 +
+                              al(4ull * (te + 1)) * 3 + al(4ull * (ta + 1));
+    need += fill_bytes;
+    if (ctx->wfa_graph.cap < need) {
+        // grow: the batch-constant inputs have to be uploaded again into the new allocation
+        di.ready = false;
+        int rc = wfa_upload_batch(ctx, b, di, al(4ull * ns) + al(16ull * ns) + fill_bytes + 8192);
+        if (rc != HP_OK) return rc;
+        base = (uint8_t*)ctx->wfa_graph.ptr + di.used;
+        d_ids = (uint32_t*)base; d_counts = (uint32_t*)(base + al(4ull * ns));
+        a = di.b; a.n_sel = ns; a.ids = d_ids; a.counts = d_counts;
+        WFA_CUDA(ctx, cudaMemcpyAsync(d_ids, ids.data(), 4ull * ns, cudaMemcpyHostToDevice, st));
+        WFA_CUDA(ctx, cudaMemcpyAsync(d_counts, counts.data(), 16ull * ns, cudaMemcpyHostToDevice, st));
+    }
+    uint8_t* q = base + al(4ull * ns) + al(16ull * ns);
+    auto carve = [&](size_t n) { uint8_t* r = q; q += al(n); return r; };
+    WfaJob* d_jobs = (WfaJob*)carve(sizeof(WfaJob) * ns);
+    uint64_t* d_eb = (uint64_t*)carve(8ull * ns);
+    uint64_t* d_ab = (uint64_t*)carve(8ull * ns);
+    a.nodes = (WfaNode*)carve(sizeof(WfaNode) * (tn + 1));
+    a.child_off = (uint32_t*)carve(4ull * (tn + ns + 1));
+    a.amap_off = (uint32_t*)carve(4ull * (tn + ns + 1));
+    a.child_idx = (uint32_t*)carve(4ull * (te + 1));
+    a.e_parent = (uint32_t*)carve(4ull * (te + 1));
+    a.e_child = (uint32_t*)carve(4ull * (te + 1));
+    a.amap = (uint32_t*)carve(4ull * (ta + 1));
+    a.jobs = d_jobs; a.edge_base = d_eb; a.amap_base = d_ab;
+    WFA_CUDA(ctx, cudaMemcpyAsync(d_jobs, fg.jobs.data(), sizeof(WfaJob) * ns, cudaMemcpyHostToDevice, st));
+    WFA_CUDA(ctx, cudaMemcpyAsync(d_eb, edge_base.data(), 8ull * ns, cudaMemcpyHostToDevice, st));
+    WFA_CUDA(ctx, cudaMemcpyAsync(d_ab, amap_base.data(), 8ull * ns, cudaMemcpyHostToDevice, st));
+    wfa_graph_build_kernel<true><<<grid, 128, 0, st>>>(a);
+    WFA_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    // edge_base / amap_base / e_* go out of scope with this function: the fill kernel must have read them
+    WFA_CUDA(ctx, cudaStreamSynchronize(st));
+    dev = di.pools;
+    dev.jobs = d_jobs; dev.nodes = a.nodes; dev.child_off = a.child_off; dev.child_idx = a.child_idx; dev.amap_off = a.amap_off; dev.amap = a.amap;
+    return HP_OK;
+}
+
 // scatter results of a run over jobs `ids` (original job indices; rows at the original row offsets)
 static void wfa_scatter(hp_ctx* ctx, const FlatGraphs& fg, const std::vector<uint32_t>& ids, const uint64_t* orig_row_off,
                         hp_wfa_out* out) {
@@ -692,7 +985,30 @@ int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
     std::vector<uint32_t> ids(b->n_jobs);
     for (uint32_t j = 0; j < b->n_jobs; j++) ids[j] = j;
     uint32_t cap = ctx->wfa_table_cap;
+    // position-sorted het / hom runs are part of the contract (the device builder merges them); the host builder sorts
+    for (uint32_t j = 0; j < b->n_jobs && !ctx->wfa_host_build; j++) {
+        for (uint32_t k = b->het_lo[j]; k + 1 < b->het_hi[j]; k++) if (vt.position[k] > vt.position[k + 1]) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "het variants of job " + std::to_string(j) + " are not sorted by position");
+        for (uint32_t k = b->hom_lo[j]; k + 1 < b->hom_hi[j]; k++) if (vt.position[k] > vt.position[k + 1]) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "hom variants of job " + std::to_string(j) + " are not sorted by position");
+        if (b->ref_end[j] > b->n_reference || b->ref_start[j] > b->ref_end[j]) return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "reference window of job " + std::to_string(j));
+    }
+    DevInputs di;
     for (int attempt = 0; attempt < 4 && !ids.empty(); attempt++) {
+      FlatGraphs fg;
+      uint64_t rows = 0;
+      DevBuilt dev;
+      const bool on_device = !ctx->wfa_host_build;
+      if (on_device) {
+        if (!di.ready) {
+            // workspace hint: ~3 nodes per variant in a window (exact sizes come from the count pass)
+            uint64_t sv = 0;
+            for (uint32_t j : ids) sv += (uint64_t)(b->het_hi[j] - b->het_lo[j]) + (b->hom_hi[j] - b->hom_lo[j]);
+            const size_t hint = ctx->wfa_no_hint ? 0 : (size_t)((3 * sv + 2 * ids.size()) * (16 + 8 + 18 + 8) + 64 * ids.size() + (1u << 20));
+            int rc0 = wfa_upload_batch(ctx, b, di, hint);
+            if (rc0 != HP_OK) return rc0;
+        }
+        int rc0 = wfa_build_on_device(ctx, b, ids, di, fg, dev, rows);
+        if (rc0 != HP_OK) return rc0;
+      } else {
         // graph construction is per job and independent: build chunks on host threads, then concatenate
         const size_t n_ids = ids.size();
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -727,8 +1043,6 @@ int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
         for (size_t c = 0; c < n_chunks; c++)
             if (part_fail[c] >= 0)
                 return wfa_fail(ctx, HP_ERR_INVALID_INPUT, "graph construction failed for job " + std::to_string(part_fail[c]) + " (the reference unwrap()s this, read_parsing.rs:777)");
-        FlatGraphs fg;
-        uint64_t rows = 0;
         {
             size_t tn = 0, tc = 0, ta = 0, tj = 0, to = 0;
             for (const FlatGraphs& pg : parts) { tn += pg.nodes.size(); tc += pg.child_idx.size(); ta += pg.amap.size(); tj += pg.jobs.size(); to += pg.child_off.size(); }
@@ -745,10 +1059,11 @@ int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
                 pg = FlatGraphs();
             }
         }
+      }
         // slabs: full occupancy on the first attempt, fewer and larger afterwards
         int max_ctas = 0;
         if (attempt > 0) max_ctas = std::max(1, (int)((8ull << 30) / (wfa_slab_bytes(cap, 16) * kWfaWarps)));
-        int rc = wfa_run(ctx, fg, in, prune, ctx->params.wfa_max_edit_distance, rows, out, cap, max_ctas);
+        int rc = wfa_run(ctx, fg, in, prune, ctx->params.wfa_max_edit_distance, rows, out, cap, max_ctas, on_device ? &dev : nullptr);
         if (rc != HP_OK) return rc;
         wfa_scatter(ctx, fg, ids, b->row_off, out);
         std::vector<uint32_t> redo;

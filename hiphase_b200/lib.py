@@ -98,6 +98,10 @@ class Context:
         """Profiling / test aid: force the speculative team size of the A* kernel (0 = automatic, 1, 2 or 4)."""
         self.check(lib().hp_debug_set_team(self._h, int(team)))
 
+    def set_wfa_build_mode(self, mode):
+        """Test / A-B aid: bit 0 = build the WFA graphs on the host, bit 1 = start without a workspace hint."""
+        self.check(lib().hp_debug_wfa_build_mode(self._h, int(mode)))
+
     def launch_count(self):
         return int(lib().hp_launch_count(self._h))
 

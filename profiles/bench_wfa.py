@@ -13,6 +13,7 @@ t0 = time.time()
 batch, jb, meta = synth.config_c4(nb)
 print("generated %d jobs in %.1fs (%.1f MB reads)" % (batch.n_jobs, time.time() - t0, len(batch.read_bytes) / 1e6), flush=True)
 ctx = lib.Context(device=0)
+ctx.set_wfa_build_mode(int(os.environ.get("HP_WFA_BUILD_MODE", "0")))   # 0 = graphs built on the device, 1 = on the host
 out = ctx.wfa_align_batch(batch, want_counters=True)
 times = []
 for _ in range(3):

@@ -116,3 +116,19 @@ def test_c4_rows_feed_astar(ctx):
     ref_blocks = synth.blocks_from_wfa_rows(batch, ref_rows, jb, meta)
     want = O.astar_solve(ref_blocks, threads=4)
     assert np.array_equal(got.h1, want.h1) and np.array_equal(got.h2, want.h2) and np.array_equal(got.stats, want.stats)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["device-build", "host-build", "device-build-regrow"])
+def test_graph_build_modes_agree(mode):
+    """Row f3: from_reference_variants_with_hom on the device (default) vs the host builder vs the oracle: same node
+    counts, traversed sets, scores and rows."""
+    from hiphase_b200 import lib
+    c = lib.Context(device=0)
+    c.set_wfa_build_mode(mode)
+    batch, jb, meta = synth.config_c4(2, window=30000, n_het=30, n_hom=40, n_reads=24, read_lo=4000, read_hi=9000, sv_max=600)
+    ref = O.wfa_align(batch, threads=4, trav_words=8)
+    out = c.wfa_align_batch(batch, trav_words=8)
+    _assert_wfa_parity(out, ref)
+    assert np.array_equal(out.n_nodes, ref.n_nodes) and np.array_equal(out.traversed, ref.traversed)
+    c.close()
