@@ -1298,7 +1298,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         coln[k] = (1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
 
-    long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0;   // counting variant only
+    long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0, tm_vec = 0, tm_rec = 0, tm_push = 0;   // counting variant only
     for (;;) {
         if (kCount) tq0 = clock64();
         if (!have_cur || key_less(qmin.hi, qmin.idx, ((uint64_t)cur_total << 32) | cur_nh, cur_idx)) {
@@ -1530,6 +1530,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         }
         cache_first = next_idx; cache_present = present;
 
+        if (kCount) { const long long t1 = clock64(); tm_vec += t1 - tq0; tq0 = t1; }
         // ---- records: siblings get copies of the parent's words + their allele bit; the best child takes the parent's
         //      record in place ----
         const uint32_t c_mine = (lane - rr) & 31u;                         // this lane's candidate (pushes), if < 4
@@ -1583,6 +1584,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 }
             }
         }
+        if (kCount) { const long long t1 = clock64(); tm_rec += t1 - tq0; tq0 = t1; }
         // ---- push the siblings (one lane each) ----
         {
             const uint32_t mt = (c_mine == 0u) ? t0 : (c_mine == 1u) ? t1 : (c_mine == 2u) ? t2 : t3;
@@ -1650,6 +1652,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         }
         __syncwarp();
 
+        if (kCount) { const long long t1 = clock64(); tm_push += t1 - tq0; tq0 = t1; }
         // ---- pruning bookkeeping (:564-585) ----
         while (trk_total > curr_thresh && min_progress < next_expected) {
             min_progress++;
@@ -1734,6 +1737,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         uint64_t* d = a.dbg_cycles + 16ull * blk;
         d[8] = tm_pop; d[9] = tm_exp; d[10] = tm_rest; d[11] = n_planes; d[12] = tm_planes;
         d[13] = n_real; d[14] = num_pruned; d[15] = qsize; d[7] = n_swept;
+        d[5] = tm_vec; d[6] = tm_rec; d[4] = tm_push;   // (overwritten below by the team's round statistics unless HP_DBG_MAIN_SPLIT)
     }
     if (w.status != HP_BLOCK_OK) return;
 
@@ -1885,7 +1889,9 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
                 if (a.dbg_cycles) {
                     uint64_t* d = a.dbg_cycles + 16ull * blk;
                     d[0] = (uint64_t)(t_mid - t_start); d[1] = (uint64_t)(clock64() - t_mid); d[2] = ts.ctr[3]; d[3] = w.pops;
+#ifndef HP_DBG_MAIN_SPLIT
                     d[4] = n_rounds; d[5] = team; d[6] = (uint64_t)t_wait;
+#endif
                 }
                 ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;
             }

@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("HP_B200_LIB") or os.path.join(CSRC, "libhiphase_b200.
 EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
            "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch",
-           "hp_local_realign_batch", "hp_edit_distance_batch")
+           "hp_local_realign_batch", "hp_edit_distance_batch", "hp_pack_write_blocks", "hp_pack_open",
+           "hp_pack_get_blocks", "hp_pack_close", "hp_pack_last_error", "hp_write_phase_stats")
 
 _LIB = None
 
@@ -30,7 +31,7 @@ def build(force=False):
     """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     if force and os.path.exists(LIB_PATH):
         os.remove(LIB_PATH)
-    subprocess.run(["make", "-s", "-C", CSRC], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    subprocess.run(["make", "-s", "-C", CSRC, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     return LIB_PATH
 
 
@@ -61,6 +62,12 @@ def lib():
                                          C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), A.u64p]
         L.hp_local_realign_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_local_batch), C.POINTER(A.hp_local_out)]
         L.hp_edit_distance_batch.argtypes = [C.c_void_p, C.c_uint32, A.u8p, C.c_uint64, A.u64p, A.u32p, A.u64p, A.u32p, A.u32p]
+        L.hp_pack_write_blocks.argtypes = [C.c_char_p, C.POINTER(A.hp_block_batch), A.i64p]
+        L.hp_pack_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.hp_pack_get_blocks.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.POINTER(A.i64p)]
+        L.hp_pack_close.argtypes = [C.c_void_p]
+        L.hp_pack_last_error.restype = C.c_char_p
+        L.hp_write_phase_stats.argtypes = [C.c_char_p, C.POINTER(A.hp_block_batch), A.i64p, C.POINTER(A.hp_astar_out), C.c_uint64]
         _LIB = L
     return _LIB
 
@@ -177,3 +184,53 @@ class Context:
     def astar_solve_device(self, dev_batch_struct, n_vars, n_reads, n_cells, max_block_vars, dev_out_struct, stream):
         self.check(lib().hp_astar_solve_device(self._h, C.byref(dev_batch_struct), n_vars, n_reads, n_cells,
                                                max_block_vars, C.byref(dev_out_struct), C.c_void_p(stream)))
+
+
+# ---- packed phase-block container (host only) -------------------------------------------------
+RUNNER_PATH = os.path.join(CSRC, "hp_phase_blocks")
+
+
+def pack_write_blocks(path, batch, var_pos=None):
+    """hp_pack_write_blocks: a BlockBatch (+ optional variant positions) -> HPB200 file."""
+    import numpy as np
+    bs = batch.as_struct()
+    vp = None if var_pos is None else np.ascontiguousarray(var_pos, np.int64)
+    rc = lib().hp_pack_write_blocks(os.fsencode(path), C.byref(bs), A.ptr(vp, A.i64p))
+    if rc != A.HP_OK:
+        raise HiPhaseB200Error(rc, (lib().hp_pack_last_error() or b"").decode())
+
+
+def pack_read_blocks(path):
+    """hp_pack_open + hp_pack_get_blocks -> (BlockBatch, var_pos or None); the arrays are copied out of the container."""
+    import numpy as np
+    h = C.c_void_p()
+    rc = lib().hp_pack_open(os.fsencode(path), C.byref(h))
+    if rc != A.HP_OK:
+        raise HiPhaseB200Error(rc, (lib().hp_pack_last_error() or b"").decode())
+    try:
+        bs, vp = A.hp_block_batch(), A.i64p()
+        lib().hp_pack_get_blocks(h, C.byref(bs), C.byref(vp))
+        nb = bs.n_blocks
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        var_off = arr(bs.var_off, nb + 1, np.uint64); read_off = arr(bs.read_off, nb + 1, np.uint64)
+        nv, nr = int(var_off[-1]), int(read_off[-1])
+        cell_off = arr(bs.cell_off, nr + 1, np.uint64)
+        nc = int(cell_off[-1])
+        batch = A.BlockBatch(var_off, read_off, arr(bs.read_start, nr, np.uint32), arr(bs.read_end, nr, np.uint32), cell_off,
+                             arr(bs.alleles, nc, np.uint8), arr(bs.quals, nc, np.uint8), arr(bs.ignored, nv, np.uint8), arr(bs.is_snv, nv, np.uint8))
+        var_pos = arr(vp, nv, np.int64) if vp else None
+        return batch, var_pos
+    finally:
+        lib().hp_pack_close(h)
+
+
+def write_phase_stats(path, batch, out, var_pos=None, first_block_index=0):
+    """hp_write_phase_stats: the solver-side columns of HiPhase's --stats-file, one row per block."""
+    import numpy as np
+    bs, os_ = batch.as_struct(), out.as_struct()
+    vp = None if var_pos is None else np.ascontiguousarray(var_pos, np.int64)
+    rc = lib().hp_write_phase_stats(os.fsencode(path), C.byref(bs), A.ptr(vp, A.i64p), C.byref(os_), int(first_block_index))
+    if rc != A.HP_OK:
+        raise HiPhaseB200Error(rc, (lib().hp_pack_last_error() or b"").decode())

@@ -331,6 +331,23 @@ int hp_edit_distance_batch(hp_ctx* ctx, uint32_t n_pairs, const uint8_t* bytes, 
                            const uint64_t* a_off, const uint32_t* a_len, const uint64_t* b_off, const uint32_t* b_len,
                            uint32_t* dist);
 
+/* ---- packed phase-block container + stats writer ----------------------------------------
+ * The wire / on-disk form of a block batch, "HPB200" v1 (layout in csrc/hp_pack.cu): what a front end that still owns
+ * VCF / BAM decoding (the HiPhase Rust code up to src/phaser.rs:541, or any other reader) writes, and what the batch
+ * runner tools/hp_phase_blocks reads.  These functions are host-only (no GPU needed). */
+typedef struct hp_packed hp_packed;
+/* var_pos may be NULL (then block tags / stats positions fall back to variant indices). */
+int  hp_pack_write_blocks(const char* path, const hp_block_batch* batch, const int64_t* var_pos);
+/* Reads and validates a whole file; the batch returned by hp_pack_get_blocks points into memory owned by *out. */
+int  hp_pack_open(const char* path, hp_packed** out);
+int  hp_pack_get_blocks(const hp_packed* packed, hp_block_batch* batch, const int64_t** var_pos);
+void hp_pack_close(hp_packed* packed);
+const char* hp_pack_last_error(void);
+/* One row per block with the solver-side columns of HiPhase's --stats-file (src/writers/phase_stats.rs:207-254);
+ * tab separated, comma separated when the path ends in ".csv" (phase_stats.rs:262-271). */
+int  hp_write_phase_stats(const char* path, const hp_block_batch* batch, const int64_t* var_pos, const hp_astar_out* out,
+                          uint64_t first_block_index);
+
 #ifdef __cplusplus
 }
 #endif
