@@ -50,7 +50,7 @@ okt = torch.tensor([ok, batch.n_vars], dtype=torch.int64, device="cuda")
 if world > 1:
     dist.all_reduce(okt, op=dist.ReduceOp.SUM)
 if rank == 0:
-    print(json.dumps({"config": "C5 scaled: C3 block stream (N 20-2000, 30x, 2% noisy), %d blocks per GPU" % per_gpu, "n_gpus": world,
+    print(json.dumps({"config": "C5 scaled: C3 block stream (N 20-2000, 30x, 2%% noisy), %d blocks per GPU" % per_gpu, "n_gpus": world,
                       "blocks": total, "variants": int(okt[1]), "blocks_ok": int(okt[0]), "e2e_s_max_over_ranks": float(t[0]),
                       "blocks_per_s": total / float(t[0]), "variants_per_s": int(okt[1]) / float(t[0]), "solver_kernels_s_max": float(t[1]),
                       "result_gather_s": gather_s, "gathered_records": int(allrec.shape[0]), "checksum_actual_cost": int(allrec[:, 2].sum()),
