@@ -333,6 +333,10 @@ constexpr bool kDeadPool = HP_DEAD_POOL != 0;
 #define HP_SWEEP_MIN_QUEUE 4096
 #endif
 constexpr uint32_t kSweepMinQueue = HP_SWEEP_MIN_QUEUE;   // dead entries are swept into the pool only while the queue is this large
+#ifndef HP_SUB_SERIAL_SCAN
+#define HP_SUB_SERIAL_SCAN 4
+#endif
+constexpr uint32_t kSubSerialScan = HP_SUB_SERIAL_SCAN;   // stripes up to this long are rescanned by their owner lane alone
 constexpr uint32_t kFreeStack = 192;   // free main-queue record slots kept in shared memory
 
 struct WarpCtx {
@@ -355,6 +359,8 @@ struct WarpCtx {
     uint32_t lencnt_cap_s;
     // counters
     uint64_t evals, sum_lp, pops, cells;
+    long long ts_pop, ts_seat, ts_score, ts_rest;   // counting variant: sub-solver phase cycles of this warp
+    uint64_t ns_real, ns_planes, ns_exp;
     int status;
     // entry i of stripe `stripe`
     __device__ __forceinline__ SubEntry* ent(uint32_t stripe, uint32_t i) const {
@@ -369,6 +375,41 @@ __device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1
     uint4* p = reinterpret_cast<uint4*>(e);
     p[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
     p[1] = make_uint4((uint32_t)h2, (uint32_t)(h2 >> 32), frozen, tag);
+}
+
+// Removes entry `pos` of stripe `owner` (swap with the stripe's last entry) and recomputes that stripe's cached minimum:
+// by the owner lane alone for short stripes, by the whole warp (one entry per lane, then a warp minimum) for longer ones.
+__device__ __forceinline__ void sub_remove_rescan(const WarpCtx& w, int owner, uint32_t pos, uint32_t& cnt, uint64_t& ckey, uint32_t& cpos) {
+    const uint32_t lane = w.lane;
+    const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1u;
+    if ((int)lane == owner) {
+        cnt--;
+        if (pos != cnt) {
+            const uint4* sp = reinterpret_cast<const uint4*>(w.ent(lane, cnt));
+            uint4* dp = reinterpret_cast<uint4*>(w.ent(lane, pos));
+            dp[0] = sp[0]; dp[1] = sp[1];
+        }
+    }
+    if (cnt_o <= kSubSerialScan) {
+        if ((int)lane == owner) {
+            ckey = ~0ull; cpos = 0;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint64_t k = w.ent(lane, i)->key;
+                if (k < ckey) { ckey = k; cpos = i; }
+            }
+        }
+        return;
+    }
+    __syncwarp();
+    uint64_t bk = ~0ull; uint32_t bp = 0;
+    for (uint32_t i = lane; i < cnt_o; i += 32) {
+        const uint64_t k = w.ent((uint32_t)owner, i)->key;
+        if (k < bk) { bk = k; bp = i; }
+    }
+    const uint64_t mk = wmin64(bk);
+    const int wl = __ffs(__ballot_sync(HP_FULL_MASK, bk == mk)) - 1;
+    const uint32_t mp = __shfl_sync(HP_FULL_MASK, bp, wl);
+    if ((int)lane == owner) { ckey = mk; cpos = mp; }
 }
 
 // astar_subsolver (astar_phaser.rs:311-405).  Returns est in .x, solved depth in .y (both warp-uniform).
@@ -420,19 +461,7 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
             cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
             cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
             __syncwarp();
-            if ((int)lane == owner) {                                    // remove + rescan own stripe
-                cnt--;
-                if (pos != cnt) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(w.ent(lane, cnt));
-                    uint4* dp = reinterpret_cast<uint4*>(w.ent(lane, pos));
-                    dp[0] = sp[0]; dp[1] = sp[1];
-                }
-                ckey = ~0ull; cpos = 0;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const uint64_t k = w.ent(lane, i)->key;
-                    if (k < ckey) { ckey = k; cpos = i; }
-                }
-            }
+            sub_remove_rescan(w, owner, pos, cnt, ckey, cpos);
             qmin = wmin64(ckey);
             // where does this node's score vector come from?
             const uint32_t d = ((cur_lo >> 6) & 0xfffffu) - cache.first_idx;
@@ -589,8 +618,11 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 0;
     const uint32_t max_visits = a.min_queue_size / 10 + a.queue_increment * clip;    // :266, :333
 
+    long long tq = 0;
     for (;;) {
+        if (kCount) tq = clock64();
         if (qmin < mk64(cur_total, cur_lo)) {
+            if (kCount) w.ns_real++;
             // ---- the dive broke: cur goes back to the queue, then a real pop of the entry whose key is qmin ----
             {
                 const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
@@ -619,20 +651,9 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 }
             }
             __syncwarp();
-            if ((int)lane == owner) {                                    // remove + rescan own stripe
-                cnt--;
-                if (pos != cnt) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(w.ent(lane, cnt));
-                    uint4* dp = reinterpret_cast<uint4*>(w.ent(lane, pos));
-                    dp[0] = sp[0]; dp[1] = sp[1];
-                }
-                ckey = ~0ull; cpos = 0;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const uint64_t k = w.ent(lane, i)->key;
-                    if (k < ckey) { ckey = k; cpos = i; }
-                }
-            }
+            sub_remove_rescan(w, owner, pos, cnt, ckey, cpos);
             qmin = wmin64(ckey);
+            if (kCount) { const long long t1 = clock64(); w.ts_pop += t1 - tq; tq = t1; }
             // re-seat the column state on this node's position
             const uint32_t Lp = cur_lo & 63u;
             const uint32_t pp = v + Lp;
@@ -653,6 +674,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 }
             }
         }
+        if (kCount) { const long long t1 = clock64(); w.ts_seat += t1 - tq; tq = t1; }
         // ---- cur is the top of the queue (peek) ----
         const uint32_t L = cur_lo & 63u;
         if (L >= clip) {                                                 // :395-399 (peek, not pop)
@@ -721,6 +743,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
 
         const uint32_t present = present_mask(bad_col, ident);
         const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
+        if (kCount) { const long long t1 = clock64(); w.ts_score += t1 - tq; tq = t1; w.ns_exp++; if (cur_src == SRC_PLANES) w.ns_planes++; }
         if (kCount) { w.pops++; w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
 
         // candidate totals / keys; low words are ordered lo0 < lo1 < lo2 < lo3, so the first minimum wins ties
@@ -825,6 +848,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         cur_src = SRC_CACHE;
         heur_p = heur;
         __syncwarp();
+        if (kCount) w.ts_rest += clock64() - tq;
         if (w.status != HP_BLOCK_OK) break;
     }
     return make_uint2(max_cost, next_expected - 1);
@@ -1773,6 +1797,13 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
 // barrier the results are verified in chain order and the longest valid prefix is committed (warp 0 never
 // speculates, so every round commits at least one variant).  Results are exactly those of the serial chain.
 constexpr int kMaxTeam = 4;
+#ifndef HP_SPEC_FAIL_ROUNDS
+#define HP_SPEC_FAIL_ROUNDS 6
+#endif
+#ifndef HP_SPEC_PAUSE_ROUNDS
+#define HP_SPEC_PAUSE_ROUNDS 24
+#endif
+constexpr uint32_t kSpecFailRounds = HP_SPEC_FAIL_ROUNDS, kSpecPauseRounds = HP_SPEC_PAUSE_ROUNDS;
 
 struct TeamShared {
     uint32_t blk;
@@ -1809,11 +1840,17 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
     int status = HP_BLOCK_OK;
     uint32_t n_rounds = 0;
     long long t_wait = 0;
+    // Speculation pays only where H[v] == H[v+1] is common.  In noisy stretches every guess fails and the guessing warps
+    // only slow warp 0 down (shared issue slots, the round lasts as long as its slowest sub-solve): after kSpecFailRounds
+    // rounds in a row that committed a single variant the team runs warp 0 alone for kSpecPauseRounds rounds, then tries
+    // again.  Which warps compute never changes what is committed.
+    uint32_t spec_streak = 0, spec_pause = 0;
     while (v_hi >= 0 && status == HP_BLOCK_OK) {
+        const uint32_t eff_team = spec_pause ? 1u : team;
         const int v = v_hi - (int)warp;
         const uint32_t clip_guess = min(clip0 + warp, HP_MAX_SEGMENT);
         const uint64_t e0 = w.evals, c0 = w.cells, l0 = w.sum_lp, p0 = w.pops;
-        if (v >= 0) {
+        if (v >= 0 && warp < eff_team) {
             w.h_floor = (uint32_t)v_hi + 1;
             w.status = HP_BLOCK_OK;
             const uint2 r = sub_solve<K, kCount>(a, m, w, (uint32_t)v, clip_guess, bad_window(ign, (uint32_t)v, N, w.lane), blk);
@@ -1831,7 +1868,7 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
 #pragma unroll
         for (uint32_t i = 0; i < (uint32_t)kMaxTeam; i++) {
             const int vi = v_hi - (int)i;
-            if (i < team && vi >= 0 && chain_ok && status == HP_BLOCK_OK && clip_chk == min(clip0 + i, HP_MAX_SEGMENT)) {
+            if (i < eff_team && vi >= 0 && chain_ok && status == HP_BLOCK_OK && clip_chk == min(clip0 + i, HP_MAX_SEGMENT)) {
                 const uint32_t est = ts.est[i], solved = ts.solved[i];
                 if (ts.status[i] != HP_BLOCK_OK) status = ts.status[i];
                 else if (solved < min(clip_chk, 2u)) status = HP_BLOCK_ASSERT;                 // :268
@@ -1865,6 +1902,11 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
             for (uint32_t i = 0; i < (uint32_t)kMaxTeam; i++)
                 if (i < accepted) { ts.hring[(v_hi - (int)i) & 63] = hv_out[i]; Hg[v_hi - (int)i] = hv_out[i]; }
         }
+        if (spec_pause) spec_pause--;
+        else if (team > 1) {
+            spec_streak = (accepted <= 1) ? spec_streak + 1 : 0;
+            if (spec_streak >= kSpecFailRounds) { spec_pause = kSpecPauseRounds; spec_streak = 0; }
+        }
         v_hi -= (int)accepted;
         clip0 = clip_chk;
         if (accepted == 0 && status == HP_BLOCK_OK) status = HP_BLOCK_ASSERT;      // cannot happen: warp 0 is never speculative
@@ -1891,6 +1933,11 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
                     d[0] = (uint64_t)(t_mid - t_start); d[1] = (uint64_t)(clock64() - t_mid); d[2] = ts.ctr[3]; d[3] = w.pops;
 #ifndef HP_DBG_MAIN_SPLIT
                     d[4] = n_rounds; d[5] = team; d[6] = (uint64_t)t_wait;
+#endif
+#ifdef HP_DBG_SUB_SPLIT
+                    // sub-solver phase split of warp 0 (its sub-solves are never speculative) instead of the main-loop split
+                    d[8] = (uint64_t)w.ts_pop; d[9] = (uint64_t)w.ts_seat; d[10] = (uint64_t)w.ts_score; d[11] = (uint64_t)w.ts_rest;
+                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp;
 #endif
                 }
                 ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;
@@ -1923,6 +1970,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     w.hring = ts.hring;
     w.h_floor = 0;
     w.evals = w.sum_lp = w.pops = w.cells = 0;
+    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
 
     // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp
     uint8_t* my_slab = a.slabs + (uint64_t)blockIdx.x * a.slab_bytes;
@@ -1953,6 +2001,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
         const uint32_t blk = a.order[first + t];
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
+        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
         w.status = m.status;
         if (threadIdx.x == 0) ts.final_status = m.status;
 

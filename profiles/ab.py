@@ -7,6 +7,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     import numpy as np
     from hiphase_b200 import lib, synth
     ctx = lib.Context(device=0)
+    if os.environ.get("AB_TEAM"):
+        ctx.set_team(int(os.environ["AB_TEAM"]))
     res = []
     for name, batch in (("c2", synth.config_c2(1000)), ("c3", synth.config_c3(int(os.environ.get("AB_C3", "1000"))))):
         ms = []
