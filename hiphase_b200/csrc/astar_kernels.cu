@@ -597,7 +597,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
     // current top (root, :325)
-    uint32_t cur_total = w.H(v + 1), cur_lo = 63u << 26, cur_frozen = 0;
+    uint32_t cur_total = w.H(v + 1), cur_lo = 63u << 26;
     uint64_t cur_h1 = 0, cur_h2 = 0;
     int cur_src = SRC_ROOT;
     uint32_t cur_x1 = 0, cur_x2 = 0;
@@ -631,7 +631,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint64_t k = mk64(cur_total, cur_lo);
-                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, cur_frozen);
+                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, 0u);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -641,7 +641,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
             const SubEntry* e = w.ent(owner, pos);
             cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
-            cur_h1 = e->h1; cur_h2 = e->h2; cur_frozen = e->frozen;
+            cur_h1 = e->h1; cur_h2 = e->h2;
             {
                 const uint32_t tag = e->tag;
                 if (tag < 4u) {                                          // parent's haplotypes + this node's candidate slot
@@ -720,8 +720,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         }
         // ---- children: deltas against base, packed two per word ----
         uint32_t A0[K], A1[K], B0[K], B1[K];
-        uint32_t pk0 = 0, pk1 = 0, e01 = 0, e10 = 0, e00 = 0, e11 = 0;
-        bool anyend = false;
+        uint32_t pk0 = 0, pk1 = 0;
         uint64_t cells = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -734,12 +733,9 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t c01 = min(A0[k], B1[k]), c10 = min(A1[k], B0[k]), c00 = min(A0[k], B0[k]), c11 = min(A1[k], B1[k]);
             pk0 += (c01 - base) | ((c10 - base) << 16);
             pk1 += (c00 - base) | ((c11 - base) << 16);
-            if ((c >> 10) & 1u) { anyend = true; e01 += c01; e10 += c10; e00 += c00; e11 += c11; }
             if (kCount) { wv[k] += 1; if (lane + 32u * k < a_cur) cells += wv[k]; }
         }
         const uint32_t r0 = wsum(pk0), r1 = wsum(pk1);
-        uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-        if (__ballot_sync(HP_FULL_MASK, anyend)) { f0 = wsum(e01); f1 = wsum(e10); f2 = wsum(e00); f3 = wsum(e11); }
 
         const uint32_t present = present_mask(bad_col, ident);
         const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
@@ -795,11 +791,10 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t rsel = (c & 2u) ? r1 : r0;
             const uint32_t mt = tb + ((c & 1u) ? (rsel >> 16) : (rsel & 0xffffu));
             const uint32_t ml = ((c & 2u) ? lo2 : lo0) + ((c & 1u) << 6);
-            const uint32_t mf = cur_frozen + ((c == 0u) ? f0 : (c == 1u) ? f1 : (c == 2u) ? f2 : f3);
             if (__ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl) == 0) {
                 if (mine) {
                     const uint64_t k = mk64(mt, ml);
-                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, mf, c);
+                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, 0u, c);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -812,10 +807,9 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                         uint32_t target = src_lane;
                         if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                         const uint32_t xt = __shfl_sync(HP_FULL_MASK, mt, src_lane), xl = __shfl_sync(HP_FULL_MASK, ml, src_lane);
-                        const uint32_t xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
                         if (lane == target) {
                             const uint64_t k = mk64(xt, xl);
-                            sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, xf, cc);
+                            sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, 0u, cc);
                             if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
@@ -839,7 +833,6 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         // ---- the best child is the new cur ----
         cur_total = tmin;
         cur_lo = ((best & 2u) ? lo2 : lo0) + ((best & 1u) << 6);
-        cur_frozen += (best == 0u) ? f0 : (best == 1u) ? f1 : (best == 2u) ? f2 : f3;
         cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
         if (!bad_col) {
             cur_h1 |= (uint64_t)cur_x1 << L;
@@ -1300,7 +1293,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     uint64_t c_hi = ~0ull; uint32_t c_idx = 0xffffffffu, c_pos = 0, cnt = 0;
     MainKey qmin; qmin.hi = ~0ull; qmin.idx = 0xffffffffu;
     // current top (root, :485-487)
-    uint32_t cur_total = Hg[0], cur_nh = 0xffffffffu, cur_idx = 0, cur_len = 0, cur_frozen = 0, cur_rec = 0;
+    uint32_t cur_total = Hg[0], cur_nh = 0xffffffffu, cur_idx = 0, cur_len = 0, cur_rec = 0;
     bool cur_ident = true, have_cur = true;
     int cur_src = SRC_ROOT;
     uint32_t cur_x1 = 0, cur_x2 = 0;
@@ -1335,7 +1328,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 if (lane == target) {
                     const uint64_t hi = ((uint64_t)cur_total << 32) | cur_nh;
                     *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = cur_idx; *klen_at(lane, cnt) = cur_len | (cur_ident ? 0x80000000u : 0u);
-                    *krec_at(lane, cnt) = cur_rec; s.kfrozen[cur_rec] = cur_frozen;
+                    *krec_at(lane, cnt) = cur_rec;
                     if (key_less(hi, cur_idx, c_hi, c_idx)) { c_hi = hi; c_idx = cur_idx; c_pos = cnt; }
                     cnt++;
                 }
@@ -1350,7 +1343,6 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             cur_len = lenf & 0x7fffffffu; cur_ident = (lenf >> 31) != 0;
             cur_rec = *krec_at(owner, pos);
             if (cur_len >= min_progress && cur_len < N) {                 // pruned / final nodes never need the payload
-                cur_frozen = s.kfrozen[cur_rec];
                 if (regs_hap) {
                     const uint64_t* r = s.recs + (uint64_t)cur_rec * 2 * HW;
                     const bool own = lane < ((cur_len + 63) >> 6);
@@ -1483,8 +1475,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             }
         }
         uint32_t A0[K], A1[K], B0[K], B1[K];
-        uint32_t pk0 = 0, pk1 = 0, e01 = 0, e10 = 0, e00 = 0, e11 = 0;
-        bool anyend = false;
+        uint32_t pk0 = 0, pk1 = 0;
         uint64_t cells = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -1497,12 +1488,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t c01 = min(A0[k], B1[k]), c10 = min(A1[k], B0[k]), c00 = min(A0[k], B0[k]), c11 = min(A1[k], B1[k]);
             pk0 += (c01 - base) | ((c10 - base) << 16);
             pk1 += (c00 - base) | ((c11 - base) << 16);
-            if ((c >> 10) & 1u) { anyend = true; e01 += c01; e10 += c10; e00 += c00; e11 += c11; }
             if (kCount) { wv[k] += 1; if (lane + 32u * k < a_cur) cells += wv[k]; }
         }
         const uint32_t r0 = wsum(pk0), r1 = wsum(pk1);
-        uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-        if (__ballot_sync(HP_FULL_MASK, anyend)) { f0 = wsum(e01); f1 = wsum(e10); f2 = wsum(e00); f3 = wsum(e11); }
         const uint32_t present = present_mask(bad_col, ident);
         const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
         if (kCount) {
@@ -1613,14 +1601,12 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         {
             const uint32_t mt = (c_mine == 0u) ? t0 : (c_mine == 1u) ? t1 : (c_mine == 2u) ? t2 : t3;
             const uint32_t mi = (c_mine == 0u) ? i0 : (c_mine == 1u) ? i1 : (c_mine == 2u) ? i2 : i3;
-            const uint32_t mf = cur_frozen + ((c_mine == 0u) ? f0 : (c_mine == 1u) ? f1 : (c_mine == 2u) ? f2 : f3);
             const uint64_t mhi = ((uint64_t)mt << 32) | ((c_mine < 2u && !bad_col) ? nh_het : cur_nh);
             const uint32_t mlen = (L + 1) | ((cur_ident && c_mine >= 2u) ? 0x80000000u : 0u);
             const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= scap);
             if (fullmask == 0) {
                 if (mine) {
                     *khi_at(lane, cnt) = mhi; *kidx_at(lane, cnt) = mi; *klen_at(lane, cnt) = mlen; *krec_at(lane, cnt) = my_rec;
-                    s.kfrozen[my_rec] = mf;
                     if (key_less(mhi, mi, c_hi, c_idx)) { c_hi = mhi; c_idx = mi; c_pos = cnt; }
                     cnt++;
                 }
@@ -1634,10 +1620,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                         if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                         const uint64_t xhi = __shfl_sync(HP_FULL_MASK, mhi, src_lane);
                         const uint32_t xi = __shfl_sync(HP_FULL_MASK, mi, src_lane), xl = __shfl_sync(HP_FULL_MASK, mlen, src_lane);
-                        const uint32_t xr = __shfl_sync(HP_FULL_MASK, my_rec, src_lane), xf = __shfl_sync(HP_FULL_MASK, mf, src_lane);
+                        const uint32_t xr = __shfl_sync(HP_FULL_MASK, my_rec, src_lane);
                         if (lane == target) {
                             *khi_at(lane, cnt) = xhi; *kidx_at(lane, cnt) = xi; *klen_at(lane, cnt) = xl; *krec_at(lane, cnt) = xr;
-                            s.kfrozen[xr] = xf;
                             if (key_less(xhi, xi, c_hi, c_idx)) { c_hi = xhi; c_idx = xi; c_pos = cnt; }
                             cnt++;
                         }
@@ -1663,7 +1648,6 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         cur_total = tmin;
         cur_nh = (best < 2u && !bad_col) ? nh_het : cur_nh;
         cur_idx = (best == 0u) ? i0 : (best == 1u) ? i1 : (best == 2u) ? i2 : i3;
-        cur_frozen += (best == 0u) ? f0 : (best == 1u) ? f1 : (best == 2u) ? f2 : f3;
         cur_len = L + 1;
         cur_ident = cur_ident && best >= 2u;
         cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
