@@ -1565,16 +1565,29 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t wl = L >> 6;
             const uint64_t bit = bad_col ? 0ull : (1ull << (L & 63));
             if (regs_hap) {
-#pragma unroll
-                for (uint32_t cc = 0; cc < 4; cc++) {
-                    if ((present >> cc) & 1u) {
-                        const uint32_t rc = (cc == best) ? cur_rec : __shfl_sync(HP_FULL_MASK, my_rec, (rr + cc) & 31u);
-                        if (lane <= wl && (cc != best || lane == wl)) {
-                            uint64_t* crow = s.recs + (uint64_t)rc * 2 * HW;
-                            crow[lane] = (lane == wl && (cc & 1u)) ? (cur_w1 | bit) : cur_w1;
-                            crow[HW + lane] = (lane == wl && ((0x9u >> cc) & 1u)) ? (cur_w2 | bit) : cur_w2;
-                        }
+                // lane = (sibling ordinal, word within a group of 8): up to 4 siblings x 8 words per step
+                const uint32_t sib = lane >> 3, wq = lane & 7u;
+                uint32_t sm = sibmask;
+                if (sib >= 1u) sm &= sm - 1u;
+                if (sib >= 2u) sm &= sm - 1u;
+                if (sib >= 3u) sm &= sm - 1u;
+                const bool has_sib = sib < nsib;
+                const uint32_t csl = has_sib ? (uint32_t)(__ffs(sm) - 1) : 0u;           // candidate slot of that sibling
+                const uint32_t rc = __shfl_sync(HP_FULL_MASK, my_rec, (rr + csl) & 31u);
+                uint64_t* crow = s.recs + (uint64_t)rc * 2 * HW;
+                const bool s1bit = (csl & 1u) != 0, s2bit = ((0x9u >> csl) & 1u) != 0;
+                for (uint32_t w0 = 0; w0 <= wl; w0 += 8) {
+                    const uint32_t wi = w0 + wq;
+                    const uint64_t x1 = __shfl_sync(HP_FULL_MASK, cur_w1, wi & 31u), x2 = __shfl_sync(HP_FULL_MASK, cur_w2, wi & 31u);
+                    if (has_sib && wi <= wl) {
+                        crow[wi] = (wi == wl && s1bit) ? (x1 | bit) : x1;
+                        crow[HW + wi] = (wi == wl && s2bit) ? (x2 | bit) : x2;
                     }
+                }
+                if (lane == wl) {                                                     // the best child: in place, one word
+                    uint64_t* brow = s.recs + (uint64_t)cur_rec * 2 * HW;
+                    brow[wl] = (best & 1u) ? (cur_w1 | bit) : cur_w1;
+                    brow[HW + wl] = ((0x9u >> best) & 1u) ? (cur_w2 | bit) : cur_w2;
                 }
             } else {
                 const uint64_t* prow = s.recs + (uint64_t)cur_rec * 2 * HW;

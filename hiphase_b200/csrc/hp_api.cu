@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -100,7 +101,9 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     // (up to 2x oversubscription of the resident warps still pays: measured on C2, 1000 blocks -> team 4)
     while (team * 2 <= astar_max_team() && (uint64_t)nb * team * 2 <= 2ull * (uint64_t)resident_warps) team *= 2;
     if (ctx->force_team > 0) team = std::min(ctx->force_team, astar_max_team());
-    int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)ctx->sm_count * (astar_warps_per_sm() / team));
+    int warps_per_sm = astar_warps_per_sm();
+    if (const char* e = getenv("HP_DBG_WARPS_PER_SM")) warps_per_sm = std::max(team, std::min(warps_per_sm, atoi(e)));   // occupancy experiments
+    int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)ctx->sm_count * (warps_per_sm / team));
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     const uint32_t hap_words = (max_block_vars + 63) / 64;
     const uint64_t slab_bytes = astar_slab_bytes(ctx->qcap, hap_words, ctx->sub_capl);
