@@ -1619,7 +1619,13 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t fullmask = __ballot_sync(HP_FULL_MASK, mine && cnt >= scap);
             if (fullmask == 0) {
                 if (mine) {
-                    *khi_at(lane, cnt) = mhi; *kidx_at(lane, cnt) = mi; *klen_at(lane, cnt) = mlen; *krec_at(lane, cnt) = my_rec;
+                    if (cnt < mqs) {                                       // shared-memory part of the stripe (the common case)
+                        const uint32_t o = lane * mqs + cnt;
+                        mq_hi[o] = mhi; mq_idx[o] = mi; mq_len[o] = mlen; mq_rec[o] = my_rec;
+                    } else {
+                        const size_t o = (size_t)lane * scap + cnt;
+                        s.khi[o] = mhi; s.kidx[o] = mi; s.klen[o] = mlen; s.krec[o] = my_rec;
+                    }
                     if (key_less(mhi, mi, c_hi, c_idx)) { c_hi = mhi; c_idx = mi; c_pos = cnt; }
                     cnt++;
                 }
@@ -1647,12 +1653,17 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         if (w.status != HP_BLOCK_OK) break;
         // queue minimum now includes the siblings
         {
-            const uint64_t h0 = ((uint64_t)t0 << 32) | nh_het, h1 = ((uint64_t)t1 << 32) | nh_het;
-            const uint64_t h2 = ((uint64_t)t2 << 32) | cur_nh, h3 = ((uint64_t)t3 << 32) | cur_nh;
-            if (best != 0u && t0 != 0xffffffffu && key_less(h0, i0, qmin.hi, qmin.idx)) { qmin.hi = h0; qmin.idx = i0; }
-            if (best != 1u && t1 != 0xffffffffu && key_less(h1, i1, qmin.hi, qmin.idx)) { qmin.hi = h1; qmin.idx = i1; }
-            if (best != 2u && key_less(h2, i2, qmin.hi, qmin.idx)) { qmin.hi = h2; qmin.idx = i2; }
-            if (best != 3u && t3 != 0xffffffffu && key_less(h3, i3, qmin.hi, qmin.idx)) { qmin.hi = h3; qmin.idx = i3; }
+            // among the siblings the smallest key is the smallest total, ties to the lowest slot (slots 0,1 carry one more
+            // het, and node indices grow with the slot)
+            const uint32_t u0 = (best == 0u) ? 0xffffffffu : t0, u1 = (best == 1u) ? 0xffffffffu : t1;
+            const uint32_t u2 = (best == 2u) ? 0xffffffffu : t2, u3 = (best == 3u) ? 0xffffffffu : t3;
+            const uint32_t m2 = min(min(u0, u1), min(u2, u3));
+            if (m2 != 0xffffffffu) {
+                const uint32_t c2 = (u0 == m2) ? 0u : (u1 == m2) ? 1u : (u2 == m2) ? 2u : 3u;
+                const uint64_t h = ((uint64_t)m2 << 32) | ((c2 < 2u && !bad_col) ? nh_het : cur_nh);
+                const uint32_t ix = (c2 == 0u) ? i0 : (c2 == 1u) ? i1 : (c2 == 2u) ? i2 : i3;
+                if (key_less(h, ix, qmin.hi, qmin.idx)) { qmin.hi = h; qmin.idx = ix; }
+            }
         }
         next_idx += nchild; qsize += nchild;
         if (lane == 0) lc[L + 1] += nchild;                               // tracker.add_hap(L+1) x nchild (:531, :558)
