@@ -332,7 +332,11 @@ constexpr bool kDeadPool = HP_DEAD_POOL != 0;
 #ifndef HP_SWEEP_MIN_QUEUE
 #define HP_SWEEP_MIN_QUEUE 4096
 #endif
-constexpr uint32_t kSweepMinQueue = HP_SWEEP_MIN_QUEUE;   // dead entries are swept into the pool only while the queue is this large
+constexpr uint32_t kSweepMinQueue = HP_SWEEP_MIN_QUEUE;
+#ifndef HP_SWEEP_MIN_DEAD
+#define HP_SWEEP_MIN_DEAD 256
+#endif
+constexpr uint32_t kSweepMinDead = HP_SWEEP_MIN_DEAD;     // ... or this many dead entries sit in the stripes   // dead entries are swept into the pool only while the queue is this large
 #ifndef HP_SUB_SERIAL_SCAN
 #define HP_SUB_SERIAL_SCAN 4
 #endif
@@ -1315,12 +1319,47 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         coln[k] = (1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
 
-    long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0, tm_vec = 0, tm_rec = 0, tm_push = 0;   // counting variant only
+    long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0, tm_vec = 0, tm_rec = 0, tm_push = 0, tm_dead = 0;   // counting variant only
     for (;;) {
         if (kCount) tq0 = clock64();
         if (!have_cur || key_less(qmin.hi, qmin.idx, ((uint64_t)cur_total << 32) | cur_nh, cur_idx)) {
             if (kCount) n_real++;
-            if (have_cur) {                                              // cur goes back to the queue
+            if (qmin.hi == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }   // empty queue (only without cur): the reference panics (:631)
+            const int owner = __ffs(__ballot_sync(HP_FULL_MASK, c_hi == qmin.hi && c_idx == qmin.idx)) - 1;
+            const uint32_t pos = __shfl_sync(HP_FULL_MASK, c_pos, owner);
+            const uint32_t lenf = *klen_at(owner, pos);
+            if ((lenf & 0x7fffffffu) < min_progress) {
+                // ---- the top entry is dead: the reference pops and discards it (:507-515).  cur stays where it is (in
+                //      registers): the discard happens before cur is looked at again, exactly as in the reference's order ----
+                const uint32_t drec = *krec_at(owner, pos);
+                const uint32_t cnt_d = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
+                __syncwarp();
+                if ((int)lane == owner) {
+                    cnt--;
+                    if (pos != cnt) {
+                        *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt);
+                        *klen_at(owner, pos) = *klen_at(owner, cnt); *krec_at(owner, pos) = *krec_at(owner, cnt);
+                    }
+                }
+                __syncwarp();
+                {
+                    uint64_t nhi; uint32_t nidx, npos;
+                    stripe_min(khi_at, kidx_at, owner, cnt_d, lane, nhi, nidx, npos);
+                    if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
+                }
+                qmin = wmin96(c_hi, c_idx);
+                qsize--;
+                if (lane == 0) lc[lenf & 0x7fffffffu] -= 1u;                  // hap_tracker.remove_hap (:495); below the threshold
+                w.pops++;
+                if (num_pruned == 0) curr_thresh = a.min_queue_size;        // :508-510
+                num_pruned++;
+                if (fs_top < kFreeStack) { if (lane == 0) w.free_stack[fs_top] = drec; fs_top++; }
+                else { if (lane == 0) s.freelist[free_top] = drec; free_top++; }
+                __syncwarp();
+                if (kCount) { const long long t1 = clock64(); tm_pop += t1 - tq0; tm_dead += t1 - tq0; }
+                continue;
+            }
+            if (have_cur) {                                              // cur goes back to the queue (appended: pos stays valid)
                 const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < scap);
                 if (room == 0) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
                 uint32_t target = rr & 31u; rr++;
@@ -1334,11 +1373,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 }
                 __syncwarp();
             }
-            // ---- real pop ----
-            if (qmin.hi == ~0ull) { w.status = HP_BLOCK_ASSERT; break; }   // empty queue: the reference panics (:631)
-            const int owner = __ffs(__ballot_sync(HP_FULL_MASK, c_hi == qmin.hi && c_idx == qmin.idx)) - 1;
-            const uint32_t pos = __shfl_sync(HP_FULL_MASK, c_pos, owner);
-            const uint32_t lenf = *klen_at(owner, pos);
+            // ---- real pop of a live entry ----
             cur_total = (uint32_t)(qmin.hi >> 32); cur_nh = (uint32_t)qmin.hi; cur_idx = qmin.idx;
             cur_len = lenf & 0x7fffffffu; cur_ident = (lenf >> 31) != 0;
             cur_rec = *krec_at(owner, pos);
@@ -1695,7 +1730,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             trk_total -= dropped; trk_thresh = min_progress;
             // sweep policy: any subset of the dead entries may move to the pool at any time (dead pops commute); entries
             // left in their stripe are discarded by the ordinary pop path when they surface
-            if (kDeadPool && dropped != 0 && qsize > kSweepMinQueue) {
+            // (swept when the queue is large, or when enough dead entries have piled up in the stripes to pay for the pass:
+            //  a sweep costs a few thousand cycles, discarding one dead entry at the top ~2000)
+            if (kDeadPool && dropped != 0 && (qsize > kSweepMinQueue || qsize - pool_n - trk_total >= kSweepMinDead)) {
                 if (lane == 0) { *w.free_ctr = free_top; *w.pool_ctr = pool_n; }
                 __syncwarp();
                 uint32_t j = 0;
@@ -1769,6 +1806,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         uint64_t* d = a.dbg_cycles + 16ull * blk;
         d[8] = tm_pop; d[9] = tm_exp; d[10] = tm_rest; d[11] = n_planes; d[12] = tm_planes;
         d[13] = n_real; d[14] = num_pruned; d[15] = qsize; d[7] = n_swept;
+#ifdef HP_DBG_MAIN_SPLIT
+        d[15] = tm_dead;     // cycles spent discarding dead top entries (part of the real-pop time)
+#endif
         d[5] = tm_vec; d[6] = tm_rec; d[4] = tm_push;   // (overwritten below by the team's round statistics unless HP_DBG_MAIN_SPLIT)
     }
     if (w.status != HP_BLOCK_OK) return;

@@ -22,4 +22,4 @@ print("main loop cycles, all blocks: " + "  ".join("%s %.3g" % (n, d[:, c].sum()
 for k in np.argsort(tot)[-5:]:
     exp = d[k, 3] - d[k, 14]
     print("block %4d main %.3g cycles, pops %d (real %d, pruned %d), expansions %d: " % (k, d[k, 1], d[k, 3], d[k, 13], d[k, 14], exp) +
-          "  ".join("%s %.0f/exp" % (n, d[k, c] / max(exp, 1)) for n, c in zip(names[1:], cols[1:])) + "  real-pop %.0f/pop" % (d[k, 8] / max(d[k, 13], 1)))
+          "  ".join("%s %.0f/exp" % (n, d[k, c] / max(exp, 1)) for n, c in zip(names[1:], cols[1:])) + "  real-pop %.0f/pop (dead discards %.0f each, live pops %.0f each)" % (d[k, 8] / max(d[k, 13], 1), d[k, 15] / max(d[k, 14], 1), (d[k, 8] - d[k, 15]) / max(d[k, 13] - d[k, 14], 1)))
