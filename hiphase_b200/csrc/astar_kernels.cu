@@ -329,14 +329,10 @@ struct __align__(16) SubEntry {
 #define HP_DEAD_POOL 1
 #endif
 constexpr bool kDeadPool = HP_DEAD_POOL != 0;
-#ifndef HP_SWEEP_MIN_QUEUE
-#define HP_SWEEP_MIN_QUEUE 4096
-#endif
-constexpr uint32_t kSweepMinQueue = HP_SWEEP_MIN_QUEUE;
 #ifndef HP_SWEEP_MIN_DEAD
 #define HP_SWEEP_MIN_DEAD 256
 #endif
-constexpr uint32_t kSweepMinDead = HP_SWEEP_MIN_DEAD;     // ... or this many dead entries sit in the stripes   // dead entries are swept into the pool only while the queue is this large
+constexpr uint32_t kSweepMinDead = HP_SWEEP_MIN_DEAD;     // dead entries are swept into the pool once this many sit in the stripes   // dead entries are swept into the pool only while the queue is this large
 #ifndef HP_SUB_SERIAL_SCAN
 #define HP_SUB_SERIAL_SCAN 4
 #endif
@@ -1285,6 +1281,11 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     uint64_t* const pool_hi = s.pool_hi; uint32_t* const pool_idx = s.pool_idx;
     uint32_t pool_n = 0;
     MainKey pool_min; pool_min.hi = ~0ull; pool_min.idx = 0xffffffffu;
+    // A pool entry with key k is popped (and discarded) by the reference right before the first live node with a larger
+    // key that is processed after the entry entered the pool.  All entries of the pool share one epoch (it restarts at
+    // every evaluation), so "popped by now" == k < pool_max, the largest live key processed since the epoch began: the
+    // count is only needed where the reference looks at it (first prune, full-prune test, final statistics).
+    MainKey pool_max; pool_max.hi = 0ull; pool_max.idx = 0u;
     uint32_t trk_total = 1, trk_thresh = 0;                              // root counted (:488)
     uint32_t curr_thresh = a.min_queue_size;
     const uint32_t max_queue = 10u * a.min_queue_size;                   // :457
@@ -1319,6 +1320,34 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         coln[k] = (1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
 
+    auto eval_pool = [&]() {
+        // counts and removes the pool entries popped so far (key < pool_max), restarts the epoch
+        uint32_t base = 0;
+        uint64_t m_hi = ~0ull; uint32_t m_idx = 0xffffffffu;
+        for (uint32_t c0 = 0; c0 < pool_n; c0 += 32) {
+            const uint32_t i = c0 + lane;
+            const bool in = i < pool_n;
+            uint64_t hi = ~0ull; uint32_t ix = 0xffffffffu;
+            if (in) { hi = pool_hi[i]; ix = pool_idx[i]; }
+            const bool keep = in && !key_less(hi, ix, pool_max.hi, pool_max.idx);
+            const uint32_t km = __ballot_sync(HP_FULL_MASK, keep);
+            if (keep) {
+                const uint32_t d = base + __popc(km & ((1u << lane) - 1u));
+                pool_hi[d] = hi; pool_idx[d] = ix;
+                if (key_less(hi, ix, m_hi, m_idx)) { m_hi = hi; m_idx = ix; }
+            }
+            base += __popc(km);
+        }
+        __syncwarp();
+        const uint32_t k = pool_n - base;
+        pool_n = base;
+        pool_min = wmin96(m_hi, m_idx);
+        pool_max.hi = 0ull; pool_max.idx = 0u;
+        if (k != 0) {
+            if (num_pruned == 0) curr_thresh = a.min_queue_size;          // :508-510
+            num_pruned += k; qsize -= k; w.pops += k;
+        }
+    };
     long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0, tm_vec = 0, tm_rec = 0, tm_push = 0, tm_dead = 0;   // counting variant only
     for (;;) {
         if (kCount) tq0 = clock64();
@@ -1419,33 +1448,12 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             qmin = wmin96(c_hi, c_idx);
             have_cur = true;
         }
-        // ---- cur is the top of the live entries: the reference first pops and discards every dead entry with a smaller
-        //      key, one by one, and nothing else happens in between (:507-515) ----
-        if (pool_n != 0 && key_less(pool_min.hi, pool_min.idx, ((uint64_t)cur_total << 32) | cur_nh, cur_idx)) {
+        // ---- cur is the top of the live entries: every pool entry with a smaller key has been popped before it (:507-515) ----
+        {
             const uint64_t k_hi = ((uint64_t)cur_total << 32) | cur_nh;
-            uint32_t base = 0;
-            uint64_t m_hi = ~0ull; uint32_t m_idx = 0xffffffffu;
-            for (uint32_t c0 = 0; c0 < pool_n; c0 += 32) {
-                const uint32_t i = c0 + lane;
-                const bool in = i < pool_n;
-                uint64_t hi = ~0ull; uint32_t ix = 0xffffffffu;
-                if (in) { hi = pool_hi[i]; ix = pool_idx[i]; }
-                const bool keep = in && !key_less(hi, ix, k_hi, cur_idx);
-                const uint32_t km = __ballot_sync(HP_FULL_MASK, keep);
-                if (keep) {
-                    const uint32_t d = base + __popc(km & ((1u << lane) - 1u));
-                    pool_hi[d] = hi; pool_idx[d] = ix;
-                    if (key_less(hi, ix, m_hi, m_idx)) { m_hi = hi; m_idx = ix; }
-                }
-                base += __popc(km);
-            }
-            __syncwarp();
-            const uint32_t k = pool_n - base;
-            pool_n = base;
-            pool_min = wmin96(m_hi, m_idx);
-            if (num_pruned == 0) curr_thresh = a.min_queue_size;          // :508-510 (k >= 1 here)
-            num_pruned += k; qsize -= k; w.pops += k;
-            if (kCount) n_swept += k;
+            if (key_less(pool_max.hi, pool_max.idx, k_hi, cur_idx)) { pool_max.hi = k_hi; pool_max.idx = cur_idx; }
+            // the first prune resets the queue threshold (:508-510): until it happened the count must be exact in time
+            if (num_pruned == 0 && pool_n != 0 && key_less(pool_min.hi, pool_min.idx, k_hi, cur_idx)) eval_pool();
         }
         const uint32_t L = cur_len;
         if (L >= N) break;                                                // :492
@@ -1730,9 +1738,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             trk_total -= dropped; trk_thresh = min_progress;
             // sweep policy: any subset of the dead entries may move to the pool at any time (dead pops commute); entries
             // left in their stripe are discarded by the ordinary pop path when they surface
-            // (swept when the queue is large, or when enough dead entries have piled up in the stripes to pay for the pass:
-            //  a sweep costs a few thousand cycles, discarding one dead entry at the top ~2000)
-            if (kDeadPool && dropped != 0 && (qsize > kSweepMinQueue || qsize - pool_n - trk_total >= kSweepMinDead)) {
+            // (swept when enough dead entries have piled up in the stripes to pay for the pass: a sweep plus the pool
+            //  evaluation cost a few thousand cycles, discarding one dead entry at the top ~2000)
+            if (kDeadPool && dropped != 0 && qsize - pool_n - trk_total >= kSweepMinDead) {
+                eval_pool();                                               // one epoch for old and new pool entries
                 if (lane == 0) { *w.free_ctr = free_top; *w.pool_ctr = pool_n; }
                 __syncwarp();
                 uint32_t j = 0;
@@ -1776,6 +1785,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 if (key_less(nm.hi, nm.idx, pool_min.hi, pool_min.idx)) pool_min = nm;
                 qmin = wmin96(c_hi, c_idx);
             }
+            if (kDeadPool && qsize > max_queue && pool_n != 0) eval_pool();   // qsize was an upper bound: make it exact
             if (kDeadPool && qsize > max_queue) {
                 // "full prune": every dead entry gets the cleared priority (cost 0)
                 uint64_t m_hi = ~0ull; uint32_t m_idx = 0xffffffffu;
@@ -1802,6 +1812,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         }
         if (kCount) tm_rest += clock64() - tq0;
     }
+    if (w.status == HP_BLOCK_OK && pool_n != 0) eval_pool();                   // dead entries popped before the final node
     if (kCount && a.dbg_cycles && lane == 0) {
         uint64_t* d = a.dbg_cycles + 16ull * blk;
         d[8] = tm_pop; d[9] = tm_exp; d[10] = tm_rest; d[11] = n_planes; d[12] = tm_planes;
