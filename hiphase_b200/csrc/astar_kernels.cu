@@ -1596,6 +1596,13 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             // sibling ordinal of candidate c = number of present non-best candidates below it
             const uint32_t sibmask = present & ~(1u << best);
             const uint32_t my_ord = __popc(sibmask & ((1u << (c_mine & 31u)) - 1u));
+            if (fs_top < nsib && free_top != 0) {
+                // refill the shared-memory stack from the slab's free list in one coalesced pass (bulk frees land there)
+                const uint32_t n = min(min(free_top, kFreeStack - fs_top), 128u);
+                for (uint32_t q = lane; q < n; q += 32) w.free_stack[fs_top + q] = s.freelist[free_top - n + q];
+                fs_top += n; free_top -= n;
+                __syncwarp();
+            }
             const uint32_t from_fs = min(nsib, fs_top);                   // shared-memory stack first, then the slab list, then fresh
             const uint32_t from_gl = min(nsib - from_fs, free_top);
             if (mine) {
