@@ -1320,6 +1320,38 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         coln[k] = (1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
 
+    // removes entry `pos` of stripe `owner` (swap with its last entry), then the warp rescans that stripe; `left` = entries
+    // left in the stripe.  Stripes that fit the shared-memory part take the direct path.
+    auto remove_rescan = [&](int owner, uint32_t pos, uint32_t left) {
+        const bool in_smem = left < mqs;                                   // positions 0..left all in shared memory
+        if ((int)lane == owner) {
+            cnt--;
+            if (pos != cnt) {
+                if (in_smem) {
+                    const uint32_t o = lane * mqs;
+                    mq_hi[o + pos] = mq_hi[o + cnt]; mq_idx[o + pos] = mq_idx[o + cnt]; mq_len[o + pos] = mq_len[o + cnt]; mq_rec[o + pos] = mq_rec[o + cnt];
+                } else {
+                    *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt);
+                    *klen_at(owner, pos) = *klen_at(owner, cnt); *krec_at(owner, pos) = *krec_at(owner, cnt);
+                }
+            }
+        }
+        __syncwarp();
+        uint64_t nhi; uint32_t nidx, npos;
+        if (in_smem) {
+            uint64_t bhi = ~0ull; uint32_t bidx = 0xffffffffu, bpos = 0;
+            const uint32_t o = (uint32_t)owner * mqs;
+            for (uint32_t q = lane; q < left; q += 32) {
+                const uint64_t hi = mq_hi[o + q]; const uint32_t ix = mq_idx[o + q];
+                if (key_less(hi, ix, bhi, bidx)) { bhi = hi; bidx = ix; bpos = q; }
+            }
+            const MainKey mk = wmin96(bhi, bidx);
+            const int wl2 = __ffs(__ballot_sync(HP_FULL_MASK, bhi == mk.hi && bidx == mk.idx)) - 1;
+            nhi = mk.hi; nidx = mk.idx; npos = __shfl_sync(HP_FULL_MASK, bpos, wl2);
+        } else stripe_min(khi_at, kidx_at, owner, left, lane, nhi, nidx, npos);
+        if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
+        qmin = wmin96(c_hi, c_idx);
+    };
     auto eval_pool = [&]() {
         // counts and removes the pool entries popped so far (key < pool_max), restarts the epoch
         uint32_t base = 0;
@@ -1363,20 +1395,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 const uint32_t drec = *krec_at(owner, pos);
                 const uint32_t cnt_d = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
                 __syncwarp();
-                if ((int)lane == owner) {
-                    cnt--;
-                    if (pos != cnt) {
-                        *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt);
-                        *klen_at(owner, pos) = *klen_at(owner, cnt); *krec_at(owner, pos) = *krec_at(owner, cnt);
-                    }
-                }
-                __syncwarp();
-                {
-                    uint64_t nhi; uint32_t nidx, npos;
-                    stripe_min(khi_at, kidx_at, owner, cnt_d, lane, nhi, nidx, npos);
-                    if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
-                }
-                qmin = wmin96(c_hi, c_idx);
+                remove_rescan(owner, pos, cnt_d);
                 qsize--;
                 if (lane == 0) lc[lenf & 0x7fffffffu] -= 1u;                  // hap_tracker.remove_hap (:495); below the threshold
                 w.pops++;
@@ -1395,8 +1414,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint64_t hi = ((uint64_t)cur_total << 32) | cur_nh;
-                    *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = cur_idx; *klen_at(lane, cnt) = cur_len | (cur_ident ? 0x80000000u : 0u);
-                    *krec_at(lane, cnt) = cur_rec;
+                    const uint32_t lenf_c = cur_len | (cur_ident ? 0x80000000u : 0u);
+                    if (cnt < mqs) { const uint32_t o = lane * mqs + cnt; mq_hi[o] = hi; mq_idx[o] = cur_idx; mq_len[o] = lenf_c; mq_rec[o] = cur_rec; }
+                    else { *khi_at(lane, cnt) = hi; *kidx_at(lane, cnt) = cur_idx; *klen_at(lane, cnt) = lenf_c; *krec_at(lane, cnt) = cur_rec; }
                     if (key_less(hi, cur_idx, c_hi, c_idx)) { c_hi = hi; c_idx = cur_idx; c_pos = cnt; }
                     cnt++;
                 }
@@ -1432,20 +1452,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             }
             const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1;
             __syncwarp();
-            if ((int)lane == owner) {
-                cnt--;
-                if (pos != cnt) {
-                    *khi_at(owner, pos) = *khi_at(owner, cnt); *kidx_at(owner, pos) = *kidx_at(owner, cnt);
-                    *klen_at(owner, pos) = *klen_at(owner, cnt); *krec_at(owner, pos) = *krec_at(owner, cnt);
-                }
-            }
-            __syncwarp();
-            {
-                uint64_t nhi; uint32_t nidx, npos;
-                stripe_min(khi_at, kidx_at, owner, cnt_o, lane, nhi, nidx, npos);
-                if ((int)lane == owner) { c_hi = nhi; c_idx = nidx; c_pos = npos; }
-            }
-            qmin = wmin96(c_hi, c_idx);
+            remove_rescan(owner, pos, cnt_o);
             have_cur = true;
         }
         // ---- cur is the top of the live entries: every pool entry with a smaller key has been popped before it (:507-515) ----
