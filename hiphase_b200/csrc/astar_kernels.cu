@@ -592,6 +592,10 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     const uint32_t* col_lane = col + lane;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
     constexpr uint32_t kEmpty = 0xffff0000u;      // column record of an unused slot: no carry, quality 0
+    SubEntry* const my_stripe = w.sq + lane * w.capl_s;                       // this lane's stripe: shared part / spill part
+    SubEntry* const my_spill = w.sq_spill + lane * (w.capl - w.capl_s) - w.capl_s;
+    const uint32_t capl_s = w.capl_s;
+    auto my_ent = [&](uint32_t q) -> SubEntry* { return q < capl_s ? my_stripe + q : my_spill + q; };
 
     // queue state
     uint64_t ckey = ~0ull, qmin = ~0ull;
@@ -631,7 +635,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint64_t k = mk64(cur_total, cur_lo);
-                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, 0u);
+                    sub_store(my_ent(cnt), k, cur_h1, cur_h2, 0u);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -794,7 +798,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             if (__ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl) == 0) {
                 if (mine) {
                     const uint64_t k = mk64(mt, ml);
-                    sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, 0u, c);
+                    sub_store(my_ent(cnt), k, cur_h1, cur_h2, 0u, c);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
@@ -809,7 +813,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                         const uint32_t xt = __shfl_sync(HP_FULL_MASK, mt, src_lane), xl = __shfl_sync(HP_FULL_MASK, ml, src_lane);
                         if (lane == target) {
                             const uint64_t k = mk64(xt, xl);
-                            sub_store(w.ent(lane, cnt), k, cur_h1, cur_h2, 0u, cc);
+                            sub_store(my_ent(cnt), k, cur_h1, cur_h2, 0u, cc);
                             if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
