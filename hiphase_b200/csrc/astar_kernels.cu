@@ -359,7 +359,7 @@ struct WarpCtx {
     uint32_t lencnt_cap_s;
     // counters
     uint64_t evals, sum_lp, pops, cells;
-    long long ts_pop, ts_seat, ts_score, ts_rest;   // counting variant: sub-solver phase cycles of this warp
+    long long ts_pop, ts_seat, ts_score, ts_rest, ts_popa, ts_popb;   // counting variant: sub-solver phase cycles of this warp
     uint64_t ns_real, ns_planes, ns_exp;
     int status;
     // entry i of stripe `stripe`
@@ -641,6 +641,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 }
                 __syncwarp();
             }
+            if (kCount) w.ts_popa += clock64() - tq;          // push-back of cur
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
             const SubEntry* e = w.ent(owner, pos);
@@ -655,6 +656,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 }
             }
             __syncwarp();
+            if (kCount) w.ts_popb += clock64() - tq;          // + owner / entry load
             sub_remove_rescan(w, owner, pos, cnt, ckey, cpos);
             qmin = wmin64(ckey);
             if (kCount) { const long long t1 = clock64(); w.ts_pop += t1 - tq; tq = t1; }
@@ -2014,7 +2016,7 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
 #ifdef HP_DBG_SUB_SPLIT
                     // sub-solver phase split of warp 0 (its sub-solves are never speculative) instead of the main-loop split
                     d[8] = (uint64_t)w.ts_pop; d[9] = (uint64_t)w.ts_seat; d[10] = (uint64_t)w.ts_score; d[11] = (uint64_t)w.ts_rest;
-                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp;
+                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp; d[15] = (uint64_t)w.ts_popa; d[7] = (uint64_t)w.ts_popb;
 #endif
                 }
                 ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;
@@ -2047,7 +2049,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     w.hring = ts.hring;
     w.h_floor = 0;
     w.evals = w.sum_lp = w.pops = w.cells = 0;
-    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
+    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
 
     // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp
     uint8_t* my_slab = a.slabs + (uint64_t)blockIdx.x * a.slab_bytes;
@@ -2078,7 +2080,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
         const uint32_t blk = a.order[first + t];
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
-        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
+        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
         w.status = m.status;
         if (threadIdx.x == 0) ts.final_status = m.status;
 
