@@ -22,8 +22,7 @@ print("kernel ms %.3f  team %d  variants committed per round: mean %.2f" % (ctx.
 print("pre-pass: cycles/pop mean %.0f  cycles/block mean %.3g max %.3g" % ((d[:, 0] / d[:, 2]).mean(), d[:, 0].mean(), d[:, 0].max()))
 print("main    : cycles/pop mean %.0f  cycles/block mean %.3g max %.3g" % ((d[:, 1] / np.maximum(d[:, 3], 1)).mean(), d[:, 1].mean(), d[:, 1].max()))
 tot = d[:, 0] + d[:, 1]
-print("sum pre-pass %.3g  sum main %.3g  slowest block %.3g cycles; warp 0 waits at the round barriers for %.1f%% of the pre-pass (slowest 5 blocks: %s)"
-      % (d[:, 0].sum(), d[:, 1].sum(), tot.max(), 100 * d[:, 6].sum() / d[:, 0].sum(), ", ".join("%.0f%%" % (100 * d[k, 6] / d[k, 0]) for k in np.argsort(tot)[-5:])))
+print("sum pre-pass %.3g  sum main %.3g  slowest block %.3g cycles" % (d[:, 0].sum(), d[:, 1].sum(), tot.max()))
 mp = d[:, 8:11].sum(0)
 print("main split (all blocks): real-pop %.3g  expand %.3g  rest %.3g cycles | real pops %d  pruned %d  plane-rescored expansions %d (%.3g cycles)"
       % (mp[0], mp[1], mp[2], d[:, 13].sum(), d[:, 14].sum(), d[:, 11].sum(), d[:, 12].sum()))
