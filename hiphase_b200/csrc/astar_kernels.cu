@@ -337,6 +337,13 @@ constexpr uint32_t kSweepMinDead = HP_SWEEP_MIN_DEAD;     // dead entries are sw
 #define HP_SUB_SERIAL_SCAN 4
 #endif
 constexpr uint32_t kSubSerialScan = HP_SUB_SERIAL_SCAN;   // stripes up to this long are rescanned by their owner lane alone
+// Per-warp global region behind the shared-memory part of the sub-solver queue: the spill part of the AoS stripes (generic
+// path) or, for the fast path, one 16-byte payload per node index (node indices reach 1 + 4*max_visits <= 43*capl + 16).
+__host__ __device__ inline uint64_t sub_spill_bytes(uint32_t capl, uint32_t capl_s) {
+    const uint64_t aos = (uint64_t)32 * (capl - capl_s) * 32;
+    const uint64_t pay = (uint64_t)16 * (43ull * capl + 16);
+    return ((aos > pay ? aos : pay) + 255) & ~255ull;
+}
 constexpr uint32_t kFreeStack = 192;   // free main-queue record slots kept in shared memory
 
 struct WarpCtx {
@@ -360,7 +367,7 @@ struct WarpCtx {
     // counters
     uint64_t evals, sum_lp, pops, cells;
     long long ts_pop, ts_seat, ts_score, ts_rest, ts_popa, ts_popb;   // counting variant: sub-solver phase cycles of this warp
-    uint64_t ns_real, ns_planes, ns_exp;
+    uint64_t ns_real, ns_planes, ns_exp, ns_spill, ns_cnt;
     int status;
     // entry i of stripe `stripe`
     __device__ __forceinline__ SubEntry* ent(uint32_t stripe, uint32_t i) const {
@@ -382,6 +389,9 @@ __device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1
 __device__ __forceinline__ void sub_remove_rescan(const WarpCtx& w, int owner, uint32_t pos, uint32_t& cnt, uint64_t& ckey, uint32_t& cpos) {
     const uint32_t lane = w.lane;
     const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1u;
+#ifdef HP_DBG_SUB_SPLIT
+    const_cast<WarpCtx&>(w).ns_cnt += cnt_o; if (cnt_o >= w.capl_s) const_cast<WarpCtx&>(w).ns_spill++;
+#endif
     if ((int)lane == owner) {
         cnt--;
         if (pos != cnt) {
@@ -572,6 +582,8 @@ __device__ uint2 sub_solve_generic(const AstarArgs& a, const BlkMeta& m, WarpCtx
     return make_uint2(max_cost, next_expected - 1);
 }
 
+extern __shared__ __align__(16) uint8_t hp_dyn_smem[];     // the CTA's dynamic shared memory (true shared-space addressing)
+
 // astar_subsolver, register-resident fast path for blocks with at most 32*K reads per column.
 //
 // Critical path per pop (the dive): select (s1,s2) of the chosen child -> A0..B1 -> four mins -> deltas against
@@ -592,10 +604,17 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     const uint32_t* col_lane = col + lane;
     const ReadMeta* rmeta = a.rmeta + m.read_base;
     constexpr uint32_t kEmpty = 0xffff0000u;      // column record of an unused slot: no carry, quality 0
-    SubEntry* const my_stripe = w.sq + lane * w.capl_s;                       // this lane's stripe: shared part / spill part
-    SubEntry* const my_spill = w.sq_spill + lane * (w.capl - w.capl_s) - w.capl_s;
-    const uint32_t capl_s = w.capl_s;
-    auto my_ent = [&](uint32_t q) -> SubEntry* { return q < capl_s ? my_stripe + q : my_spill + q; };
+    // queue layout of this path: keys only in shared memory (KS per stripe, all stripes fit), one 16-byte payload per node
+    // index in the warp's global region: {h1, h2 | tag << 56}.  tag 0xff: the node's own haplotypes; tag < 4: the PARENT's
+    // haplotypes and the node's candidate slot.  Entries never move their payload; the payload load of a pop is issued
+    // as soon as the popped key is known and overlaps the stripe bookkeeping.
+    const uint32_t KS = w.capl_s * 4u;                                      // 32-byte AoS slots -> 8-byte keys
+    uint64_t* const keys = reinterpret_cast<uint64_t*>(hp_dyn_smem) + (size_t)(threadIdx.x >> 5) * 32u * KS;
+    uint64_t* const my_keys = keys + lane * KS;
+    uint4* const pay = reinterpret_cast<uint4*>(w.sq_spill);
+    auto pay_store = [&](uint32_t idx, uint64_t h1, uint64_t h2, uint32_t tag) {
+        pay[idx] = make_uint4((uint32_t)h1, (uint32_t)(h1 >> 32), (uint32_t)h2, (uint32_t)(h2 >> 32) | (tag << 24));
+    };
 
     // queue state
     uint64_t ckey = ~0ull, qmin = ~0ull;
@@ -629,36 +648,47 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             if (kCount) w.ns_real++;
             // ---- the dive broke: cur goes back to the queue, then a real pop of the entry whose key is qmin ----
             {
-                const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
+                const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < KS);
                 if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
                 uint32_t target = rr & 31u; rr++;
                 if (!((room >> target) & 1u)) target = __ffs(room) - 1;
                 if (lane == target) {
                     const uint64_t k = mk64(cur_total, cur_lo);
-                    sub_store(my_ent(cnt), k, cur_h1, cur_h2, 0u);
+                    my_keys[cnt] = k;
+                    pay_store((cur_lo >> 6) & 0xfffffu, cur_h1, cur_h2, 0xffu);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
                 __syncwarp();
             }
             if (kCount) w.ts_popa += clock64() - tq;          // push-back of cur
+            cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
+            const uint4 pl = pay[(cur_lo >> 6) & 0xfffffu];               // in flight while the stripe is fixed up
             const int owner = __ffs(__ballot_sync(HP_FULL_MASK, ckey == qmin)) - 1;
             const uint32_t pos = __shfl_sync(HP_FULL_MASK, cpos, owner);
-            const SubEntry* e = w.ent(owner, pos);
-            cur_total = (uint32_t)(qmin >> 32); cur_lo = (uint32_t)qmin;
-            cur_h1 = e->h1; cur_h2 = e->h2;
+            if (kCount) w.ts_popb += clock64() - tq;          // + owner
+            {   // remove (swap with the stripe's last key) and rescan that stripe
+                const uint32_t left = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1u;
+                uint64_t* const ok = keys + (uint32_t)owner * KS;
+                if ((int)lane == owner) { cnt--; if (pos != cnt) ok[pos] = ok[cnt]; }
+                __syncwarp();
+                uint64_t bk = ~0ull; uint32_t bp = 0;
+                for (uint32_t q = lane; q < left; q += 32) { const uint64_t k = ok[q]; if (k < bk) { bk = k; bp = q; } }
+                const uint64_t mk = wmin64(bk);
+                const int wl = __ffs(__ballot_sync(HP_FULL_MASK, bk == mk)) - 1;
+                const uint32_t mp = __shfl_sync(HP_FULL_MASK, bp, wl);
+                if ((int)lane == owner) { ckey = mk; cpos = mp; }
+            }
+            qmin = wmin64(ckey);
+            cur_h1 = ((uint64_t)pl.y << 32) | pl.x; cur_h2 = ((uint64_t)(pl.w & 0x00ffffffu) << 32) | pl.z;
             {
-                const uint32_t tag = e->tag;
+                const uint32_t tag = pl.w >> 24;
                 if (tag < 4u) {                                          // parent's haplotypes + this node's candidate slot
                     const uint32_t lb = (cur_lo & 63u) - 1u;
                     cur_h1 |= (uint64_t)(tag & 1u) << lb;
                     cur_h2 |= (uint64_t)((0x9u >> tag) & 1u) << lb;
                 }
             }
-            __syncwarp();
-            if (kCount) w.ts_popb += clock64() - tq;          // + owner / entry load
-            sub_remove_rescan(w, owner, pos, cnt, ckey, cpos);
-            qmin = wmin64(ckey);
             if (kCount) { const long long t1 = clock64(); w.ts_pop += t1 - tq; tq = t1; }
             // re-seat the column state on this node's position
             const uint32_t Lp = cur_lo & 63u;
@@ -797,17 +827,18 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t rsel = (c & 2u) ? r1 : r0;
             const uint32_t mt = tb + ((c & 1u) ? (rsel >> 16) : (rsel & 0xffffu));
             const uint32_t ml = ((c & 2u) ? lo2 : lo0) + ((c & 1u) << 6);
-            if (__ballot_sync(HP_FULL_MASK, mine && cnt >= w.capl) == 0) {
+            if (__ballot_sync(HP_FULL_MASK, mine && cnt >= KS) == 0) {
                 if (mine) {
                     const uint64_t k = mk64(mt, ml);
-                    sub_store(my_ent(cnt), k, cur_h1, cur_h2, 0u, c);
+                    my_keys[cnt] = k;
+                    pay_store((ml >> 6) & 0xfffffu, cur_h1, cur_h2, c);
                     if (k < ckey) { ckey = k; cpos = cnt; }
                     cnt++;
                 }
             } else {                                                     // rare: a target stripe is full
                 for (uint32_t cc = 0; cc < 4; cc++) {
                     if (((present >> cc) & 1u) && cc != best) {
-                        const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < w.capl);
+                        const uint32_t room = __ballot_sync(HP_FULL_MASK, cnt < KS);
                         if (room == 0) { w.status = HP_BLOCK_ASSERT; break; }
                         const uint32_t src_lane = (rr + cc) & 31u;
                         uint32_t target = src_lane;
@@ -815,7 +846,8 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                         const uint32_t xt = __shfl_sync(HP_FULL_MASK, mt, src_lane), xl = __shfl_sync(HP_FULL_MASK, ml, src_lane);
                         if (lane == target) {
                             const uint64_t k = mk64(xt, xl);
-                            sub_store(my_ent(cnt), k, cur_h1, cur_h2, 0u, cc);
+                            my_keys[cnt] = k;
+                            pay_store((xl >> 6) & 0xfffffu, cur_h1, cur_h2, cc);
                             if (k < ckey) { ckey = k; cpos = cnt; }
                             cnt++;
                         }
@@ -857,7 +889,12 @@ template <int K, bool kCount>
 __device__ __forceinline__ uint2 sub_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, uint32_t v, uint32_t clip,
                                            uint64_t badwin, uint32_t blk) {
     if constexpr (K == 0) return sub_solve_generic<0, kCount>(a, m, w, v, clip, badwin, blk);
-    else return sub_solve_fast<K, kCount>(a, m, w, v, clip, badwin, blk);
+    else {
+        // the fast path keeps every stripe's keys in shared memory (4 keys per AoS slot): larger queues (non-default
+        // min_queue_size / queue_increment) take the generic path
+        if (w.capl > 4u * w.capl_s) return sub_solve_generic<K, kCount>(a, m, w, v, clip, badwin, blk);
+        return sub_solve_fast<K, kCount>(a, m, w, v, clip, badwin, blk);
+    }
 }
 
 // ---- main-queue slab (global memory, private to one warp) -----------------------------------------------------
@@ -2016,7 +2053,7 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
 #ifdef HP_DBG_SUB_SPLIT
                     // sub-solver phase split of warp 0 (its sub-solves are never speculative) instead of the main-loop split
                     d[8] = (uint64_t)w.ts_pop; d[9] = (uint64_t)w.ts_seat; d[10] = (uint64_t)w.ts_score; d[11] = (uint64_t)w.ts_rest;
-                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp; d[15] = (uint64_t)w.ts_popa; d[7] = (uint64_t)w.ts_popb;
+                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp; d[15] = (uint64_t)w.ts_popa; d[7] = (uint64_t)w.ts_popb; d[5] = w.ns_spill; d[6] = w.ns_cnt;
 #endif
                 }
                 ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;
@@ -2049,12 +2086,12 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     w.hring = ts.hring;
     w.h_floor = 0;
     w.evals = w.sum_lp = w.pops = w.cells = 0;
-    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
+    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = w.ns_spill = w.ns_cnt = 0;
 
     // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp
     uint8_t* my_slab = a.slabs + (uint64_t)blockIdx.x * a.slab_bytes;
     const Slab slab = carve_slab(my_slab, a.qcap, a.hap_words);
-    const uint64_t spill_bytes = (uint64_t)32 * (w.capl - w.capl_s) * sizeof(SubEntry);
+    const uint64_t spill_bytes = sub_spill_bytes(w.capl, w.capl_s);
     w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)(kMaxTeam - warp) * spill_bytes);
     // main-queue keys reuse the whole team's sub-queue shared memory (12 B per key)
     // ... minus a 4 KB tail for the tracker's length counts
@@ -2080,7 +2117,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
         const uint32_t blk = a.order[first + t];
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
-        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
+        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = w.ns_spill = w.ns_cnt = 0;
         w.status = m.status;
         if (threadIdx.x == 0) ts.final_status = m.status;
 
@@ -2120,7 +2157,7 @@ int astar_max_team() { return kMaxTeam; }
 int astar_warps_per_sm() { return 16; }
 uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl) {
     const uint32_t capl_s = std::min<uint32_t>(sub_capl, kSubCaplShared);
-    const uint64_t spill = (uint64_t)kMaxTeam * 32 * (sub_capl - capl_s) * sizeof(SubEntry);
+    const uint64_t spill = (uint64_t)kMaxTeam * sub_spill_bytes(sub_capl, capl_s);
     return ((slab_bytes_for(qcap, hap_words) + spill + 255) & ~255ull);
 }
 
