@@ -1912,7 +1912,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
 // known H entry as H[v_hi+1] and assuming every earlier sub-solve of the round solves its full clip.  After a CTA
 // barrier the results are verified in chain order and the longest valid prefix is committed (warp 0 never
 // speculates, so every round commits at least one variant).  Results are exactly those of the serial chain.
-constexpr int kMaxTeam = 4;
+#ifndef HP_MAX_TEAM
+#define HP_MAX_TEAM 4
+#endif
+constexpr int kMaxTeam = HP_MAX_TEAM;
 #ifndef HP_SPEC_FAIL_ROUNDS
 #define HP_SPEC_FAIL_ROUNDS 6
 #endif

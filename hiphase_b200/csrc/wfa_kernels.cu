@@ -152,6 +152,16 @@ __device__ __forceinline__ const uint8_t* node_seq(const WfaArgs& a, const WfaNo
     return base + n.seq_off;
 }
 
+// 64 bits starting at an arbitrary byte address (little endian), from one or two aligned 64-bit loads
+__device__ __forceinline__ uint64_t ld64_unaligned(const uint8_t* p) {
+    const uintptr_t u = (uintptr_t)p;
+    const uint64_t* q = (const uint64_t*)(u & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(u & 7u) * 8u;
+    const uint64_t lo = __ldg(q);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (__ldg(q + 1) << (64u - sh));
+}
+
 __device__ __forceinline__ uint64_t wfa_key(uint32_t node, int32_t diag) { return ((uint64_t)node << 32) | (uint32_t)diag; }
 __device__ __forceinline__ uint32_t wfa_hash(uint64_t k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 29;
@@ -174,10 +184,20 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
         const uint8_t* seq = node_seq(*c.a, nd);
         uint32_t off = offset;
         uint32_t pos = (uint32_t)(diag + (int32_t)off);
+        // eight bases per step (unaligned 64-bit windows assembled from aligned loads; every byte pool is followed by
+        // at least 16 readable bytes of staging slack); n_cmp counts the byte compares of the reference: the matches plus
+        // the mismatch that stops the run
         while (off < nd.len && pos < c.read_len) {
-            c.n_cmp++;
-            if (__ldg(seq + off) != __ldg(c.read + pos)) break;
-            off++; pos++;
+            const uint32_t rem = min(nd.len - off, c.read_len - pos);
+            uint64_t x = ld64_unaligned(seq + off) ^ ld64_unaligned(c.read + pos);
+            if (rem < 8u) x &= (1ull << (8u * rem)) - 1ull;
+            if (x) {
+                const uint32_t adv = (uint32_t)(__ffsll((long long)x) - 1) >> 3;
+                off += adv; pos += adv; c.n_cmp += adv + 1;
+                break;
+            }
+            const uint32_t adv = min(rem, 8u);
+            off += adv; pos += adv; c.n_cmp += adv;
         }
         // ---- find or insert the slot ----
         const uint64_t key = wfa_key(node, diag);
