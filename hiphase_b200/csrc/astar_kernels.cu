@@ -1958,7 +1958,7 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
     uint32_t clip0 = 1;
     int status = HP_BLOCK_OK;
     uint32_t n_rounds = 0;
-    long long t_wait = 0;
+    long long t_wait = 0, t_subs = 0;
     // Speculation pays only where H[v] == H[v+1] is common.  In noisy stretches every guess fails and the guessing warps
     // only slow warp 0 down (shared issue slots, the round lasts as long as its slowest sub-solve): after kSpecFailRounds
     // rounds in a row that committed a single variant the team runs warp 0 alone for kSpecPauseRounds rounds, then tries
@@ -1972,7 +1972,9 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
         if (v >= 0 && warp < eff_team) {
             w.h_floor = (uint32_t)v_hi + 1;
             w.status = HP_BLOCK_OK;
+            const long long ts0 = kCount ? clock64() : 0;
             const uint2 r = sub_solve<K, kCount>(a, m, w, (uint32_t)v, clip_guess, bad_window(ign, (uint32_t)v, N, w.lane), blk);
+            if (kCount) t_subs += clock64() - ts0;
             if (w.lane == 0) { ts.est[warp] = r.x; ts.solved[warp] = r.y; ts.status[warp] = w.status; }
         }
         const long long tw0 = kCount ? clock64() : 0;
@@ -2056,7 +2058,7 @@ __device__ void solve_block(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, co
 #ifdef HP_DBG_SUB_SPLIT
                     // sub-solver phase split of warp 0 (its sub-solves are never speculative) instead of the main-loop split
                     d[8] = (uint64_t)w.ts_pop; d[9] = (uint64_t)w.ts_seat; d[10] = (uint64_t)w.ts_score; d[11] = (uint64_t)w.ts_rest;
-                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp; d[15] = (uint64_t)w.ts_popa; d[7] = (uint64_t)w.ts_popb; d[5] = w.ns_spill; d[6] = w.ns_cnt;
+                    d[12] = w.ns_real; d[13] = w.ns_planes; d[14] = w.ns_exp; d[15] = (uint64_t)w.ts_popa; d[7] = (uint64_t)w.ts_popb; d[5] = (uint64_t)t_subs; d[6] = (uint64_t)t_wait;
 #endif
                 }
                 ts.ctr[0] += w.evals; ts.ctr[1] += tot; ts.ctr[2] += w.sum_lp; ts.ctr[3] += w.pops;

@@ -21,6 +21,6 @@ print("kernel %.3f ms; warp-0 sub-solver cycles, all blocks: pop %.3g  re-seat %
       % (ctx.last_kernel_ms(), d[:, 8].sum(), d[:, 9].sum(), d[:, 10].sum(), d[:, 11].sum(), d[:, 14].sum(), d[:, 12].sum(), d[:, 13].sum()))
 for k in np.argsort(tot)[-5:]:
     e, r = max(d[k, 14], 1), max(d[k, 12], 1)
-    print("block %5d N %4d pre-pass %.3g cycles, rounds %d: warp 0 expansions %d (real pops %d, plane-rescored %d): pop %.0f/real  re-seat %.0f/real  score %.0f/exp  rest %.0f/exp  | sum %.3g | pop = push-back %.0f + owner/entry %.0f + remove/rescan/min %.0f | stripe length at pop: mean %.1f, %.0f%% of pops touch the spill part"
+    print("block %5d N %4d pre-pass %.3g cycles, rounds %d: warp 0 expansions %d (real pops %d, plane-rescored %d): pop %.0f/real  re-seat %.0f/real  score %.0f/exp  rest %.0f/exp  | sum %.3g | pop = push-back %.0f + owner/entry %.0f + remove/rescan/min %.0f | warp 0: in sub-solves %.3g, waiting at the round barrier %.3g cycles"
           % (k, nvar[k], d[k, 0], d[k, 4], d[k, 14], d[k, 12], d[k, 13], d[k, 8] / r, d[k, 9] / r, d[k, 10] / e, d[k, 11] / e, d[k, 8:12].sum(),
-             d[k, 15] / r, (d[k, 7] - d[k, 15]) / r, (d[k, 8] - d[k, 7]) / r, d[k, 6] / r, 100 * d[k, 5] / r))
+             d[k, 15] / r, (d[k, 7] - d[k, 15]) / r, (d[k, 8] - d[k, 7]) / r, d[k, 5], d[k, 6]))
