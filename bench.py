@@ -264,7 +264,9 @@ def main():
         traffic = None
         try:
             tb = 0.0
-            for ln in open(os.path.join(ROOT, "profiles", "r1_ncu_astar_solve_kernel.txt")):
+            import glob
+            # the latest committed capture of this kernel (profiles/r1*_ncu_astar_solve_kernel.txt sort by name)
+            for ln in open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r1*_ncu_astar_solve_kernel.txt")))[-1]):
                 f = ln.split()
                 if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     tb += float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
