@@ -96,3 +96,33 @@ def local_realignment(read: AlignedRead, variant_calls, ctx=None):
         raise RuntimeError("local realignment failed with job status %d" % out.status[0])
     vt = [int(v.get_type()) for v in variant_calls]
     return out.alleles.tolist(), out.quals.tolist(), read_stats(out.alleles, out.match_class, vt)
+
+
+def plan_global_realignment(read: AlignedRead, variant_positions, hom_positions):
+    """The CIGAR-projection half of global_realignment (read_parsing.rs:672-742): what one job of hp_wfa_align_batch needs.
+
+    variant_positions / hom_positions: Variant::position() of the block's het / hom calls, ascending.
+    Returns None when the mapping overlaps no het variant (the short-circuit at :703-712), else a dict with
+      ref_start, ref_end        min_position, max_position + 1 of the aligned pairs           (:677-689, :773-774)
+      het_lo, het_hi            first_overlap, last_overlap (indices into variant_positions)  (:692-701)
+      hom_lo, hom_hi            first_hom_overlap, last_hom_overlap                           (:718-729)
+      read_start, read_end      slice of the read that is aligned: read[read_start:read_end]  (:737-741)
+    """
+    segs = list(read.segments)
+    if not segs:
+        raise AssertionError("max_position >= min_position")              # the reference asserts at :686
+    min_position = min(s[0] for s in segs)
+    max_position = max(s[0] + s[2] - 1 for s in segs)
+
+    def overlap(positions):
+        idx = [i for i, p in enumerate(positions) if min_position <= p <= max_position]
+        return (idx[0], idx[-1] + 1) if idx else None
+
+    het = overlap(variant_positions)
+    if het is None:
+        return None
+    hom = overlap(hom_positions) or (0, 0)
+    first = min(segs, key=lambda s: s[0])
+    last = max(segs, key=lambda s: s[0] + s[2] - 1)
+    return dict(ref_start=min_position, ref_end=max_position + 1, het_lo=het[0], het_hi=het[1], hom_lo=hom[0], hom_hi=hom[1],
+                read_start=first[1], read_end=last[1] + last[2])

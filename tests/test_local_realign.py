@@ -250,3 +250,14 @@ def test_gpu_local_realignment_mirror():
     assert stats.allele0_matches[0] == 1 and stats.allele1_matches[5] == 1 and stats.num_alleles == 2 and stats.local_aligned == 1
     with pytest.raises(RuntimeError):
         local_realignment(read, [Variant(0, 6, 10, 1, b"G", b"GG")])
+
+
+def test_plan_global_realignment_window():
+    """read_parsing.rs:672-742: window, overlap index ranges and read slice from the aligned segments."""
+    from hiphase_b200.read_parsing import AlignedRead, plan_global_realignment
+    read = AlignedRead.from_cigar(100, [("S", 5), ("M", 20), ("D", 10), ("M", 30), ("I", 4), ("M", 6), ("S", 3)], b"A" * 68, [30] * 68)
+    assert read.segments == [(100, 5, 20), (130, 25, 30), (160, 59, 6)]
+    plan = plan_global_realignment(read, [50, 100, 125, 165, 166, 400], [10, 120, 165, 170])
+    assert plan == dict(ref_start=100, ref_end=166, het_lo=1, het_hi=4, hom_lo=1, hom_hi=3, read_start=5, read_end=65)
+    assert plan_global_realignment(read, [50, 99, 166], [120]) is None          # no het overlap: the job is skipped (:703-712)
+    assert plan_global_realignment(read, [110], [])["hom_lo"] == 0             # first_hom_overlap.unwrap_or(0)
