@@ -367,7 +367,7 @@ struct WarpCtx {
     // counters
     uint64_t evals, sum_lp, pops, cells;
     long long ts_pop, ts_seat, ts_score, ts_rest, ts_popa, ts_popb;   // counting variant: sub-solver phase cycles of this warp
-    uint64_t ns_real, ns_planes, ns_exp, ns_spill, ns_cnt;
+    uint64_t ns_real, ns_planes, ns_exp;
     int status;
     // entry i of stripe `stripe`
     __device__ __forceinline__ SubEntry* ent(uint32_t stripe, uint32_t i) const {
@@ -389,9 +389,6 @@ __device__ __forceinline__ void sub_store(SubEntry* e, uint64_t key, uint64_t h1
 __device__ __forceinline__ void sub_remove_rescan(const WarpCtx& w, int owner, uint32_t pos, uint32_t& cnt, uint64_t& ckey, uint32_t& cpos) {
     const uint32_t lane = w.lane;
     const uint32_t cnt_o = __shfl_sync(HP_FULL_MASK, cnt, owner) - 1u;
-#ifdef HP_DBG_SUB_SPLIT
-    const_cast<WarpCtx&>(w).ns_cnt += cnt_o; if (cnt_o >= w.capl_s) const_cast<WarpCtx&>(w).ns_spill++;
-#endif
     if ((int)lane == owner) {
         cnt--;
         if (pos != cnt) {
@@ -2091,7 +2088,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
     w.hring = ts.hring;
     w.h_floor = 0;
     w.evals = w.sum_lp = w.pops = w.cells = 0;
-    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = w.ns_spill = w.ns_cnt = 0;
+    w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
 
     // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp
     uint8_t* my_slab = a.slabs + (uint64_t)blockIdx.x * a.slab_bytes;
@@ -2122,7 +2119,7 @@ __global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kern
         const uint32_t blk = a.order[first + t];
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
-        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = w.ns_spill = w.ns_cnt = 0;
+        w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
         w.status = m.status;
         if (threadIdx.x == 0) ts.final_status = m.status;
 
