@@ -1913,6 +1913,9 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
 #define HP_MAX_TEAM 4
 #endif
 constexpr int kMaxTeam = HP_MAX_TEAM;
+#ifndef HP_CTAS_PER_SM
+#define HP_CTAS_PER_SM (16 / HP_MAX_TEAM)
+#endif
 #ifndef HP_SPEC_FAIL_ROUNDS
 #define HP_SPEC_FAIL_ROUNDS 6
 #endif
@@ -2073,7 +2076,7 @@ constexpr int kSubCaplShared = HP_SUB_CAPL_S;    // sub-solver queue entries per
 // One kernel per score-vector class K (1: <= 32 reads per column, 2: <= 64, 0: any) keeps the register footprint of the
 // common class small.  Class c owns order[class_start[c] .. +class_count[c]) and ticket[c].
 template <int K, bool kCount>
-__global__ void __launch_bounds__(kMaxTeam * 32, 16 / kMaxTeam) astar_solve_kernel(AstarArgs a) {
+__global__ void __launch_bounds__(kMaxTeam * 32, HP_CTAS_PER_SM) astar_solve_kernel(AstarArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ TeamShared ts;
     constexpr int cls = (K == 1) ? 0 : (K == 2 ? 1 : 2);
@@ -2156,7 +2159,7 @@ size_t astar_smem_bytes(uint32_t sub_capl, int team) {
     return (size_t)team * capl_s * 32 * sizeof(SubEntry);
 }
 int astar_max_team() { return kMaxTeam; }
-int astar_warps_per_sm() { return 16; }
+int astar_warps_per_sm() { return HP_CTAS_PER_SM * kMaxTeam; }
 uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl) {
     const uint32_t capl_s = std::min<uint32_t>(sub_capl, kSubCaplShared);
     const uint64_t spill = (uint64_t)kMaxTeam * sub_spill_bytes(sub_capl, capl_s);
