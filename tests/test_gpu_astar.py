@@ -30,9 +30,12 @@ def assert_parity(batch, out, ref):
 
 def run_both(ctx, batch, params=None):
     c = ctx if params is None else lib.Context(params, device=0)
-    out = c.astar_solve_batch(batch, want_heuristic=True, want_counters=True)
+    out = c.astar_solve_batch(batch, want_heuristic=True, want_counters=True)      # counting kernel variant
     ref = O.astar_solve(batch, params, threads=8)
     assert_parity(batch, out, ref)
+    prod = c.astar_solve_batch(batch, want_heuristic=True)                          # production kernel variant
+    assert np.array_equal(prod.status, out.status) and np.array_equal(prod.h1, ref.h1) and np.array_equal(prod.h2, ref.h2)
+    assert np.array_equal(prod.stats, ref.stats) and np.array_equal(prod.heuristic, ref.heuristic)
     if params is not None:
         c.close()
     return out, ref
@@ -93,6 +96,16 @@ def test_pruning_and_full_prune(ctx):
     batch = A.BlockBatch.from_blocks(_rand_blocks(23, 40, 20, 60, p_err=0.3))
     out, ref = run_both(ctx, batch, params)
     assert (ref.stats["pruned_solutions"] > 0).any()
+
+
+@pytest.mark.parametrize("mq,inc", [(40, 1), (60, 2), (100, 1), (150, 3)])
+def test_dead_pool_with_full_prunes(ctx, mq, inc):
+    """Queue parameters for which dead entries pile up (swept into the lazily counted pool) AND the queue outgrows
+    10 x min_queue_size, so the full-prune re-keying (astar_phaser.rs:570-582) meets a non-empty pool."""
+    params = A.hp_params(mq, inc, 500, 500)
+    batch = A.BlockBatch.from_blocks(_rand_blocks(40 + mq, 10, 120, 320, smax_hi=30, p_err=0.25))
+    out, ref = run_both(ctx, batch, params)
+    assert (ref.stats["pruned_solutions"] > 300).any()
 
 
 def test_noisy_default_params(ctx):
