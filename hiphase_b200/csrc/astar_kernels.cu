@@ -1437,7 +1437,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 __syncwarp();
                 remove_rescan(owner, pos, cnt_d);
                 qsize--;
-                if (lane == 0) lc[lenf & 0x7fffffffu] -= 1u;                  // hap_tracker.remove_hap (:495); below the threshold
+                if (lane == 0) atomicAdd(lc + (lenf & 0x7fffffffu), 0xffffffffu);   // hap_tracker.remove_hap (:495); below the threshold
                 w.pops++;
                 if (num_pruned == 0) curr_thresh = a.min_queue_size;        // :508-510
                 num_pruned++;
@@ -1505,7 +1505,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         const uint32_t L = cur_len;
         if (L >= N) break;                                                // :492
         qsize--;
-        if (lane == 0) lc[L] -= 1u;                                       // hap_tracker.remove_hap (:495)
+        if (lane == 0) atomicAdd(lc + L, 0xffffffffu);                    // hap_tracker.remove_hap (:495); no result needed
         if (L >= trk_thresh) trk_total--;
         w.pops++;
         if (L == next_expected) {                                         // :497-504
@@ -1763,7 +1763,7 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             }
         }
         next_idx += nchild; qsize += nchild;
-        if (lane == 0) lc[L + 1] += nchild;                               // tracker.add_hap(L+1) x nchild (:531, :558)
+        if (lane == 0) atomicAdd(lc + L + 1, nchild);                     // tracker.add_hap(L+1) x nchild (:531, :558)
         if (L + 1 >= trk_thresh) trk_total += nchild;
         // ---- the best child is the new cur (record inherited in place) ----
         cur_total = tmin;
