@@ -107,3 +107,17 @@ def test_runner_matches_api(tmp_path):
     assert haps.shape[0] == batch.n_vars
     assert np.array_equal(haps[:, 2], pos) and np.array_equal(haps[:, 3], ref.h1) and np.array_equal(haps[:, 4], ref.h2)
     assert np.array_equal(haps[:, 5].astype(np.uint64), post.block_tags)
+
+
+def test_runner_fails_loudly_without_gpu(tmp_path):
+    """The batch runner has no CPU solver inside: without a CUDA device it reports the library's error and exits non-zero."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib.build()
+    batch = synth.config_c2(n_blocks=2, n_var=30, n_reads=12)
+    path = str(tmp_path / "blocks.hpb")
+    lib.pack_write_blocks(path, batch, _positions(batch))
+    r = subprocess.run([lib.RUNNER_PATH, path, str(tmp_path / "run"), "0"], capture_output=True, text=True)
+    assert r.returncode != 0 and "error" in r.stderr.lower()
+    assert not os.path.exists(str(tmp_path / "run.stats.tsv"))
