@@ -353,3 +353,81 @@ class LocalOut:
     def as_struct(self):
         return hp_local_out(ptr(self.alleles, u8p), ptr(self.quals, u8p), ptr(self.match_class, u8p),
                             ptr(self.edit_distance, u32p), ptr(self.status, i32p))
+
+
+# ---- matrix assembly (read_segments.rs:40-121; read_parsing.rs:612-629) -------------------------------------------
+HP_GROUP_DROPPED, HP_GROUP_PHASABLE, HP_GROUP_KEPT, HP_GROUP_ASSERT = 0, 1, 2, 3
+
+
+class hp_rows_batch(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint32), ("var_off", u64p), ("group_off", u64p), ("group_row_off", u64p), ("row_start", u32p),
+                ("row_cell_off", u64p), ("alleles", u8p), ("quals", u8p), ("min_matched_alleles", C.c_uint32)]
+
+
+class hp_assembled(C.Structure):
+    _fields_ = [("read_off", u64p), ("read_start", u32p), ("read_end", u32p), ("cell_off", u64p), ("alleles", u8p), ("quals", u8p),
+                ("cell_capacity", C.c_uint64), ("group_class", u8p), ("group_num_set", u32p), ("n_reads", C.c_uint64),
+                ("n_cells", C.c_uint64)]
+
+
+class RowsBatch:
+    """numpy side of hp_rows_batch.  blocks: list of dict(n_var, groups=[[(row_start, alleles, quals), ...], ...])."""
+
+    def __init__(self, blocks, min_matched_alleles=2):
+        var_off, group_off, group_row_off, row_start, row_cell_off, al, ql = [0], [0], [0], [], [0], [], []
+        for b in blocks:
+            var_off.append(var_off[-1] + int(b["n_var"]))
+            for grp in b["groups"]:
+                for (s, a, q) in grp:
+                    a = np.asarray(a, np.uint8); q = np.asarray(q, np.uint8)
+                    assert len(a) == len(q)
+                    row_start.append(int(s)); al.append(a); ql.append(q)
+                    row_cell_off.append(row_cell_off[-1] + len(a))
+                group_row_off.append(len(row_start))
+            group_off.append(len(group_row_off) - 1)
+        self.n_blocks = len(blocks)
+        self.var_off = _np(var_off, np.uint64); self.group_off = _np(group_off, np.uint64)
+        self.group_row_off = _np(group_row_off, np.uint64); self.row_start = _np(row_start, np.uint32)
+        self.row_cell_off = _np(row_cell_off, np.uint64)
+        self.alleles = _np(np.concatenate(al) if al else np.zeros(0, np.uint8), np.uint8)
+        self.quals = _np(np.concatenate(ql) if ql else np.zeros(0, np.uint8), np.uint8)
+        self.min_matched_alleles = int(min_matched_alleles)
+        self.n_groups = len(self.group_row_off) - 1
+        # capacity: the span every group can touch
+        cap = 0
+        for g in range(self.n_groups):
+            r0, r1 = int(self.group_row_off[g]), int(self.group_row_off[g + 1])
+            lens = np.diff(self.row_cell_off[r0:r1 + 1].astype(np.int64))
+            if r1 > r0 and lens.sum():
+                st = self.row_start[r0:r1].astype(np.int64)
+                cap += int((st + lens)[lens > 0].max() - st[lens > 0].min())
+        self.cell_capacity = cap
+
+    def as_struct(self):
+        return hp_rows_batch(self.n_blocks, ptr(self.var_off, u64p), ptr(self.group_off, u64p), ptr(self.group_row_off, u64p),
+                             ptr(self.row_start, u32p), ptr(self.row_cell_off, u64p), ptr(self.alleles, u8p), ptr(self.quals, u8p),
+                             self.min_matched_alleles)
+
+
+class Assembled:
+    def __init__(self, rows):
+        n = max(rows.n_groups, 1)
+        self.read_off = np.zeros(rows.n_blocks + 1, np.uint64)
+        self.read_start = np.zeros(n, np.uint32); self.read_end = np.zeros(n, np.uint32)
+        self.cell_off = np.zeros(n + 1, np.uint64)
+        self.cell_capacity = max(rows.cell_capacity, 1)
+        self.alleles = np.full(self.cell_capacity, 255, np.uint8); self.quals = np.full(self.cell_capacity, 255, np.uint8)
+        self.group_class = np.full(n, 255, np.uint8); self.group_num_set = np.zeros(n, np.uint32)
+        self._s = hp_assembled(ptr(self.read_off, u64p), ptr(self.read_start, u32p), ptr(self.read_end, u32p), ptr(self.cell_off, u64p),
+                               ptr(self.alleles, u8p), ptr(self.quals, u8p), self.cell_capacity, ptr(self.group_class, u8p),
+                               ptr(self.group_num_set, u32p), 0, 0)
+
+    def as_struct(self):
+        return self._s
+
+    def block_batch(self, rows, ignored=None, is_snv=None):
+        """The assembled reads as a BlockBatch ready for astar_solve_batch."""
+        nr, nc, nv = int(self._s.n_reads), int(self._s.n_cells), int(rows.var_off[-1])
+        return BlockBatch(rows.var_off, self.read_off, self.read_start[:nr], self.read_end[:nr], self.cell_off[:nr + 1],
+                          self.alleles[:nc], self.quals[:nc], np.zeros(nv, np.uint8) if ignored is None else ignored,
+                          np.ones(nv, np.uint8) if is_snv is None else is_snv)

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HP_B200_LIB") or os.path.join(CSRC, "libhiphase_b200.
 EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
            "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch",
-           "hp_local_realign_batch", "hp_edit_distance_batch", "hp_pack_write_blocks", "hp_pack_open",
+           "hp_local_realign_batch", "hp_edit_distance_batch", "hp_assemble_blocks", "hp_pack_write_blocks", "hp_pack_open",
            "hp_pack_get_blocks", "hp_pack_close", "hp_pack_last_error", "hp_write_phase_stats")
 
 _LIB = None
@@ -62,6 +62,7 @@ def lib():
                                          C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), A.u64p]
         L.hp_local_realign_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_local_batch), C.POINTER(A.hp_local_out)]
         L.hp_edit_distance_batch.argtypes = [C.c_void_p, C.c_uint32, A.u8p, C.c_uint64, A.u64p, A.u32p, A.u64p, A.u32p, A.u32p]
+        L.hp_assemble_blocks.argtypes = [C.c_void_p, C.POINTER(A.hp_rows_batch), C.POINTER(A.hp_assembled)]
         L.hp_pack_write_blocks.argtypes = [C.c_char_p, C.POINTER(A.hp_block_batch), A.i64p]
         L.hp_pack_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.hp_pack_get_blocks.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.POINTER(A.i64p)]
@@ -180,6 +181,14 @@ class Context:
         self.check(lib().hp_edit_distance_batch(self._h, len(pairs), A.ptr(blob, A.u8p), pos, A.ptr(a_off, A.u64p), A.ptr(a_len, A.u32p),
                                                 A.ptr(b_off, A.u64p), A.ptr(b_len, A.u32p), A.ptr(dist, A.u32p)))
         return dist
+
+    # ---- matrix assembly ----
+    def assemble_blocks(self, rows):
+        """ReadSegment::new + collapse + the min-matched-alleles filter for a RowsBatch.  Returns an Assembled."""
+        out = A.Assembled(rows)
+        rs = rows.as_struct()
+        self.check(lib().hp_assemble_blocks(self._h, C.byref(rs), C.byref(out.as_struct())))
+        return out
 
     def astar_solve_device(self, dev_batch_struct, n_vars, n_reads, n_cells, max_block_vars, dev_out_struct, stream):
         self.check(lib().hp_astar_solve_device(self._h, C.byref(dev_batch_struct), n_vars, n_reads, n_cells,

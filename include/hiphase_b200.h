@@ -331,6 +331,51 @@ int hp_edit_distance_batch(hp_ctx* ctx, uint32_t n_pairs, const uint8_t* bytes, 
                            const uint64_t* a_off, const uint32_t* a_len, const uint64_t* b_off, const uint32_t* b_len,
                            uint32_t* dist);
 
+/* ---- matrix assembly: per-mapping rows -> collapsed ReadSegments -> the A* block batch ------------------------------
+ *      replaces ReadSegment::new (src/data_types/read_segments.rs:40-62), ReadSegment::collapse (:71-121), get_num_set
+ *      (:151-155) and the min-matched-alleles filter of load_full_read_segments (src/read_parsing.rs:612-629): the glue
+ *      between the realignment outputs (hp_wfa_align_batch / hp_local_realign_batch rows) and hp_astar_solve_batch. -- */
+#define HP_GROUP_DROPPED   0   /* no allele set after collapsing                                                    */
+#define HP_GROUP_PHASABLE  1   /* 0 < num_set < min_matched_alleles: "phasable_segments" only (read_parsing.rs:622-626) */
+#define HP_GROUP_KEPT      2   /* becomes a read of the block                                                      */
+#define HP_GROUP_ASSERT    3   /* equal alleles with quality 0 on both mappings: the reference asserts (:108)       */
+/*
+ * Block b owns read groups [group_off[b], group_off[b+1]) (one group per read name, read_parsing.rs:559-562); group g owns
+ * rows [group_row_off[g], group_row_off[g+1]) in the order the mappings were pushed.  Row r covers block-relative variant
+ * indices [row_start[r], row_start[r] + len) with len = row_cell_off[r+1] - row_cell_off[r]; every other cell of the block
+ * is NoOverlap / 0 for that row (the rows of hp_wfa_out / hp_local_out have exactly this shape).
+ */
+typedef struct hp_rows_batch {
+    uint32_t        n_blocks;
+    const uint64_t* var_off;          /* [n_blocks+1]                                                               */
+    const uint64_t* group_off;        /* [n_blocks+1]                                                               */
+    const uint64_t* group_row_off;    /* [n_groups+1]                                                               */
+    const uint32_t* row_start;        /* [n_rows]                                                                   */
+    const uint64_t* row_cell_off;     /* [n_rows+1]                                                                 */
+    const uint8_t*  alleles;          /* [n_row_cells] HP_ALLELE_*                                                  */
+    const uint8_t*  quals;            /* [n_row_cells]                                                              */
+    uint32_t        min_matched_alleles;  /* --min-matched-alleles (cli.rs), default 2                              */
+} hp_rows_batch;
+
+/* Caller-provided buffers: up to n_groups reads and cell_capacity cells (sum over groups of the span from the first to
+ * the last row cell always suffices).  read_off .. quals plug straight into hp_block_batch. */
+typedef struct hp_assembled {
+    uint64_t* read_off;       /* [n_blocks+1]                                                                       */
+    uint32_t* read_start;     /* [n_groups]                                                                         */
+    uint32_t* read_end;       /* [n_groups]                                                                         */
+    uint64_t* cell_off;       /* [n_groups+1]                                                                       */
+    uint8_t*  alleles;        /* [cell_capacity]                                                                    */
+    uint8_t*  quals;          /* [cell_capacity]                                                                    */
+    uint64_t  cell_capacity;
+    uint8_t*  group_class;    /* optional [n_groups] HP_GROUP_*                                                     */
+    uint32_t* group_num_set;  /* optional [n_groups] ReadSegment::get_num_set of the collapsed segment              */
+    uint64_t  n_reads;        /* out                                                                                */
+    uint64_t  n_cells;        /* out                                                                                */
+} hp_assembled;
+
+/* Host buffers in / out.  Returns HP_ERR_INVALID_INPUT if cell_capacity is too small or a row leaves its block. */
+int hp_assemble_blocks(hp_ctx* ctx, const hp_rows_batch* rows, hp_assembled* out);
+
 /* ---- packed phase-block container + stats writer ----------------------------------------
  * The wire / on-disk form of a block batch, "HPB200" v1 (layout in csrc/hp_pack.cu): what a front end that still owns
  * VCF / BAM decoding (the HiPhase Rust code up to src/phaser.rs:541, or any other reader) writes, and what the batch

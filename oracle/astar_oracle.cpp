@@ -492,6 +492,47 @@ int hpo_collapse(uint32_t k, uint64_t n, const uint8_t* alleles, const uint8_t* 
     } catch (const OracleError&) { return 1; }
 }
 
+// Matrix assembly (read_parsing.rs:559-562, 612-629): every row becomes a block-length ReadSegment (ReadSegment::new), the
+// rows of a read group are collapsed, groups with at least min_matched_alleles set alleles become reads of the block.
+int hpo_assemble_blocks(const hp_rows_batch* b, hp_assembled* out) {
+    uint64_t n_reads = 0, n_cells = 0;
+    out->read_off[0] = 0; out->cell_off[0] = 0;
+    for (uint32_t blk = 0; blk < b->n_blocks; blk++) {
+        const size_t N = (size_t)(b->var_off[blk + 1] - b->var_off[blk]);
+        for (uint64_t g = b->group_off[blk]; g < b->group_off[blk + 1]; g++) {
+            std::vector<ReadSegment> segs;
+            for (uint64_t r = b->group_row_off[g]; r < b->group_row_off[g + 1]; r++) {
+                std::vector<uint8_t> al(N, HP_ALLELE_NOOVERLAP), ql(N, 0);
+                const uint64_t c0 = b->row_cell_off[r], len = b->row_cell_off[r + 1] - c0;
+                if (b->row_start[r] + len > N) return 2;
+                for (uint64_t i = 0; i < len; i++) { al[b->row_start[r] + i] = b->alleles[c0 + i]; ql[b->row_start[r] + i] = b->quals[c0 + i]; }
+                segs.push_back(ReadSegment::make(al.data(), ql.data(), N));
+            }
+            uint8_t cls = HP_GROUP_DROPPED;
+            uint32_t nset = 0;
+            ReadSegment c;
+            if (!segs.empty()) {
+                try { c = collapse(segs); nset = (uint32_t)c.num_set(); }
+                catch (const OracleError&) { cls = HP_GROUP_ASSERT; }
+            }
+            if (cls != HP_GROUP_ASSERT) cls = (nset >= b->min_matched_alleles && nset > 0) ? HP_GROUP_KEPT : (nset > 0 ? HP_GROUP_PHASABLE : HP_GROUP_DROPPED);
+            if (out->group_class) out->group_class[g] = cls;
+            if (out->group_num_set) out->group_num_set[g] = nset;
+            if (cls != HP_GROUP_KEPT) continue;
+            if (n_cells + (c.end - c.start) > out->cell_capacity) return 3;
+            out->read_start[n_reads] = (uint32_t)c.start; out->read_end[n_reads] = (uint32_t)c.end;
+            std::copy(c.alleles.begin(), c.alleles.end(), out->alleles + n_cells);
+            std::copy(c.quals.begin(), c.quals.end(), out->quals + n_cells);
+            n_cells += c.end - c.start;
+            n_reads++;
+            out->cell_off[n_reads] = n_cells;
+        }
+        out->read_off[blk + 1] = n_reads;
+    }
+    out->n_reads = n_reads; out->n_cells = n_cells;
+    return 0;
+}
+
 int hpo_astar_node_path(const hp_block_batch* b, const uint64_t* H, uint32_t n_steps, const uint8_t* a1, const uint8_t* a2,
                         uint64_t* frozen, uint64_t* total, uint64_t* hets) {
     try {

@@ -39,6 +39,9 @@ uint64_t hpo_score_partial(uint64_t start, uint64_t end, const uint8_t* alleles,
 int hpo_collapse(uint32_t k, uint64_t n, const uint8_t* alleles /*k*n*/, const uint8_t* quals /*k*n*/,
                  uint8_t* out_alleles /*n, NoOverlap outside region*/, uint8_t* out_quals, uint64_t* start, uint64_t* end);
 
+/* matrix assembly (read_segments.rs:40-121, 151-155; read_parsing.rs:612-629); returns 0 ok */
+int hpo_assemble_blocks(const hp_rows_batch* rows, hp_assembled* out);
+
 /* ---- AstarNode / tracker probes for the reference's unit tests (astar_phaser.rs:663-798) ---- */
 /*
  * Walks one path of a single block: child d appends (a1[d], a2[d]) with heuristic H[d+1] (main-solver

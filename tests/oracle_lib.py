@@ -65,6 +65,7 @@ def lib():
         L.hpo_closest_allele_clip.argtypes = [C.POINTER(A.hp_local_batch), C.c_uint32, A.u8p, C.c_uint64, C.c_uint64,
                                               C.c_uint64, A.u64p, A.u64p]
         L.hpo_local_realign_batch.argtypes = [C.POINTER(A.hp_local_batch), C.POINTER(A.hp_local_out)]
+        L.hpo_assemble_blocks.argtypes = [C.POINTER(A.hp_rows_batch), C.POINTER(A.hp_assembled)]
         _LIB = L
     return _LIB
 
@@ -200,4 +201,11 @@ def local_realign(batch):
     out = A.LocalOut(batch)
     bs, os_ = batch.as_struct(), out.as_struct()
     out.rc = lib().hpo_local_realign_batch(C.byref(bs), C.byref(os_))
+    return out
+
+
+def assemble_blocks(rows):
+    out = A.Assembled(rows)
+    rs = rows.as_struct()
+    out.rc = lib().hpo_assemble_blocks(C.byref(rs), C.byref(out.as_struct()))
     return out
