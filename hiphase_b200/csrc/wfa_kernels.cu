@@ -515,6 +515,7 @@ struct BuildArgs {
     uint32_t* e_child;
 };
 
+constexpr uint32_t kNoisyProbe = 6;    // probe estimate (edit distance over the first 256 bases) from which a job is scheduled first
 constexpr int kBuildCap = 64;      // open ALT branches / parents of one node / pending allele-0 tags
 constexpr uint32_t kBuildOk = 0, kBuildInvalid = 1, kBuildOverflow = 2;
 
@@ -622,6 +623,60 @@ __global__ void __launch_bounds__(128) wfa_graph_build_kernel(BuildArgs a) {
     for (uint32_t e = 0; e < n_edges; e++) a.child_idx[coff[a.e_parent[ebase + e]]++] = a.e_child[ebase + e];
     for (uint32_t i = n_nodes; i >= 1; i--) coff[i] = coff[i - 1];      // undo the fill cursors
     coff[0] = (uint32_t)ebase;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scheduling probe: jobs that will run to MaxEditDistance take ~10x longer than the others, so they should start first.
+// The first base of a job's read is aligned to the first base of its reference window (read_parsing.rs:737-741, 773),
+// so the unit-cost edit distance of four 64-base pieces of the read's head against the same pieces of the window (Myers
+// bit-vector, one thread per job) separates noisy reads from clean ones.  The estimate only orders the persistent
+// kernel's ticket queue: results never depend on it.
+// ---------------------------------------------------------------------------------------------------------------
+struct ProbeArgs {
+    uint32_t n_sel;
+    const uint32_t* ids;
+    const uint64_t* ref_start;
+    const uint64_t* ref_end;
+    const uint64_t* read_off;      // [n_jobs + 1] of the caller's batch
+    const uint8_t* reference;
+    const uint8_t* read_bytes;
+    uint32_t* noise;               // [n_sel]
+};
+
+__device__ __forceinline__ uint32_t probe_ed64(const uint8_t* pat, const uint8_t* txt) {
+    uint64_t pA = 0, pC = 0, pG = 0, pT = 0;
+    for (uint32_t j = 0; j < 64; j++) {
+        const uint8_t c = pat[j];
+        const uint64_t bit = 1ull << j;
+        if (c == 'A') pA |= bit; else if (c == 'C') pC |= bit; else if (c == 'G') pG |= bit; else if (c == 'T') pT |= bit;
+    }
+    uint64_t Pv = ~0ull, Mv = 0;
+    uint32_t score = 64;
+    for (uint32_t i = 0; i < 64; i++) {
+        const uint8_t c = txt[i];
+        const uint64_t Eq = c == 'A' ? pA : c == 'C' ? pC : c == 'G' ? pG : c == 'T' ? pT : 0ull;
+        const uint64_t Xv = Eq | Mv;
+        const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        uint64_t Ph = Mv | ~(Xh | Pv);
+        uint64_t Mh = Pv & Xh;
+        if (Ph >> 63) score++; else if (Mh >> 63) score--;
+        Ph = (Ph << 1) | 1ull; Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph); Mv = Ph & Xv;
+    }
+    return score;
+}
+
+__global__ void __launch_bounds__(128) wfa_noise_probe_kernel(ProbeArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_sel) return;
+    const uint32_t j = a.ids[slot];
+    const uint64_t rlen = a.read_off[j + 1] - a.read_off[j], wlen = a.ref_end[j] - a.ref_start[j];
+    const uint8_t* rd = a.read_bytes + a.read_off[j];
+    const uint8_t* rf = a.reference + a.ref_start[j];
+    uint32_t est = 0;
+    for (uint32_t k = 0; k < 4; k++)
+        if ((k + 1) * 64ull <= rlen && (k + 1) * 64ull <= wlen) est += probe_ed64(rd + 64 * k, rf + 64 * k);
+    a.noise[slot] = est;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -771,7 +826,12 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     a.n_jobs = nj;
     std::vector<uint32_t> order(nj);
     for (uint32_t i = 0; i < nj; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return fg.jobs[x].read_len > fg.jobs[y].read_len; });
+    // ticket order: jobs the probe marks as noisy first (they run ~10x longer), then longest reads first
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        const bool nx = fg.jobs[x].pad >= kNoisyProbe, ny = fg.jobs[y].pad >= kNoisyProbe;
+        if (nx != ny) return nx;
+        return fg.jobs[x].read_len > fg.jobs[y].read_len;
+    });
     if (dev) {
         a.jobs = dev->jobs; a.nodes = dev->nodes; a.child_off = dev->child_off; a.child_idx = dev->child_idx;
         a.amap_off = dev->amap_off; a.amap = dev->amap;
@@ -844,6 +904,7 @@ struct DevInputs {
     bool ready = false;
     BuildArgs b{};
     DevBuilt pools;
+    const uint64_t* read_off = nullptr;   // device copy of the batch's read offsets (scheduling probe)
     size_t used = 0;               // bytes of ctx->wfa_graph taken by the batch-constant inputs
 };
 
@@ -853,7 +914,7 @@ static int wfa_upload_batch(hp_ctx* ctx, const hp_wfa_batch* b, DevInputs& di, s
     const uint64_t n_read = b->read_off[nj];
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t bytes = al(8ull * nv) * 3 + al(4ull * nv) * 3 + al(nv) * 3 + al(vt.n_allele_bytes) + al(b->n_reference) + al(n_read) +
-                         al(8ull * nj) * 2 + al(4ull * nj) * 4 + 4096;
+                         al(8ull * nj) * 2 + al(4ull * nj) * 4 + al(8ull * (nj + 1)) + 4096;
     if (!ctx->wfa_graph.reserve(bytes + graph_bytes_hint)) return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA graph workspace allocation failed");
     cudaStream_t st = ctx->stream;
     uint8_t* p = (uint8_t*)ctx->wfa_graph.ptr;
@@ -872,6 +933,7 @@ static int wfa_upload_batch(hp_ctx* ctx, const hp_wfa_batch* b, DevInputs& di, s
     a.het_lo = (const uint32_t*)up(b->het_lo, 4ull * nj); a.het_hi = (const uint32_t*)up(b->het_hi, 4ull * nj);
     a.hom_lo = (const uint32_t*)up(b->hom_lo, 4ull * nj); a.hom_hi = (const uint32_t*)up(b->hom_hi, 4ull * nj);
     a.n_reference = b->n_reference;
+    di.read_off = (const uint64_t*)up(b->read_off, 8ull * (nj + 1));
     if (!ok) { cudaGetLastError(); return wfa_fail(ctx, HP_ERR_CUDA, "WFA batch upload failed"); }
     di.used = (size_t)(p - (uint8_t*)ctx->wfa_graph.ptr);
     di.ready = true;
@@ -956,8 +1018,20 @@ static int wfa_build_on_device(hp_ctx* ctx, const hp_wfa_batch* b, const std::ve
     wfa_graph_build_kernel<true><<<grid, 128, 0, st>>>(a);
     WFA_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
+    // scheduling probe (reuses the count-pass slice, which the fill kernel has consumed by stream order)
+    std::vector<uint32_t> noise(ns, 0);
+    {
+        ProbeArgs pa;
+        pa.n_sel = ns; pa.ids = d_ids; pa.ref_start = di.b.ref_start; pa.ref_end = di.b.ref_end; pa.read_off = di.read_off;
+        pa.reference = di.pools.reference; pa.read_bytes = di.pools.read_bytes; pa.noise = d_counts;
+        wfa_noise_probe_kernel<<<grid, 128, 0, st>>>(pa);
+        WFA_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        WFA_CUDA(ctx, cudaMemcpyAsync(noise.data(), d_counts, 4ull * ns, cudaMemcpyDeviceToHost, st));
+    }
     // edge_base / amap_base / e_* go out of scope with this function: the fill kernel must have read them
     WFA_CUDA(ctx, cudaStreamSynchronize(st));
+    for (uint32_t k = 0; k < ns; k++) fg.jobs[k].pad = noise[k];
     dev = di.pools;
     dev.jobs = d_jobs; dev.nodes = a.nodes; dev.child_off = a.child_off; dev.child_idx = a.child_idx; dev.amap_off = a.amap_off; dev.amap = a.amap;
     return HP_OK;
