@@ -1420,6 +1420,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             num_pruned += k; qsize -= k; w.pops += k;
         }
     };
+#ifdef HP_DBG_RING_AGE
+    uint32_t hist_first = 0xffffffffu, hist_n = 0;     // lane l: first child index of the expansion made (l+1) expansions ago ... ring of 32
+    unsigned long long age_le[4] = {0, 0, 0, 0};        // plane-rescored pops whose parent expansion is <= 4 / 8 / 16 / 32 expansions old
+#endif
     long long tm_pop = 0, tm_exp = 0, tm_rest = 0, tm_planes = 0, n_real = 0, n_planes = 0, n_swept = 0, tq0 = 0, tm_vec = 0, tm_rec = 0, tm_push = 0, tm_dead = 0;   // counting variant only
     for (;;) {
         if (kCount) tq0 = clock64();
@@ -1586,6 +1590,20 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         if (kCount) {
             const long long t1 = clock64(); tm_exp += t1 - tq0;
             if (cur_src == SRC_PLANES) { tm_planes += t1 - tq0; n_planes++; }
+#ifdef HP_DBG_RING_AGE
+            if (cur_src == SRC_PLANES) {
+                // which of the last 32 expansions created cur?  (children of an expansion have consecutive indices)
+                const uint32_t dd = cur_idx - hist_first;
+                const uint32_t hit = __ballot_sync(HP_FULL_MASK, hist_first != 0xffffffffu && dd < 4u);
+                if (hit) {
+                    const uint32_t slot = __ffs(hit) - 1;                    // lane = ring slot; age = (hist_n - 1 - slot) mod 32 + 1
+                    const uint32_t age = ((hist_n - 1u - slot) & 31u) + 1u;
+                    if (age <= 4) age_le[0]++; if (age <= 8) age_le[1]++; if (age <= 16) age_le[2]++; age_le[3]++;
+                }
+            }
+            if (lane == (hist_n & 31u)) hist_first = next_idx;               // this expansion's first child index
+            hist_n++;
+#endif
             tq0 = t1;
         }
         if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
@@ -1874,7 +1892,10 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
 #ifdef HP_DBG_MAIN_SPLIT
         d[15] = tm_dead;     // cycles spent discarding dead top entries (part of the real-pop time)
 #endif
-        d[5] = tm_vec; d[6] = tm_rec; d[4] = tm_push;   // (overwritten below by the team's round statistics unless HP_DBG_MAIN_SPLIT)
+        d[5] = tm_vec; d[6] = tm_rec; d[4] = tm_push;
+#ifdef HP_DBG_RING_AGE
+        d[8] = age_le[0]; d[9] = age_le[1]; d[10] = age_le[2]; d[12] = age_le[3];
+#endif   // (overwritten below by the team's round statistics unless HP_DBG_MAIN_SPLIT)
     }
     if (w.status != HP_BLOCK_OK) return;
 
