@@ -26,6 +26,8 @@ HP_BLOCK_IGNORED_NOT_NOOVERLAP = 1
 HP_BLOCK_COST_OVERFLOW = 2
 HP_BLOCK_QUEUE_OVERFLOW = 3
 HP_BLOCK_ASSERT = 4
+HP_BLOCK_TOO_DENSE = 5
+HP_BLOCK_INDEX_EXHAUSTED = 6
 
 HP_WFA_OK = 0
 HP_WFA_MAX_EDIT_DISTANCE = 1
@@ -192,6 +194,18 @@ class AstarOut:
         self.status = np.full(batch.n_blocks, -1, np.int32)
         self.heuristic = np.zeros(batch.n_vars + batch.n_blocks, np.uint64) if want_heuristic else None
         self.counters = np.zeros(batch.n_blocks, COUNTERS_DTYPE) if want_counters else None
+
+    @staticmethod
+    def sized(n_vars, n_blocks, alloc=None):
+        """Result buffers for n_vars variants / n_blocks blocks; alloc(n, dtype) -> array (e.g. pinned memory)."""
+        o = AstarOut.__new__(AstarOut)
+        mk = alloc or (lambda n, dt: np.zeros(n, dt))
+        o.h1 = mk(n_vars, np.uint8); o.h2 = mk(n_vars, np.uint8)
+        o.h1[...] = 255; o.h2[...] = 255
+        o.stats = mk(n_blocks, STATS_DTYPE)
+        o.status = mk(n_blocks, np.int32); o.status[...] = -1
+        o.heuristic = None; o.counters = None
+        return o
 
     def as_struct(self):
         return hp_astar_out(ptr(self.h1, u8p), ptr(self.h2, u8p),

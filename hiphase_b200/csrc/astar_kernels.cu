@@ -1123,7 +1123,8 @@ __device__ void main_solve(const AstarArgs& a, const BlkMeta& m, WarpCtx& w, con
         if (kCount) { const long long t1 = clock64(); tm_exp += t1 - t0; t0 = t1; }
         if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
         if (bad_col && cur_frozen + tot[2] + heur != total) { w.status = HP_BLOCK_ASSERT; break; }   // :529
-        if (qsize + nchild + 64 > a.qcap || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+        if (next_idx > 0xfffffff0u) { w.status = HP_BLOCK_INDEX_EXHAUSTED; break; }
+        if (qsize + nchild + 64 > a.qcap) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
 
         // keys, creation order
         uint64_t khi[4]; uint32_t kix[4];
@@ -1607,7 +1608,8 @@ __device__ void main_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             tq0 = t1;
         }
         if (kCount) { w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
-        if (qsize + nchild + 64 > a.qcap || next_idx > 0xfffffff0u) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
+        if (next_idx > 0xfffffff0u) { w.status = HP_BLOCK_INDEX_EXHAUSTED; break; }
+        if (qsize + nchild + 64 > a.qcap) { w.status = HP_BLOCK_QUEUE_OVERFLOW; break; }
 
         // candidate keys: total_c = cur_total - H[p] + H[p+1] + delta_c; hi_c = total_c << 32 | (~hets_c); idx in creation
         // order.  (~hets) is smaller for the heterozygous candidates 0,1, so ties on the total go to the lowest slot.
@@ -2114,11 +2116,14 @@ __global__ void __launch_bounds__(kMaxTeam * 32, HP_CTAS_PER_SM) astar_solve_ker
     w.evals = w.sum_lp = w.pops = w.cells = 0;
     w.ts_pop = w.ts_seat = w.ts_score = w.ts_rest = w.ts_popa = w.ts_popb = 0; w.ns_real = w.ns_planes = w.ns_exp = 0;
 
-    // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp
-    uint8_t* my_slab = a.slabs + (uint64_t)blockIdx.x * a.slab_bytes;
-    const Slab slab = carve_slab(my_slab, a.qcap, a.hap_words);
+    // one slab per CTA (team): the main queue (used by warp 0) followed by one sub-queue spill region per warp.  Slabs
+    // come from a pool shared by every launch of the context (batches in flight on different lanes run concurrently): the
+    // CTA claims a free one when it gets its first block and gives it back when it exits.  The pool holds at least as many
+    // slabs as CTAs can be resident, and a waiting CTA holds nothing, so the probe loop always terminates.
+    __shared__ uint32_t s_slab;
+    bool have_slab = false;
+    Slab slab;
     const uint64_t spill_bytes = sub_spill_bytes(w.capl, w.capl_s);
-    w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)(kMaxTeam - warp) * spill_bytes);
     // main-queue keys reuse the whole team's sub-queue shared memory (12 B per key)
     // ... minus a 4 KB tail for the tracker's length counts
     const size_t team_smem = (size_t)team * w.capl_s * 32 * sizeof(SubEntry);
@@ -2140,6 +2145,19 @@ __global__ void __launch_bounds__(kMaxTeam * 32, HP_CTAS_PER_SM) astar_solve_ker
         __syncthreads();
         const uint32_t t = ts.blk;
         if (t >= n_mine) break;
+        if (!have_slab) {
+            if (threadIdx.x == 0) {
+                uint32_t i = (blockIdx.x + a.slab_seed) % a.n_slabs;
+                while (atomicCAS(a.slab_busy + i, 0u, 1u) != 0u) { i = (i + 1u == a.n_slabs) ? 0u : i + 1u; }
+                __threadfence();
+                s_slab = i;
+            }
+            __syncthreads();
+            uint8_t* my_slab = a.slabs + (uint64_t)s_slab * a.slab_bytes;
+            slab = carve_slab(my_slab, a.qcap, a.hap_words);
+            w.sq_spill = (SubEntry*)(my_slab + a.slab_bytes - (uint64_t)(kMaxTeam - warp) * spill_bytes);
+            have_slab = true;
+        }
         const uint32_t blk = a.order[first + t];
         const BlkMeta m = a.meta[blk];
         w.evals = w.sum_lp = w.pops = w.cells = 0;
@@ -2167,6 +2185,10 @@ __global__ void __launch_bounds__(kMaxTeam * 32, HP_CTAS_PER_SM) astar_solve_ker
             }
             if (w.lane == 0) a.out_status[blk] = status;
         }
+    }
+    if (have_slab) {
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); atomicExch(a.slab_busy + s_slab, 0u); }
     }
 }
 
@@ -2201,18 +2223,34 @@ static cudaError_t launch_one(const AstarArgs& a, int n_ctas, int team, size_t s
     return cudaGetLastError();
 }
 
-// Three launches (one per score-vector class); a class without blocks exits at once.
-cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t stream) {
+// Three launches (one per score-vector class, each on its own stream so they run side by side); a class without blocks
+// exits at once.
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t* streams) {
     const size_t smem = astar_smem_bytes(a.sub_capl, team);
     cudaError_t e;
     if (a.out_counters) {
-        if ((e = launch_one<1, true>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
-        if ((e = launch_one<2, true>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
-        return launch_one<0, true>(a, n_ctas, team, smem, stream);
+        if ((e = launch_one<1, true>(a, n_ctas, team, smem, streams[0])) != cudaSuccess) return e;
+        if ((e = launch_one<2, true>(a, n_ctas, team, smem, streams[1])) != cudaSuccess) return e;
+        return launch_one<0, true>(a, n_ctas, team, smem, streams[2]);
     }
-    if ((e = launch_one<1, false>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
-    if ((e = launch_one<2, false>(a, n_ctas, team, smem, stream)) != cudaSuccess) return e;
-    return launch_one<0, false>(a, n_ctas, team, smem, stream);
+    if ((e = launch_one<1, false>(a, n_ctas, team, smem, streams[0])) != cudaSuccess) return e;
+    if ((e = launch_one<2, false>(a, n_ctas, team, smem, streams[1])) != cudaSuccess) return e;
+    return launch_one<0, false>(a, n_ctas, team, smem, streams[2]);
+}
+
+// Upper bound of solver CTAs resident on one SM over every kernel variant at the smallest team (sizes the slab pool).
+int astar_max_ctas_per_sm(uint32_t sub_capl) {
+    int best = 0;
+    const size_t smem = astar_smem_bytes(sub_capl, 1);
+    auto probe = [&](auto kern) {
+        int nb = 0;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem) == cudaSuccess) best = std::max(best, nb);
+        else cudaGetLastError();
+    };
+    probe(astar_solve_kernel<1, false>); probe(astar_solve_kernel<2, false>); probe(astar_solve_kernel<0, false>);
+    probe(astar_solve_kernel<1, true>); probe(astar_solve_kernel<2, true>); probe(astar_solve_kernel<0, true>);
+    return best > 0 ? best : 32;
 }
 
 }  // namespace hp

@@ -58,7 +58,7 @@ __global__ void order_fill_kernel(const BlkMeta* meta, uint32_t n, uint32_t* bin
     if (i < n) order[atomicAdd(&bins[order_bin(meta[i])], 1u)] = i;
 }
 
-static int fail(hp_ctx* ctx, int code, const std::string& msg) {
+int fail(hp_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
     return code;
 }
@@ -79,7 +79,63 @@ static uint32_t sub_capl_for(const hp_params& p) {
     return (uint32_t)((live + 31) / 32 + 1);
 }
 
-int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads, uint64_t n_cells,
+// ---- lanes ----------------------------------------------------------------------------------------------------
+static int lane_get(hp_ctx* ctx, int idx, AstarLane** out) {
+    while ((int)ctx->lanes.size() <= idx) ctx->lanes.push_back(nullptr);
+    if (!ctx->lanes[idx]) {
+        AstarLane* l = new AstarLane();
+        bool ok = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&l->aux[0], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&l->aux[1], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreate(&l->ev0) == cudaSuccess && cudaEventCreate(&l->ev1) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&l->ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&l->ev_join[1], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); delete l; return fail(ctx, HP_ERR_CUDA, "lane stream/event creation failed"); }
+        ctx->lanes[idx] = l;
+    }
+    *out = ctx->lanes[idx];
+    return HP_OK;
+}
+
+static void lane_destroy(AstarLane* l) {
+    if (!l) return;
+    for (DevBuf* b : {&l->meta, &l->rmeta, &l->planes, &l->act_off, &l->act_cur, &l->act_idx, &l->col, &l->order, &l->heur,
+                      &l->ticket, &l->stage_in, &l->stage_out, &l->dbg})
+        b->release();
+    for (cudaEvent_t e : {l->ev0, l->ev1, l->ev_fork, l->ev_join[0], l->ev_join[1], l->ev_done}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {l->stream, l->aux[0], l->aux[1]}) if (st) cudaStreamDestroy(st);
+    delete l;
+}
+
+// Waits until no lane has device work in flight (needed before the slab pool is re-sized).
+static int lanes_quiesce(hp_ctx* ctx) {
+    for (AstarLane* l : ctx->lanes)
+        if (l && l->used) HP_CUDA(ctx, cudaEventSynchronize(l->ev_done));
+    return HP_OK;
+}
+
+// The slab pool must hold slabs of at least this geometry.  n_min = CTAs that may ask for a slab at the same time.
+static int slab_pool_reserve(hp_ctx* ctx, uint32_t qcap, uint32_t hap_words, uint32_t n_min) {
+    const uint64_t bytes = astar_slab_bytes(qcap, hap_words, ctx->sub_capl);
+    if (ctx->slab_qcap == qcap && ctx->slab_hap_words >= hap_words && ctx->n_slabs >= n_min) return HP_OK;
+    int rc = lanes_quiesce(ctx);
+    if (rc != HP_OK) return rc;
+    const bool same = ctx->slab_qcap == qcap;
+    const uint32_t hw = std::max(hap_words, same ? ctx->slab_hap_words : 0u);
+    const uint64_t sb = std::max(bytes, astar_slab_bytes(qcap, hw, ctx->sub_capl));
+    const uint32_t n = same ? std::max(n_min, ctx->n_slabs) : n_min;
+    if (!ctx->slabs.reserve(sb * (uint64_t)n) || !ctx->slab_busy.reserve(4ull * n))
+        return fail(ctx, HP_ERR_OUT_OF_MEMORY, "queue slab pool allocation failed");
+    HP_CUDA(ctx, cudaMemset(ctx->slab_busy.ptr, 0, 4ull * n));
+    ctx->n_slabs = n; ctx->slab_bytes = sb; ctx->slab_hap_words = hw; ctx->slab_qcap = qcap;
+    return HP_OK;
+}
+
+// Enqueues prep + ordering + the three class kernels of one batch (device pointers) on `stream`, using the workspaces
+// of `lane`.  Returns without synchronising.  max_ctas > 0 caps the grid (retry path with huge slabs).
+int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads, uint64_t n_cells,
                  uint32_t max_block_vars, hp_astar_out* out, cudaStream_t stream, int max_ctas) {
     const uint32_t nb = batch->n_blocks;
     if (nb == 0) return HP_OK;
@@ -87,12 +143,15 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
         return fail(ctx, HP_ERR_UNSUPPORTED, "batch too large for 32-bit indices: split it");
     if (max_block_vars == 0) return fail(ctx, HP_ERR_INVALID_INPUT, "max_block_vars must be > 0");
 
+    // the lane's workspaces may still be in use by the previous batch enqueued on another stream
+    if (L->used) HP_CUDA(ctx, cudaStreamWaitEvent(stream, L->ev_done, 0));
+
     const uint64_t n_words = n_cells / 64 + n_reads + 1;
     const uint64_t n_vb = n_vars + nb;
-    if (!ctx->meta.reserve(sizeof(BlkMeta) * (size_t)nb) || !ctx->rmeta.reserve(sizeof(ReadMeta) * (size_t)(n_reads + 1)) ||
-        !ctx->planes.reserve(8ull * HP_PLANE_STRIDE * n_words) || !ctx->act_off.reserve(4 * n_vb) ||
-        !ctx->act_cur.reserve(4 * n_vb) || !ctx->act_idx.reserve(4 * (n_cells + 1)) || !ctx->col.reserve(4 * (n_cells + 130)) || !ctx->order.reserve(4ull * nb) ||
-        !ctx->heur.reserve(4 * n_vb) || !ctx->ticket.reserve(512 + 4 * 192))
+    if (!L->meta.reserve(sizeof(BlkMeta) * (size_t)nb) || !L->rmeta.reserve(sizeof(ReadMeta) * (size_t)(n_reads + 1)) ||
+        !L->planes.reserve(8ull * HP_PLANE_STRIDE * n_words) || !L->act_off.reserve(4 * n_vb) ||
+        !L->act_cur.reserve(4 * n_vb) || !L->act_idx.reserve(4 * (n_cells + 1)) || !L->col.reserve(4 * (n_cells + 130)) || !L->order.reserve(4ull * nb) ||
+        !L->heur.reserve(4 * n_vb) || !L->ticket.reserve(512 + 4 * 192))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "workspace allocation failed");
 
     // team size: use otherwise idle warps for speculative sub-solves (exact, see astar_kernels.cu)
@@ -106,29 +165,30 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)ctx->sm_count * (warps_per_sm / team));
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     const uint32_t hap_words = (max_block_vars + 63) / 64;
-    const uint64_t slab_bytes = astar_slab_bytes(ctx->qcap, hap_words, ctx->sub_capl);
-    if (!ctx->slabs.reserve(slab_bytes * (uint64_t)n_ctas))
-        return fail(ctx, HP_ERR_OUT_OF_MEMORY, "queue slab allocation failed");
+    // every CTA that can be resident at once (any mix of launches) finds a free slab
+    const uint32_t pool_min = max_ctas > 0 ? (uint32_t)n_ctas : (uint32_t)(ctx->sm_count * ctx->max_ctas_per_sm);
+    int rc = slab_pool_reserve(ctx, ctx->qcap, hap_words, pool_min);
+    if (rc != HP_OK) return rc;
 
-    HP_CUDA(ctx, cudaMemsetAsync(ctx->act_off.ptr, 0, 4 * n_vb, stream));
-    HP_CUDA(ctx, cudaMemsetAsync(ctx->act_cur.ptr, 0, 4 * n_vb, stream));
-    HP_CUDA(ctx, cudaMemsetAsync(ctx->ticket.ptr, 0, 512 + 4 * 192, stream));
+    HP_CUDA(ctx, cudaMemsetAsync(L->act_off.ptr, 0, 4 * n_vb, stream));
+    HP_CUDA(ctx, cudaMemsetAsync(L->act_cur.ptr, 0, 4 * n_vb, stream));
+    HP_CUDA(ctx, cudaMemsetAsync(L->ticket.ptr, 0, 512 + 4 * 192, stream));
 
     PrepArgs pa;
     pa.n_blocks = nb; pa.var_off = batch->var_off; pa.read_off = batch->read_off; pa.read_start = batch->read_start;
     pa.read_end = batch->read_end; pa.cell_off = batch->cell_off; pa.alleles = batch->alleles; pa.quals = batch->quals;
     pa.ignored = batch->ignored;
-    pa.meta = (BlkMeta*)ctx->meta.ptr; pa.rmeta = (ReadMeta*)ctx->rmeta.ptr; pa.planes = (uint64_t*)ctx->planes.ptr;
-    pa.act_off = (uint32_t*)ctx->act_off.ptr; pa.act_cur = (uint32_t*)ctx->act_cur.ptr; pa.act_idx = (uint32_t*)ctx->act_idx.ptr; pa.col = (uint32_t*)ctx->col.ptr;
+    pa.meta = (BlkMeta*)L->meta.ptr; pa.rmeta = (ReadMeta*)L->rmeta.ptr; pa.planes = (uint64_t*)L->planes.ptr;
+    pa.act_off = (uint32_t*)L->act_off.ptr; pa.act_cur = (uint32_t*)L->act_cur.ptr; pa.act_idx = (uint32_t*)L->act_idx.ptr; pa.col = (uint32_t*)L->col.ptr;
     HP_CUDA(ctx, launch_astar_prep(pa, stream));
     ctx->launches++;
 
-    uint32_t* class_info = (uint32_t*)((uint8_t*)ctx->ticket.ptr + 256);
-    uint32_t* bins = (uint32_t*)((uint8_t*)ctx->ticket.ptr + 512);
+    uint32_t* class_info = (uint32_t*)((uint8_t*)L->ticket.ptr + 256);
+    uint32_t* bins = (uint32_t*)((uint8_t*)L->ticket.ptr + 512);
     const int tb = 256, gb = (nb + tb - 1) / tb;
     order_count_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins);
     order_scan_kernel<<<1, 1, 0, stream>>>(bins, class_info);
-    order_fill_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins, (uint32_t*)ctx->order.ptr);
+    order_fill_kernel<<<gb, tb, 0, stream>>>(pa.meta, nb, bins, (uint32_t*)L->order.ptr);
     HP_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
 
@@ -136,24 +196,41 @@ int astar_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint
     a.n_blocks = nb;
     a.alleles = batch->alleles; a.quals = batch->quals; a.ignored = batch->ignored; a.is_snv = batch->is_snv;
     a.meta = pa.meta; a.rmeta = pa.rmeta; a.planes = pa.planes; a.act_off = pa.act_off; a.act_idx = pa.act_idx; a.col = pa.col;
-    a.order = (uint32_t*)ctx->order.ptr; a.class_info = class_info;
-    a.heur = (uint32_t*)ctx->heur.ptr; a.ticket = (uint32_t*)ctx->ticket.ptr;
-    a.slabs = (uint8_t*)ctx->slabs.ptr; a.slab_bytes = slab_bytes; a.qcap = ctx->qcap; a.hap_words = hap_words;
+    a.order = (uint32_t*)L->order.ptr; a.class_info = class_info;
+    a.heur = (uint32_t*)L->heur.ptr; a.ticket = (uint32_t*)L->ticket.ptr;
+    a.slabs = (uint8_t*)ctx->slabs.ptr; a.slab_bytes = ctx->slab_bytes; a.qcap = ctx->qcap; a.hap_words = ctx->slab_hap_words;
+    a.slab_busy = (uint32_t*)ctx->slab_busy.ptr; a.n_slabs = ctx->n_slabs;
+    a.slab_seed = (uint32_t)((ctx->launches * 977u) % ctx->n_slabs);
     a.min_queue_size = ctx->params.min_queue_size; a.queue_increment = ctx->params.queue_increment;
     a.sub_capl = ctx->sub_capl;
     a.out_h1 = out->h1; a.out_h2 = out->h2; a.out_stats = (uint64_t*)out->stats; a.out_status = out->status;
     a.out_heur = out->heuristic; a.out_counters = (uint64_t*)out->counters;
     a.dbg_cycles = nullptr;
     if (out->counters && ctx->want_dbg) {
-        if (!ctx->dbg.reserve(128ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
-        a.dbg_cycles = (uint64_t*)ctx->dbg.ptr; ctx->dbg_blocks = nb;
+        if (!L->dbg.reserve(128ull * nb)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
+        a.dbg_cycles = (uint64_t*)L->dbg.ptr; ctx->dbg_blocks = nb;
     }
 
-    HP_CUDA(ctx, cudaEventRecord(ctx->ev0, stream));
-    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, team, stream));
-    HP_CUDA(ctx, cudaEventRecord(ctx->ev1, stream));
+    // the three score-vector classes run side by side (aux streams fork from / join `stream`)
+    HP_CUDA(ctx, cudaEventRecord(L->ev0, stream));
+    HP_CUDA(ctx, cudaEventRecord(L->ev_fork, stream));
+    cudaStream_t cls_stream[3] = {stream, L->aux[0], L->aux[1]};
+    for (int c = 1; c < 3; c++) HP_CUDA(ctx, cudaStreamWaitEvent(cls_stream[c], L->ev_fork, 0));
+    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, team, cls_stream));
+    for (int c = 1; c < 3; c++) {
+        HP_CUDA(ctx, cudaEventRecord(L->ev_join[c - 1], cls_stream[c]));
+        HP_CUDA(ctx, cudaStreamWaitEvent(stream, L->ev_join[c - 1], 0));
+    }
+    HP_CUDA(ctx, cudaEventRecord(L->ev1, stream));
     ctx->launches += 3;
-    ctx->timing_pending = true;
+    L->timing_pending = true;
+    return HP_OK;
+}
+
+// Marks the end of everything enqueued for this lane on `stream` (kernels and result copies).
+static int lane_mark_done(hp_ctx* ctx, AstarLane* L, cudaStream_t stream) {
+    HP_CUDA(ctx, cudaEventRecord(L->ev_done, stream));
+    L->used = true;
     return HP_OK;
 }
 
@@ -199,6 +276,7 @@ int hp_ctx_create(const hp_params* params, int device, hp_ctx** out_ctx) {
 
     hp_ctx* ctx = new hp_ctx();
     ctx->params = p; ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->sub_capl = capl;
+    ctx->max_ctas_per_sm = astar_max_ctas_per_sm(capl);
     uint64_t q = std::max<uint64_t>(16ull * p.min_queue_size + 384, 4096);
     ctx->qcap = (uint32_t)std::min<uint64_t>((q + 31) & ~31ull, 1u << 24);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -214,9 +292,14 @@ void hp_ctx_destroy(hp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->meta, &ctx->rmeta, &ctx->planes, &ctx->act_off, &ctx->act_cur, &ctx->act_idx, &ctx->col, &ctx->order,
-                      &ctx->heur, &ctx->ticket, &ctx->dbg, &ctx->slabs, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in, &ctx->wfa_out, &ctx->wfa_graph})
+    hp_comm_destroy(ctx);
+    for (AstarLane* l : ctx->lanes) {
+        if (l) { if (l->used) cudaEventSynchronize(l->ev_done); delete l->job; lane_destroy(l); }
+    }
+    for (DevBuf* b : {&ctx->ticket, &ctx->slabs, &ctx->slab_busy, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in,
+                      &ctx->wfa_out, &ctx->wfa_graph, &ctx->comm_send, &ctx->comm_recv})
         b->release();
+    ctx->pin_send.release(); ctx->pin_recv.release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -224,20 +307,39 @@ void hp_ctx_destroy(hp_ctx* ctx) {
 
 uint64_t hp_launch_count(const hp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int hp_ctx_set_lanes(hp_ctx* ctx, int lanes) {
+    if (!ctx || lanes < 1 || lanes > 16) return HP_ERR_INVALID_INPUT;
+    ctx->n_lanes = lanes;
+    if (ctx->next_lane >= lanes) ctx->next_lane = 0;
+    return HP_OK;
+}
+
 // Not part of the public header: per-block phase cycles of the last counting run (profiling aid for bench/profiles).
 int hp_debug_set_team(hp_ctx* ctx, int team) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->force_team = team; return HP_OK; }
 // bit 0: build the WFA graphs on the host (A/B aid); bit 1: no workspace hint (exercises the regrow path)
 int hp_debug_wfa_build_mode(hp_ctx* ctx, int mode) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->wfa_host_build = (mode & 1) != 0; ctx->wfa_no_hint = (mode & 2) != 0; return HP_OK; }
 int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
 int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
-    if (!ctx || !out || n_blocks > ctx->dbg_blocks || !ctx->dbg.ptr) return HP_ERR_INVALID_INPUT;
-    if (cudaMemcpy(out, ctx->dbg.ptr, 128ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
+    if (!ctx || !out || n_blocks > ctx->dbg_blocks) return HP_ERR_INVALID_INPUT;
+    AstarLane* L = (size_t)ctx->last_lane < ctx->lanes.size() ? ctx->lanes[ctx->last_lane] : nullptr;
+    if (!L || !L->dbg.ptr) return HP_ERR_INVALID_INPUT;
+    if (cudaMemcpy(out, L->dbg.ptr, 128ull * n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return HP_ERR_CUDA;
     return HP_OK;
 }
 
+// Device time of the solver kernels of the last A* call (or of the last WFA / local kernel timed through ctx->ev0/ev1).
 float hp_last_kernel_ms(const hp_ctx* cctx) {
     hp_ctx* ctx = const_cast<hp_ctx*>(cctx);
     if (!ctx) return 0.f;
+    AstarLane* L = (size_t)ctx->last_lane < ctx->lanes.size() ? ctx->lanes[ctx->last_lane] : nullptr;
+    if (L && L->timing_pending) {
+        if (cudaEventSynchronize(L->ev1) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, L->ev0, L->ev1) == cudaSuccess) ctx->last_ms = ms;
+        }
+        cudaGetLastError();
+        L->timing_pending = false;
+    }
     if (ctx->timing_pending) {
         if (cudaEventSynchronize(ctx->ev1) == cudaSuccess) {
             float ms = 0.f;
@@ -249,11 +351,44 @@ float hp_last_kernel_ms(const hp_ctx* cctx) {
     return ctx->last_ms;
 }
 
+// Lane policy: the first lane that holds no job and has no device work in flight (so strictly sequential callers stay on
+// lane 0 and its workspaces); when every lane is busy on the device, lanes are taken in rotation (the new batch queues
+// behind that lane's previous one).
+static int take_lane(hp_ctx* ctx, AstarLane** L, int* idx) {
+    int pick = -1;
+    for (int i = 0; i < ctx->n_lanes && pick < 0; i++) {
+        AstarLane* l = (size_t)i < ctx->lanes.size() ? ctx->lanes[i] : nullptr;
+        if (!l) { pick = i; break; }
+        if (l->job) continue;
+        if (!l->used) { pick = i; break; }
+        const cudaError_t e = cudaEventQuery(l->ev_done);
+        if (e == cudaSuccess) pick = i; else cudaGetLastError();
+    }
+    if (pick < 0) {
+        for (int k = 0; k < ctx->n_lanes; k++) {
+            const int i = (ctx->next_lane + k) % ctx->n_lanes;
+            if (!ctx->lanes[i]->job) { pick = i; break; }
+        }
+        if (pick < 0) return fail(ctx, HP_ERR_INVALID_INPUT, "every lane holds an unfinished job: call hp_astar_wait on the oldest first");
+        ctx->next_lane = (pick + 1) % ctx->n_lanes;
+    }
+    int rc = lane_get(ctx, pick, L);
+    if (rc != HP_OK) return rc;
+    *idx = pick; ctx->last_lane = pick;
+    return HP_OK;
+}
+
 int hp_astar_solve_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads, uint64_t n_cells,
                           uint32_t max_block_vars, hp_astar_out* out, void* stream) {
     if (!ctx || !batch || !out) return HP_ERR_INVALID_INPUT;
     HP_CUDA(ctx, cudaSetDevice(ctx->device));
-    return astar_device(ctx, batch, n_vars, n_reads, n_cells, max_block_vars, out, (cudaStream_t)stream, 0);
+    AstarLane* L; int li;
+    int rc = take_lane(ctx, &L, &li);
+    if (rc != HP_OK) return rc;
+    if (L->job) return fail(ctx, HP_ERR_INVALID_INPUT, "lane busy with a submitted job: wait for it first");
+    rc = astar_device(ctx, L, batch, n_vars, n_reads, n_cells, max_block_vars, out, (cudaStream_t)stream, 0);
+    if (rc != HP_OK) return rc;
+    return lane_mark_done(ctx, L, (cudaStream_t)stream);
 }
 
 static int validate_host_batch(hp_ctx* ctx, const hp_block_batch* b, uint32_t* max_n) {
@@ -278,14 +413,18 @@ static int validate_host_batch(hp_ctx* ctx, const hp_block_batch* b, uint32_t* m
 // Carves `bytes` (256-aligned) out of a staging buffer.
 static uint8_t* carve(uint8_t*& p, size_t bytes) { uint8_t* r = p; p += (bytes + 255) & ~(size_t)255; return r; }
 
-static int astar_host_once(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out, uint32_t max_n, int max_ctas) {
+// H2D + kernels + D2H of one host batch, all asynchronous on the lane's stream (no synchronisation).
+static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, hp_astar_out* out, uint32_t max_n, int max_ctas) {
     const uint32_t nb = b->n_blocks;
     const uint64_t n_vars = b->var_off[nb], n_reads = b->read_off[nb], n_cells = b->cell_off[n_reads];
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = L->stream;
+    // the staging buffers may still feed the lane's previous batch
+    if (L->used) HP_CUDA(ctx, cudaStreamWaitEvent(st, L->ev_done, 0));
     // ---- H2D ----
     const size_t in_bytes = 256 * 12 + 8 * (nb + 1) * 2 + 4 * n_reads * 2 + 8 * (n_reads + 1) + n_cells * 2 + n_vars * 2;
-    if (!ctx->stage_in.reserve(in_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "input staging allocation failed");
-    uint8_t* p = (uint8_t*)ctx->stage_in.ptr;
+    if (in_bytes > L->stage_in.cap && L->used) HP_CUDA(ctx, cudaEventSynchronize(L->ev_done));   // re-allocation frees the old buffer
+    if (!L->stage_in.reserve(in_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "input staging allocation failed");
+    uint8_t* p = (uint8_t*)L->stage_in.ptr;
     hp_block_batch d = *b;
 #define HP_UP(field, type, count)                                                                                  \
     do {                                                                                                           \
@@ -301,8 +440,9 @@ static int astar_host_once(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* o
     // ---- device outputs ----
     const size_t out_bytes = 256 * 8 + n_vars * 2 + sizeof(hp_phase_stats) * (size_t)nb + 4ull * nb +
                              (out->heuristic ? 8 * (n_vars + nb) : 0) + (out->counters ? sizeof(hp_astar_counters) * (size_t)nb : 0);
-    if (!ctx->stage_out.reserve(out_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "output staging allocation failed");
-    uint8_t* q = (uint8_t*)ctx->stage_out.ptr;
+    if (out_bytes > L->stage_out.cap && L->used) HP_CUDA(ctx, cudaEventSynchronize(L->ev_done));
+    if (!L->stage_out.reserve(out_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "output staging allocation failed");
+    uint8_t* q = (uint8_t*)L->stage_out.ptr;
     hp_astar_out dout;
     dout.h1 = carve(q, n_vars); dout.h2 = carve(q, n_vars);
     dout.stats = (hp_phase_stats*)carve(q, sizeof(hp_phase_stats) * (size_t)nb);
@@ -310,7 +450,7 @@ static int astar_host_once(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* o
     dout.heuristic = out->heuristic ? (uint64_t*)carve(q, 8 * (n_vars + nb)) : nullptr;
     dout.counters = out->counters ? (hp_astar_counters*)carve(q, sizeof(hp_astar_counters) * (size_t)nb) : nullptr;
 
-    int rc = astar_device(ctx, &d, n_vars, n_reads, n_cells, max_n, &dout, st, max_ctas);
+    int rc = astar_device(ctx, L, &d, n_vars, n_reads, n_cells, max_n, &dout, st, max_ctas);
     if (rc != HP_OK) return rc;
     // ---- D2H ----
     HP_CUDA(ctx, cudaMemcpyAsync(out->h1, dout.h1, n_vars, cudaMemcpyDeviceToHost, st));
@@ -319,21 +459,12 @@ static int astar_host_once(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* o
     HP_CUDA(ctx, cudaMemcpyAsync(out->status, dout.status, 4ull * nb, cudaMemcpyDeviceToHost, st));
     if (out->heuristic) HP_CUDA(ctx, cudaMemcpyAsync(out->heuristic, dout.heuristic, 8 * (n_vars + nb), cudaMemcpyDeviceToHost, st));
     if (out->counters) HP_CUDA(ctx, cudaMemcpyAsync(out->counters, dout.counters, sizeof(hp_astar_counters) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-    HP_CUDA(ctx, cudaStreamSynchronize(st));
-    return HP_OK;
+    return lane_mark_done(ctx, L, st);
 }
 
-int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out) {
-    if (!ctx || !b || !out || !out->h1 || !out->h2 || !out->stats || !out->status) return HP_ERR_INVALID_INPUT;
-    if (b->n_blocks == 0) return HP_OK;
-    HP_CUDA(ctx, cudaSetDevice(ctx->device));
-    uint32_t max_n = 0;
-    int rc = validate_host_batch(ctx, b, &max_n);
-    if (rc != HP_OK) return rc;
-    rc = astar_host_once(ctx, b, out, max_n, 0);
-    if (rc != HP_OK) return rc;
-
-    // Blocks whose main queue outgrew its slab are re-run with a 4x larger slab (and fewer resident warps).
+// Blocks whose main queue outgrew its slab are re-run (synchronously, on the same lane) with a 4x larger slab and
+// fewer resident CTAs.  Called once the first pass of the batch has landed in *out.
+static int astar_host_retry(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, hp_astar_out* out) {
     const uint32_t qcap0 = ctx->qcap;
     for (int attempt = 0; attempt < 4; attempt++) {
         std::vector<uint32_t> redo;
@@ -376,7 +507,8 @@ int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out
         // keep the slab arena under ~24 GB
         const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64, ctx->sub_capl);
         int max_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>(ctx->sm_count, (24ull << 30) / std::max<uint64_t>(slab, 1)));
-        rc = astar_host_once(ctx, &sb, &so, sub_max, max_ctas);
+        int rc = astar_host_enqueue(ctx, L, &sb, &so, sub_max, max_ctas);
+        if (rc == HP_OK && cudaStreamSynchronize(L->stream) != cudaSuccess) { cudaGetLastError(); rc = fail(ctx, HP_ERR_CUDA, "retry pass failed on the device"); }
         if (rc != HP_OK) { ctx->qcap = qcap0; return rc; }
         for (size_t k = 0; k < redo.size(); k++) {
             const uint32_t i = redo[k];
@@ -389,6 +521,66 @@ int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out
     }
     ctx->qcap = qcap0;
     return HP_OK;
+}
+
+int hp_astar_submit(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out, hp_astar_job** job) {
+    if (!ctx || !b || !out || !job || !out->h1 || !out->h2 || !out->stats || !out->status) return HP_ERR_INVALID_INPUT;
+    *job = nullptr;
+    HP_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t max_n = 0;
+    if (b->n_blocks != 0) {
+        int rc = validate_host_batch(ctx, b, &max_n);
+        if (rc != HP_OK) return rc;
+    }
+    AstarLane* L; int li;
+    int rc = take_lane(ctx, &L, &li);
+    if (rc != HP_OK) return rc;
+    if (L->job) return fail(ctx, HP_ERR_INVALID_INPUT, "every lane holds an unfinished job: call hp_astar_wait on the oldest first");
+    hp_astar_job* j = new hp_astar_job();
+    j->lane = li; j->batch = *b; j->out = *out; j->max_n = max_n;
+    if (b->n_blocks != 0) {
+        rc = astar_host_enqueue(ctx, L, b, out, max_n, 0);
+        if (rc != HP_OK) { delete j; return rc; }
+    }
+    L->job = j;
+    *job = j;
+    return HP_OK;
+}
+
+int hp_astar_poll(hp_ctx* ctx, hp_astar_job* job, int* done) {
+    if (!ctx || !job || !done || (size_t)job->lane >= ctx->lanes.size() || ctx->lanes[job->lane]->job != job) return HP_ERR_INVALID_INPUT;
+    AstarLane* L = ctx->lanes[job->lane];
+    if (job->batch.n_blocks == 0 || !L->used) { *done = 1; return HP_OK; }
+    const cudaError_t e = cudaEventQuery(L->ev_done);
+    if (e == cudaSuccess) { *done = 1; return HP_OK; }
+    if (e == cudaErrorNotReady) { cudaGetLastError(); *done = 0; return HP_OK; }
+    cudaGetLastError();
+    return fail(ctx, HP_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+}
+
+int hp_astar_wait(hp_ctx* ctx, hp_astar_job* job) {
+    if (!ctx || !job || (size_t)job->lane >= ctx->lanes.size() || ctx->lanes[job->lane]->job != job) return HP_ERR_INVALID_INPUT;
+    AstarLane* L = ctx->lanes[job->lane];
+    int rc = HP_OK;
+    if (job->batch.n_blocks != 0) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(L->stream) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, HP_ERR_CUDA, "device work of the job failed");
+        } else {
+            ctx->last_lane = job->lane;
+            rc = astar_host_retry(ctx, L, &job->batch, &job->out);
+        }
+    }
+    L->job = nullptr;
+    delete job;
+    return rc;
+}
+
+int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out) {
+    hp_astar_job* job = nullptr;
+    int rc = hp_astar_submit(ctx, b, out, &job);
+    if (rc != HP_OK) return rc;
+    return hp_astar_wait(ctx, job);
 }
 
 int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads, const uint32_t* read_start, const uint32_t* read_end,

@@ -52,8 +52,11 @@ struct AstarArgs {
     // scratch
     uint32_t* heur;              // [n_vars + n_blocks] H[] per block (u32 is exact: total quals < 2^31 is enforced)
     uint32_t* ticket;            // work-queue counters, one per class
-    uint8_t*  slabs;             // per-warp main-queue slabs
+    uint8_t*  slabs;             // pool of main-queue slabs; a CTA claims one when it gets its first block
     uint64_t  slab_bytes;
+    uint32_t* slab_busy;         // [n_slabs] 0 = free, 1 = claimed (the pool is shared by every launch of the context)
+    uint32_t  n_slabs;
+    uint32_t  slab_seed;         // where this launch starts probing (spreads concurrent launches over the pool)
     uint32_t  qcap;              // main-queue capacity per warp (entries, multiple of 32)
     uint32_t  hap_words;         // 64-bit words per haplotype in a main-queue record (covers the largest block)
     // parameters

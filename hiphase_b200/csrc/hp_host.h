@@ -20,15 +20,50 @@ struct DevBuf {
     void release();
 };
 
+// Grow-only pinned host buffer (staging of the result hand-off).
+struct HostPin {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        if (cudaHostAlloc(&ptr, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); ptr = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+};
+
 // kernel launchers (astar_kernels.cu)
 size_t astar_smem_bytes(uint32_t sub_capl, int team);
 int astar_max_team();
 int astar_warps_per_sm();
 uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl);
 cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream);
-cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t stream);
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t* streams /* [3]: one per class */);
+int astar_max_ctas_per_sm(uint32_t sub_capl);
 
 }  // namespace hp
+
+// One A* lane: a stream and a private set of workspaces.  Batches in flight on different lanes overlap on the device.
+struct AstarLane {
+    cudaStream_t stream = nullptr, aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_done = nullptr;
+    bool used = false;                       // ev_done has been recorded at least once
+    bool timing_pending = false;
+    hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, stage_in, stage_out, dbg;
+    struct hp_astar_job* job = nullptr;      // job in flight on this lane (streaming entry)
+};
+
+// A job of the streaming entry (hp_astar_submit .. hp_astar_wait).
+struct hp_astar_job {
+    int lane = 0;
+    hp_block_batch batch;                    // the caller's host batch (pointers stay the caller's)
+    hp_astar_out out;                        // the caller's host outputs
+    uint32_t max_n = 0;
+};
 
 struct hp_ctx {
     hp_params params;
@@ -43,11 +78,20 @@ struct hp_ctx {
     float last_ms = 0.f;
     uint64_t launches = 0;
     std::string err;
-    // A* workspaces
+    // A* lanes (created on demand) and the slab pool they share: main-queue slabs are acquired per CTA on the device
+    std::vector<AstarLane*> lanes;
+    int n_lanes = 4;
+    int next_lane = 0;
+    int last_lane = 0;
+    hp::DevBuf slabs, slab_busy;
+    uint32_t n_slabs = 0;
+    int max_ctas_per_sm = 16;               // solver CTAs that can be resident on one SM (occupancy query)
+    uint64_t slab_bytes = 0;
+    uint32_t slab_hap_words = 0, slab_qcap = 0;
     bool want_dbg = false;
     uint32_t dbg_blocks = 0;
-    hp::DevBuf dbg;
-    hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, slabs, stage_in, stage_out;
+    // staging / scratch of the other entry points (WFA, local realignment, assembly, post-solve)
+    hp::DevBuf ticket, stage_in, stage_out;
     // WFA workspaces
     hp::DevBuf wfa_ws, wfa_in, wfa_out, wfa_graph;
     bool wfa_no_hint = false;               // test aid: start with an unsized graph workspace (exercises the regrow path)
@@ -57,4 +101,13 @@ struct hp_ctx {
     std::vector<uint32_t> wfa_h_score, wfa_h_nodes;
     std::vector<uint8_t> wfa_h_alleles, wfa_h_quals;
     std::vector<uint64_t> wfa_h_trav, wfa_h_ctr;
+    // NCCL communicator (hp_comm_*), resolved at run time from libnccl.so.2
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    hp::DevBuf comm_send, comm_recv;
+    hp::HostPin pin_send, pin_recv;
 };
+
+namespace hp {
+int fail(hp_ctx* ctx, int code, const std::string& msg);
+}

@@ -16,7 +16,10 @@ EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destr
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
            "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch",
            "hp_local_realign_batch", "hp_edit_distance_batch", "hp_assemble_blocks", "hp_pack_write_blocks", "hp_pack_open",
-           "hp_pack_get_blocks", "hp_pack_close", "hp_pack_last_error", "hp_write_phase_stats")
+           "hp_pack_get_blocks", "hp_pack_close", "hp_pack_last_error", "hp_write_phase_stats",
+           "hp_ctx_set_lanes", "hp_astar_submit", "hp_astar_poll", "hp_astar_wait", "hp_host_alloc", "hp_host_free",
+           "hp_host_register", "hp_host_unregister", "hp_block_costs", "hp_lpt_partition", "hp_comm_unique_id",
+           "hp_comm_init", "hp_comm_destroy", "hp_comm_allgather", "hp_comm_gather_results")
 
 _LIB = None
 
@@ -31,7 +34,7 @@ def build(force=False):
     """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     if force and os.path.exists(LIB_PATH):
         os.remove(LIB_PATH)
-    subprocess.run(["make", "-s", "-C", CSRC, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    subprocess.run(["make", "-s", "-j8", "-C", CSRC, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     return LIB_PATH
 
 
@@ -69,8 +72,78 @@ def lib():
         L.hp_pack_close.argtypes = [C.c_void_p]
         L.hp_pack_last_error.restype = C.c_char_p
         L.hp_write_phase_stats.argtypes = [C.c_char_p, C.POINTER(A.hp_block_batch), A.i64p, C.POINTER(A.hp_astar_out), C.c_uint64]
+        L.hp_ctx_set_lanes.argtypes = [C.c_void_p, C.c_int]
+        L.hp_astar_submit.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.POINTER(A.hp_astar_out), C.POINTER(C.c_void_p)]
+        L.hp_astar_poll.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.hp_astar_wait.argtypes = [C.c_void_p, C.c_void_p]
+        L.hp_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.hp_host_free.argtypes = [C.c_void_p]
+        L.hp_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.hp_host_unregister.argtypes = [C.c_void_p]
+        L.hp_block_costs.argtypes = [C.c_uint64, A.u32p, A.u64p, A.u64p]
+        L.hp_lpt_partition.argtypes = [A.u64p, C.c_uint64, C.c_uint32, A.u32p]
+        L.hp_comm_unique_id.argtypes = [A.u8p]
+        L.hp_comm_init.argtypes = [C.c_void_p, A.u8p, C.c_int, C.c_int]
+        L.hp_comm_destroy.argtypes = [C.c_void_p]
+        L.hp_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.hp_comm_gather_results.argtypes = [C.c_void_p, C.c_uint64, A.u64p, A.u64p, C.POINTER(A.hp_astar_out), C.c_uint64,
+                                             A.u64p, C.c_int, C.POINTER(A.hp_astar_out)]
         _LIB = L
     return _LIB
+
+
+# ---- host-only helpers of the sharding layer (no GPU needed) ------------------------------------------------------
+def block_costs(n_var, n_cells):
+    """hp_block_costs: serial-chain cost model of each block (cells * min(N, 40) + N)."""
+    import numpy as np
+    n_var = np.ascontiguousarray(n_var, np.uint32); n_cells = np.ascontiguousarray(n_cells, np.uint64)
+    cost = np.zeros(len(n_var), np.uint64)
+    rc = lib().hp_block_costs(len(n_var), A.ptr(n_var, A.u32p), A.ptr(n_cells, A.u64p), A.ptr(cost, A.u64p))
+    if rc != A.HP_OK:
+        raise HiPhaseB200Error(rc, "hp_block_costs")
+    return cost
+
+
+def lpt_partition(costs, n_shards):
+    """hp_lpt_partition -> shard_of[n] (uint32)."""
+    import numpy as np
+    costs = np.ascontiguousarray(costs, np.uint64)
+    shard_of = np.zeros(len(costs), np.uint32)
+    rc = lib().hp_lpt_partition(A.ptr(costs, A.u64p), len(costs), int(n_shards), A.ptr(shard_of, A.u32p))
+    if rc != A.HP_OK:
+        raise HiPhaseB200Error(rc, "hp_lpt_partition")
+    return shard_of
+
+
+class PinnedArena:
+    """Pinned host memory from hp_host_alloc, handed out as numpy views (kept alive by the arena)."""
+
+    def __init__(self):
+        self._ptrs = []
+
+    def alloc(self, nbytes):
+        import numpy as np
+        p = C.c_void_p()
+        rc = lib().hp_host_alloc(C.byref(p), int(max(nbytes, 1)))
+        if rc != A.HP_OK:
+            raise HiPhaseB200Error(rc, "hp_host_alloc(%d)" % nbytes)
+        self._ptrs.append(p)
+        return np.ctypeslib.as_array(C.cast(p, A.u8p), shape=(int(max(nbytes, 1)),))[:nbytes]
+
+    def empty(self, n, dtype):
+        import numpy as np
+        dt = np.dtype(dtype)
+        return self.alloc(int(n) * dt.itemsize).view(dt)
+
+    def copy(self, arr):
+        out = self.empty(arr.size, arr.dtype)
+        out[...] = arr.reshape(-1)
+        return out
+
+    def close(self):
+        for p in self._ptrs:
+            lib().hp_host_free(p)
+        self._ptrs = []
 
 
 class Context:
@@ -123,6 +196,54 @@ class Context:
         bs, os_ = batch.as_struct(), out.as_struct()
         self.check(lib().hp_astar_solve_batch(self._h, C.byref(bs), C.byref(os_)))
         return out
+
+    def set_lanes(self, lanes):
+        """Number of batches that may be in flight on the device at once (hp_ctx_set_lanes)."""
+        self.check(lib().hp_ctx_set_lanes(self._h, int(lanes)))
+
+    def astar_submit(self, batch, out=None, want_heuristic=False, want_counters=False):
+        """hp_astar_submit: enqueue one host batch, return a job handle (keeps batch / out alive until waited)."""
+        out = out if out is not None else A.AstarOut(batch, want_heuristic, want_counters)
+        bs, os_ = batch.as_struct(), out.as_struct()
+        job = C.c_void_p()
+        self.check(lib().hp_astar_submit(self._h, C.byref(bs), C.byref(os_), C.byref(job)))
+        return (job, batch, out)
+
+    def astar_poll(self, handle):
+        done = C.c_int(0)
+        self.check(lib().hp_astar_poll(self._h, handle[0], C.byref(done)))
+        return bool(done.value)
+
+    def astar_wait(self, handle):
+        """hp_astar_wait: block until the job's results are in its AstarOut; returns it."""
+        self.check(lib().hp_astar_wait(self._h, handle[0]))
+        return handle[2]
+
+    # ---- multi-GPU hand-off (NCCL communicator owned by the context) ----
+    def comm_init(self, unique_id, rank, world):
+        import numpy as np
+        uid = np.ascontiguousarray(unique_id, np.uint8) if unique_id is not None else None
+        self.check(lib().hp_comm_init(self._h, A.ptr(uid, A.u8p), int(rank), int(world)))
+
+    def comm_allgather(self, send, recv):
+        self.check(lib().hp_comm_allgather(self._h, send.ctypes.data_as(C.c_void_p), recv.ctypes.data_as(C.c_void_p), send.nbytes))
+
+    def comm_gather_results(self, local_ids, local_batch, local_out, all_var_off, all_out=None, root=-1, rank=0):
+        """hp_comm_gather_results: the results of all blocks ordered by global block index, on every rank (root < 0) or on
+        rank `root` only (the other ranks get None)."""
+        import numpy as np
+        local_ids = np.ascontiguousarray(local_ids, np.uint64)
+        all_var_off = np.ascontiguousarray(all_var_off, np.uint64)
+        n_total = len(all_var_off) - 1
+        receive = root < 0 or root == rank
+        if all_out is None and receive:
+            all_out = A.AstarOut.sized(int(all_var_off[-1]), n_total)
+        ls = local_out.as_struct()
+        as_ = all_out.as_struct() if receive else None
+        self.check(lib().hp_comm_gather_results(self._h, len(local_ids), A.ptr(local_ids, A.u64p), A.ptr(local_batch.var_off, A.u64p),
+                                                C.byref(ls), n_total, A.ptr(all_var_off, A.u64p), int(root),
+                                                C.byref(as_) if receive else None))
+        return all_out if receive else None
 
     # ---- post-solve (span counts, block tags, haplotags) ----
     def post_solve_batch(self, batch, var_pos, h1, h2):

@@ -127,6 +127,98 @@ def config_c3(n_blocks=10000, first_block=0, n_lo=20, n_hi=2000, coverage=30):
     return BlockBatch.from_blocks(c3_blocks(n_blocks, first_block, n_lo, n_hi, coverage))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# HG002-scale stream (C3 = its first 10 000 blocks, C5 = its first 200 000): multi-threaded C++ generator
+# (csrc/hp_synth.cpp -> libhp_synth.so).  Block b depends on (config_id, b) alone, so ranks regenerate their own shards.
+# ---------------------------------------------------------------------------------------------------------------
+import ctypes as _C
+import os as _os
+
+_SYNTH_LIB = None
+
+
+class hp_synth_params(_C.Structure):
+    _fields_ = [("config_id", _C.c_uint64), ("n_lo", _C.c_uint32), ("n_hi", _C.c_uint32), ("coverage", _C.c_double),
+                ("p_noisy", _C.c_double), ("p_err", _C.c_double), ("p_err_noisy", _C.c_double), ("p_amb", _C.c_double),
+                ("p_gap", _C.c_double), ("p_ignored", _C.c_double)]
+
+
+def _synth_lib():
+    global _SYNTH_LIB
+    if _SYNTH_LIB is None:
+        from . import _abi as A
+        path = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "csrc", "libhp_synth.so")
+        L = _C.CDLL(path)
+        L.hp_synth_default_params.argtypes = [_C.POINTER(hp_synth_params)]
+        L.hp_synth_headers.argtypes = [_C.POINTER(hp_synth_params), _C.c_uint64, _C.c_uint64, A.u32p, A.u8p]
+        L.hp_synth_generate.argtypes = [_C.POINTER(hp_synth_params), A.u64p, _C.c_uint64, _C.c_int, _C.POINTER(_C.c_void_p)]
+        L.hp_synth_view.argtypes = [_C.c_void_p, _C.POINTER(A.hp_block_batch)]
+        L.hp_synth_free.argtypes = [_C.c_void_p]
+        _SYNTH_LIB = L
+    return _SYNTH_LIB
+
+
+def stream_params(**kw):
+    p = hp_synth_params()
+    _synth_lib().hp_synth_default_params(_C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def stream_headers(first_block, n_blocks, params=None):
+    """(n_var[n], noisy[n]) of blocks [first_block, first_block + n) of the stream, without generating them."""
+    from . import _abi as A
+    p = params or stream_params()
+    nv = np.zeros(n_blocks, np.uint32)
+    noisy = np.zeros(n_blocks, np.uint8)
+    _synth_lib().hp_synth_headers(_C.byref(p), int(first_block), int(n_blocks), A.ptr(nv, A.u32p), A.ptr(noisy, A.u8p))
+    return nv, noisy
+
+
+def stream_blocks(ids, params=None, threads=None, alloc=None):
+    """The stream's blocks `ids` (any order) as a BlockBatch.  alloc(nbytes) -> writable uint8 array (e.g. pinned memory)."""
+    from . import _abi as A
+    p = params or stream_params()
+    ids = np.ascontiguousarray(ids, np.uint64)
+    h = _C.c_void_p()
+    L = _synth_lib()
+    L.hp_synth_generate(_C.byref(p), A.ptr(ids, A.u64p), len(ids), int(threads or _os.cpu_count() or 1), _C.byref(h))
+    try:
+        v = A.hp_block_batch()
+        L.hp_synth_view(h, _C.byref(v))
+        nb = len(ids)
+
+        def take(ptr_, n, dt):
+            dt = np.dtype(dt)
+            if n == 0:
+                return np.zeros(0, dt)
+            src = np.ctypeslib.as_array(ptr_, shape=(n,))
+            if alloc is None:
+                return src.astype(dt, copy=True)
+            dst = alloc(n * dt.itemsize).view(dt)
+            dst[:] = src
+            return dst
+        var_off = take(v.var_off, nb + 1, np.uint64); read_off = take(v.read_off, nb + 1, np.uint64)
+        nv, nr = int(var_off[-1]), int(read_off[-1])
+        cell_off = take(v.cell_off, nr + 1, np.uint64)
+        nc = int(cell_off[-1])
+        b = BlockBatch.__new__(BlockBatch)
+        b.var_off, b.read_off, b.cell_off = var_off, read_off, cell_off
+        b.read_start = take(v.read_start, nr, np.uint32); b.read_end = take(v.read_end, nr, np.uint32)
+        b.alleles = take(v.alleles, nc, np.uint8); b.quals = take(v.quals, nc, np.uint8)
+        b.ignored = take(v.ignored, nv, np.uint8); b.is_snv = take(v.is_snv, nv, np.uint8)
+        b.n_blocks = nb
+        return b
+    finally:
+        L.hp_synth_free(h)
+
+
+def config_c3_stream(n_blocks=10000, first_block=0, threads=None):
+    """C3 / C5: blocks [first_block, first_block + n_blocks) of the HG002-scale stream."""
+    return stream_blocks(np.arange(first_block, first_block + n_blocks, dtype=np.uint64), threads=threads)
+
+
 def brute_force_mec(block):
     """Exhaustive minimum of sum_r min(score(h1), score(h2)) over all (h1,h2) in {0,1}^N x {0,1}^N (N <= 8)."""
     N = block["n_var"]

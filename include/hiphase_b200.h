@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HP_ABI_VERSION 1
+#define HP_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------------------------- */
 #define HP_OK                      0
@@ -50,6 +50,7 @@ extern "C" {
 #define HP_BLOCK_QUEUE_OVERFLOW    3   /* internal: main queue outgrew its slab (retried transparently)         */
 #define HP_BLOCK_ASSERT            4   /* a reference assert! would have fired (e.g. astar_phaser.rs:284, 529)  */
 #define HP_BLOCK_TOO_DENSE         5   /* more than 65534 reads cover one variant: outside the kernel's range   */
+#define HP_BLOCK_INDEX_EXHAUSTED   6   /* more than 2^32-16 nodes created: a larger slab cannot help (not retried) */
 
 /* per-job status written to hp_wfa_out.status */
 #define HP_WFA_OK                  0
@@ -154,7 +155,8 @@ int hp_astar_solve_batch(hp_ctx* ctx, const hp_block_batch* batch, hp_astar_out*
  * work is enqueued on `stream` (a cudaStream_t) and the call returns without synchronising.  n_vars / n_reads /
  * n_cells are the array lengths and max_block_vars the largest block's variant count (sizes the queue records).
  * A block whose main queue outgrows its slab reports HP_BLOCK_QUEUE_OVERFLOW (hp_astar_solve_batch retries those
- * transparently with a larger slab; this entry point leaves the retry to the caller).
+ * transparently with a larger slab; this entry point leaves the retry to the caller: check out->status[]).
+ * Calls on different streams overlap on the device (each takes the next of the context's lanes, see hp_ctx_set_lanes).
  */
 int hp_astar_solve_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads,
                           uint64_t n_cells, uint32_t max_block_vars, hp_astar_out* out, void* stream);
@@ -166,6 +168,61 @@ int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads,
                        const uint8_t* ignored, const uint8_t* is_snv,
                        uint8_t* h1, uint8_t* h2, hp_phase_stats* stats);
 
+
+/*
+ * Streaming entry: the reference keeps 40 x threads jobs in flight and streams results back (src/main.rs:328, 344-355).
+ * hp_astar_submit enqueues H2D + kernels + D2H of one batch on one of the context's lanes (own stream and workspaces;
+ * hp_ctx_set_lanes, default 4) and returns without waiting; batches in flight on different lanes share the GPU, so the
+ * long serial chain of one noisy block overlaps the next batches instead of idling the device.  The caller's buffers
+ * (*batch arrays and *out arrays) must stay valid and untouched until hp_astar_wait returns; they should be pinned
+ * (hp_host_alloc / hp_host_register) -- pageable buffers work but make the copies synchronous.
+ * hp_astar_wait blocks until the results are in *out (overflowed blocks are re-run there, as in hp_astar_solve_batch)
+ * and releases the job.  Submitting more jobs than lanes waits for the oldest job's device work first.
+ * HP_OK from wait / solve_batch means the call ran: each block's own outcome is in out->status[] (HP_BLOCK_*).
+ */
+typedef struct hp_astar_job hp_astar_job;
+int hp_ctx_set_lanes(hp_ctx* ctx, int lanes);     /* 1..16 */
+int hp_astar_submit(hp_ctx* ctx, const hp_block_batch* batch, hp_astar_out* out, hp_astar_job** job);
+int hp_astar_poll(hp_ctx* ctx, hp_astar_job* job, int* done);   /* *done = 1 when hp_astar_wait would not block on the device */
+int hp_astar_wait(hp_ctx* ctx, hp_astar_job* job);
+
+/* Pinned host memory for the host entry points (a Rust Vec can be registered in place). */
+int hp_host_alloc(void** ptr, size_t bytes);
+int hp_host_free(void* ptr);
+int hp_host_register(void* ptr, size_t bytes);
+int hp_host_unregister(void* ptr);
+
+/* ---- sharding phase blocks over the GPUs of one box --------------------------------------------------
+ * Blocks share nothing (src/main.rs:385-408 runs them as independent pool jobs), so there is no data-path collective:
+ * the work-queue hand-off is a cost-sorted deal of whole blocks before the solve, and one gather of the results after.
+ */
+/* Serial-chain cost model of a block: n_cells * min(n_var, 40) + n_var (the heuristic look-ahead is 40 variants). */
+int hp_block_costs(uint64_t n_blocks, const uint32_t* n_var, const uint64_t* n_cells, uint64_t* cost);
+/* Longest-processing-time-first deal: blocks by descending cost (ties: lower index first), each to the least loaded
+ * shard (ties: lower shard).  shard_of[i] in [0, n_shards). */
+int hp_lpt_partition(const uint64_t* cost, uint64_t n_blocks, uint32_t n_shards, uint32_t* shard_of);
+
+/* NCCL communicator owned by the context (one process per GPU; NVLink 5 / NVSwitch).  Rank 0 calls hp_comm_unique_id and
+ * hands the 128 bytes to every rank (any out-of-band channel); then every rank calls hp_comm_init. */
+#define HP_COMM_ID_BYTES 128
+int hp_comm_unique_id(uint8_t id[HP_COMM_ID_BYTES]);
+int hp_comm_init(hp_ctx* ctx, const uint8_t id[HP_COMM_ID_BYTES], int rank, int world);
+int hp_comm_destroy(hp_ctx* ctx);
+/* all-gather of bytes_per_rank bytes from every rank (host buffers; staged through the device, ncclAllGather). */
+int hp_comm_allgather(hp_ctx* ctx, const void* send, void* recv, uint64_t bytes_per_rank);
+/*
+ * Result hand-off: every rank passes the results of its own blocks (local_out, n_local blocks with global indices
+ * local_ids[], ascending or not) and receives the results of ALL n_total blocks ordered by global block index, the order
+ * OrderedVcfWriter restores for the reference's workers (src/writers/ordered_vcf_writer.rs:158-170).
+ * all_var_off[n_total + 1] are the global variant offsets (every rank knows every block's variant count).
+ * root < 0: every rank receives (all_out filled everywhere); root >= 0: only that rank copies the gathered message to the
+ * host and fills all_out (the other ranks may pass NULL).  all_out->h1, h2 [all_var_off[n_total]], stats, status [n_total];
+ * heuristic / counters are not gathered.  Two ncclAllGather calls: the shard sizes, then one message per rank holding its
+ * fixed-stride records {index, status, PhaseStats} and its haplotype bytes.
+ */
+int hp_comm_gather_results(hp_ctx* ctx, uint64_t n_local, const uint64_t* local_ids, const uint64_t* local_var_off,
+                           const hp_astar_out* local_out, uint64_t n_total, const uint64_t* all_var_off, int root,
+                           hp_astar_out* all_out);
 
 /* ---- post-solve: span counts, block splitting and haplotagging ------------------------
  *      replaces get_solution_span_counts (src/phaser.rs:350-388), the block_split / block_tags loop

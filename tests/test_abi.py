@@ -20,7 +20,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     for sym in declared:
         assert getattr(L, sym) is not None
-    assert L.hp_abi_version() == 1
+    assert L.hp_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -62,3 +62,45 @@ def test_gather_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_c_lpt_partition_matches_the_python_restatement():
+    """hp_lpt_partition / hp_block_costs (C, host only) against sharding.lpt_partition / block_costs."""
+    from hiphase_b200 import lib
+    rng = np.random.default_rng(1)
+    n_var = np.exp(rng.uniform(np.log(20), np.log(2000), 3000)).astype(np.uint32)
+    n_cells = (n_var.astype(np.uint64) * 30 + rng.integers(0, 50, 3000).astype(np.uint64))
+    cost = lib.block_costs(n_var, n_cells)
+    assert np.array_equal(cost.astype(np.int64), sharding.block_costs(n_var, n_cells))
+    for world in (1, 2, 3, 8):
+        shard_of = lib.lpt_partition(cost, world)
+        parts = sharding.lpt_partition(cost.astype(np.int64), world)
+        for r in range(world):
+            assert np.array_equal(np.flatnonzero(shard_of == r), parts[r])
+    # more shards than blocks: some shards stay empty, every block is dealt once
+    shard_of = lib.lpt_partition(cost[:3], 8)
+    assert len(set(shard_of.tolist())) == 3
+
+
+def test_stream_generator_is_shard_independent():
+    """The C++ HG002-scale stream: block b is the same whatever subset / order / thread count generates it."""
+    from hiphase_b200 import synth
+    a = synth.config_c3_stream(64, first_block=100, threads=1)
+    b = synth.stream_blocks(np.arange(100, 164)[::-1].copy(), threads=4)
+    nv, noisy = synth.stream_headers(100, 64)
+    assert np.array_equal(nv, np.diff(a.var_off.astype(np.int64)))
+    for i in (0, 5, 63):
+        x, y = a.block(i), b.block(63 - i)
+        assert x["n_var"] == y["n_var"] and len(x["reads"]) == len(y["reads"])
+        assert all(r[0] == s[0] and np.array_equal(r[1], s[1]) and np.array_equal(r[2], s[2]) for r, s in zip(x["reads"], y["reads"]))
+        assert np.array_equal(x["ignored"], y["ignored"])
+    # the shape SURVEY 8d asks for: N in [20, 2000], ~30x coverage, every variant covered, reads with >= 2 set alleles
+    assert nv.min() >= 20 and nv.max() <= 2000
+    cover = np.zeros(a.n_vars + 1, np.int64)
+    for blk in range(a.n_blocks):
+        v0 = int(a.var_off[blk])
+        for r in range(int(a.read_off[blk]), int(a.read_off[blk + 1])):
+            cover[v0 + int(a.read_start[r])] += 1; cover[v0 + int(a.read_end[r])] -= 1
+            c0, c1 = int(a.cell_off[r]), int(a.cell_off[r + 1])
+            assert a.alleles[c0] < 2 and a.alleles[c1 - 1] < 2 and (a.alleles[c0:c1] < 2).sum() >= 2
+    assert 25 < a.n_cells / a.n_vars < 35
