@@ -28,6 +28,7 @@ HP_BLOCK_QUEUE_OVERFLOW = 3
 HP_BLOCK_ASSERT = 4
 HP_BLOCK_TOO_DENSE = 5
 HP_BLOCK_INDEX_EXHAUSTED = 6
+HP_COMM_ID_BYTES = 128
 
 HP_WFA_OK = 0
 HP_WFA_MAX_EDIT_DISTANCE = 1

@@ -91,7 +91,8 @@ static int lane_get(hp_ctx* ctx, int idx, AstarLane** out) {
                   cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&l->ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&l->ev_join[1], cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming) == cudaSuccess;
+                  cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&l->ev_in, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { cudaGetLastError(); delete l; return fail(ctx, HP_ERR_CUDA, "lane stream/event creation failed"); }
         ctx->lanes[idx] = l;
     }
@@ -104,7 +105,7 @@ static void lane_destroy(AstarLane* l) {
     for (DevBuf* b : {&l->meta, &l->rmeta, &l->planes, &l->act_off, &l->act_cur, &l->act_idx, &l->col, &l->order, &l->heur,
                       &l->ticket, &l->stage_in, &l->stage_out, &l->dbg})
         b->release();
-    for (cudaEvent_t e : {l->ev0, l->ev1, l->ev_fork, l->ev_join[0], l->ev_join[1], l->ev_done}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {l->ev0, l->ev1, l->ev_fork, l->ev_join[0], l->ev_join[1], l->ev_done, l->ev_in}) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {l->stream, l->aux[0], l->aux[1]}) if (st) cudaStreamDestroy(st);
     delete l;
 }
@@ -136,7 +137,7 @@ static int slab_pool_reserve(hp_ctx* ctx, uint32_t qcap, uint32_t hap_words, uin
 // Enqueues prep + ordering + the three class kernels of one batch (device pointers) on `stream`, using the workspaces
 // of `lane`.  Returns without synchronising.  max_ctas > 0 caps the grid (retry path with huge slabs).
 int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_t n_vars, uint64_t n_reads, uint64_t n_cells,
-                 uint32_t max_block_vars, hp_astar_out* out, cudaStream_t stream, int max_ctas) {
+                 uint32_t max_block_vars, hp_astar_out* out, cudaStream_t stream, int max_ctas, int busy_lanes) {
     const uint32_t nb = batch->n_blocks;
     if (nb == 0) return HP_OK;
     if (n_cells >= (1ull << 32) || n_reads >= (1ull << 32) || n_cells / 64 + n_reads >= (1ull << 32))
@@ -154,15 +155,25 @@ int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_
         !L->heur.reserve(4 * n_vb) || !L->ticket.reserve(512 + 4 * 192))
         return fail(ctx, HP_ERR_OUT_OF_MEMORY, "workspace allocation failed");
 
-    // team size: use otherwise idle warps for speculative sub-solves (exact, see astar_kernels.cu)
-    const int resident_warps = ctx->sm_count * astar_warps_per_sm();
-    int team = 1;
-    // (up to 2x oversubscription of the resident warps still pays: measured on C2, 1000 blocks -> team 4)
-    while (team * 2 <= astar_max_team() && (uint64_t)nb * team * 2 <= 2ull * (uint64_t)resident_warps) team *= 2;
-    if (ctx->force_team > 0) team = std::min(ctx->force_team, astar_max_team());
+    // Share of the device this launch may occupy.  A batch alone on the device takes every resident warp; with other
+    // batches in flight each launch takes capacity x over / (busy lanes + 1) warps, so the launches are co-resident and the
+    // serial chain of one launch's slowest block runs beside the bulk of the others (a launch that holds the whole grid
+    // would keep the next launch's CTAs queued behind it until its bulk has drained).
     int warps_per_sm = astar_warps_per_sm();
-    if (const char* e = getenv("HP_DBG_WARPS_PER_SM")) warps_per_sm = std::max(team, std::min(warps_per_sm, atoi(e)));   // occupancy experiments
-    int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)ctx->sm_count * (warps_per_sm / team));
+    if (const char* e = getenv("HP_DBG_WARPS_PER_SM")) warps_per_sm = std::max(1, std::min(warps_per_sm, atoi(e)));   // occupancy experiments
+    const int resident_warps = ctx->sm_count * warps_per_sm;
+    int share_warps = resident_warps;
+    if (busy_lanes > 0) {
+        double over = 1.5;              // measured on C3 (profiles/r2c_sweep.txt): 1.0-1.5 equal within noise, 2.0 slower
+        if (const char* e = getenv("HP_DBG_OVERSUB")) over = std::max(0.25, atof(e));
+        share_warps = (int)std::min<double>(resident_warps, std::max(1.0, resident_warps * over / (busy_lanes + 1)));
+    }
+    // team size: use otherwise idle warps for speculative sub-solves (exact, see astar_kernels.cu)
+    int team = 1;
+    // (up to 2x oversubscription of the share still pays: measured on C2, 1000 blocks alone -> team 4)
+    while (team * 2 <= astar_max_team() && (uint64_t)nb * team * 2 <= 2ull * (uint64_t)share_warps) team *= 2;
+    if (ctx->force_team > 0) team = std::min(ctx->force_team, astar_max_team());
+    int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)std::max(1, share_warps / team));
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     const uint32_t hap_words = (max_block_vars + 63) / 64;
     // every CTA that can be resident at once (any mix of launches) finds a free slab
@@ -249,6 +260,8 @@ void hp_default_params(hp_params* p) {
 const char* hp_last_error(const hp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int hp_ctx_create(const hp_params* params, int device, hp_ctx** out_ctx) {
+    // lanes are streams: give them their own hardware queues (no effect once the process has initialised CUDA)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     if (!out_ctx) return HP_ERR_INVALID_INPUT;
     *out_ctx = nullptr;
     int n_dev = 0;
@@ -354,15 +367,17 @@ float hp_last_kernel_ms(const hp_ctx* cctx) {
 // Lane policy: the first lane that holds no job and has no device work in flight (so strictly sequential callers stay on
 // lane 0 and its workspaces); when every lane is busy on the device, lanes are taken in rotation (the new batch queues
 // behind that lane's previous one).
-static int take_lane(hp_ctx* ctx, AstarLane** L, int* idx) {
-    int pick = -1;
-    for (int i = 0; i < ctx->n_lanes && pick < 0; i++) {
+static int take_lane(hp_ctx* ctx, AstarLane** L, int* idx, int* busy) {
+    int pick = -1, n_busy = 0;
+    for (int i = 0; i < ctx->n_lanes; i++) {
         AstarLane* l = (size_t)i < ctx->lanes.size() ? ctx->lanes[i] : nullptr;
-        if (!l) { pick = i; break; }
-        if (l->job) continue;
-        if (!l->used) { pick = i; break; }
-        const cudaError_t e = cudaEventQuery(l->ev_done);
-        if (e == cudaSuccess) pick = i; else cudaGetLastError();
+        bool idle = !l || !l->used;
+        if (l && l->used) {
+            const cudaError_t e = cudaEventQuery(l->ev_done);
+            if (e == cudaSuccess) idle = true; else cudaGetLastError();
+        }
+        if (!idle) n_busy++;
+        if (pick < 0 && idle && !(l && l->job)) pick = i;
     }
     if (pick < 0) {
         for (int k = 0; k < ctx->n_lanes; k++) {
@@ -371,10 +386,11 @@ static int take_lane(hp_ctx* ctx, AstarLane** L, int* idx) {
         }
         if (pick < 0) return fail(ctx, HP_ERR_INVALID_INPUT, "every lane holds an unfinished job: call hp_astar_wait on the oldest first");
         ctx->next_lane = (pick + 1) % ctx->n_lanes;
+        n_busy--;                       // the picked lane's batch precedes this one on the device
     }
     int rc = lane_get(ctx, pick, L);
     if (rc != HP_OK) return rc;
-    *idx = pick; ctx->last_lane = pick;
+    *idx = pick; ctx->last_lane = pick; *busy = std::max(0, n_busy);
     return HP_OK;
 }
 
@@ -383,12 +399,20 @@ int hp_astar_solve_device(hp_ctx* ctx, const hp_block_batch* batch, uint64_t n_v
     if (!ctx || !batch || !out) return HP_ERR_INVALID_INPUT;
     HP_CUDA(ctx, cudaSetDevice(ctx->device));
     AstarLane* L; int li;
-    int rc = take_lane(ctx, &L, &li);
+    int busy = 0;
+    int rc = take_lane(ctx, &L, &li, &busy);
     if (rc != HP_OK) return rc;
     if (L->job) return fail(ctx, HP_ERR_INVALID_INPUT, "lane busy with a submitted job: wait for it first");
-    rc = astar_device(ctx, L, batch, n_vars, n_reads, n_cells, max_block_vars, out, (cudaStream_t)stream, 0);
+    // The kernels run on the lane's own streams (one hardware queue each); the caller's stream only orders them: the lane
+    // starts after what the caller has enqueued so far, and the caller's stream continues once the lane is done.
+    HP_CUDA(ctx, cudaEventRecord(L->ev_in, (cudaStream_t)stream));
+    HP_CUDA(ctx, cudaStreamWaitEvent(L->stream, L->ev_in, 0));
+    rc = astar_device(ctx, L, batch, n_vars, n_reads, n_cells, max_block_vars, out, L->stream, 0, busy);
     if (rc != HP_OK) return rc;
-    return lane_mark_done(ctx, L, (cudaStream_t)stream);
+    rc = lane_mark_done(ctx, L, L->stream);
+    if (rc != HP_OK) return rc;
+    HP_CUDA(ctx, cudaStreamWaitEvent((cudaStream_t)stream, L->ev_done, 0));
+    return HP_OK;
 }
 
 static int validate_host_batch(hp_ctx* ctx, const hp_block_batch* b, uint32_t* max_n) {
@@ -414,7 +438,7 @@ static int validate_host_batch(hp_ctx* ctx, const hp_block_batch* b, uint32_t* m
 static uint8_t* carve(uint8_t*& p, size_t bytes) { uint8_t* r = p; p += (bytes + 255) & ~(size_t)255; return r; }
 
 // H2D + kernels + D2H of one host batch, all asynchronous on the lane's stream (no synchronisation).
-static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, hp_astar_out* out, uint32_t max_n, int max_ctas) {
+static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, hp_astar_out* out, uint32_t max_n, int max_ctas, int busy_lanes) {
     const uint32_t nb = b->n_blocks;
     const uint64_t n_vars = b->var_off[nb], n_reads = b->read_off[nb], n_cells = b->cell_off[n_reads];
     cudaStream_t st = L->stream;
@@ -450,7 +474,7 @@ static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b
     dout.heuristic = out->heuristic ? (uint64_t*)carve(q, 8 * (n_vars + nb)) : nullptr;
     dout.counters = out->counters ? (hp_astar_counters*)carve(q, sizeof(hp_astar_counters) * (size_t)nb) : nullptr;
 
-    int rc = astar_device(ctx, L, &d, n_vars, n_reads, n_cells, max_n, &dout, st, max_ctas);
+    int rc = astar_device(ctx, L, &d, n_vars, n_reads, n_cells, max_n, &dout, st, max_ctas, busy_lanes);
     if (rc != HP_OK) return rc;
     // ---- D2H ----
     HP_CUDA(ctx, cudaMemcpyAsync(out->h1, dout.h1, n_vars, cudaMemcpyDeviceToHost, st));
@@ -507,7 +531,7 @@ static int astar_host_retry(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, 
         // keep the slab arena under ~24 GB
         const uint64_t slab = astar_slab_bytes(ctx->qcap, (sub_max + 63) / 64, ctx->sub_capl);
         int max_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>(ctx->sm_count, (24ull << 30) / std::max<uint64_t>(slab, 1)));
-        int rc = astar_host_enqueue(ctx, L, &sb, &so, sub_max, max_ctas);
+        int rc = astar_host_enqueue(ctx, L, &sb, &so, sub_max, max_ctas, 0);
         if (rc == HP_OK && cudaStreamSynchronize(L->stream) != cudaSuccess) { cudaGetLastError(); rc = fail(ctx, HP_ERR_CUDA, "retry pass failed on the device"); }
         if (rc != HP_OK) { ctx->qcap = qcap0; return rc; }
         for (size_t k = 0; k < redo.size(); k++) {
@@ -533,13 +557,14 @@ int hp_astar_submit(hp_ctx* ctx, const hp_block_batch* b, hp_astar_out* out, hp_
         if (rc != HP_OK) return rc;
     }
     AstarLane* L; int li;
-    int rc = take_lane(ctx, &L, &li);
+    int busy = 0;
+    int rc = take_lane(ctx, &L, &li, &busy);
     if (rc != HP_OK) return rc;
     if (L->job) return fail(ctx, HP_ERR_INVALID_INPUT, "every lane holds an unfinished job: call hp_astar_wait on the oldest first");
     hp_astar_job* j = new hp_astar_job();
     j->lane = li; j->batch = *b; j->out = *out; j->max_n = max_n;
     if (b->n_blocks != 0) {
-        rc = astar_host_enqueue(ctx, L, b, out, max_n, 0);
+        rc = astar_host_enqueue(ctx, L, b, out, max_n, 0, busy);
         if (rc != HP_OK) { delete j; return rc; }
     }
     L->job = j;

@@ -50,7 +50,7 @@ int astar_max_ctas_per_sm(uint32_t sub_capl);
 // One A* lane: a stream and a private set of workspaces.  Batches in flight on different lanes overlap on the device.
 struct AstarLane {
     cudaStream_t stream = nullptr, aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_done = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_done = nullptr, ev_in = nullptr;
     bool used = false;                       // ev_done has been recorded at least once
     bool timing_pending = false;
     hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, stage_in, stage_out, dbg;

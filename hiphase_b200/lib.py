@@ -115,6 +115,16 @@ def lpt_partition(costs, n_shards):
     return shard_of
 
 
+def comm_unique_id():
+    """hp_comm_unique_id: the 128-byte NCCL id rank 0 hands to every rank (any out-of-band channel)."""
+    import numpy as np
+    uid = np.zeros(A.HP_COMM_ID_BYTES, np.uint8)
+    rc = lib().hp_comm_unique_id(A.ptr(uid, A.u8p))
+    if rc != A.HP_OK:
+        raise HiPhaseB200Error(rc, (lib().hp_last_error(None) or b"").decode())
+    return uid
+
+
 class PinnedArena:
     """Pinned host memory from hp_host_alloc, handed out as numpy views (kept alive by the arena)."""
 
