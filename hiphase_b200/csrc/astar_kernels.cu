@@ -32,9 +32,40 @@ __device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) {
     return a;
 }
 
-constexpr int kPrepThreads = 128;
+constexpr int kPrepThreads = 128;            // = reads per tile (one read per thread per tile)
+constexpr uint32_t kStageBytes = 4096;       // per array (alleles / quals) and stage
+constexpr uint32_t kPrepStages = 2;
 
+// ---- bulk-async (TMA) staging primitives: cp.async.bulk global -> shared, completion on an mbarrier ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One CTA per phase block.  The block's cells (alleles / quals, the reference's u8 layout) are streamed twice through a
+// two-stage shared-memory ring by the bulk-async copy engine (cp.async.bulk + mbarrier, 128-read tiles, 16-byte aligned
+// supersets of the tile's cell range), the per-variant coverage counters and active-list cursors live in shared memory
+// (blocks with more variants than the launch's cap fall back to the global arrays), and only the products leave the SM:
+// read metadata, bit-plane word records, active lists and column records.
 __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
+    extern __shared__ __align__(16) uint8_t prep_dyn[];
     const uint32_t b = blockIdx.x;
     if (b >= a.n_blocks) return;
     const uint64_t v0 = a.var_off[b], v1 = a.var_off[b + 1];
@@ -51,13 +82,74 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
     __shared__ uint8_t s_div[256];
     __shared__ uint32_t s_partial[kPrepThreads];
     __shared__ uint32_t s_g, s_planes, s_maxact;
+    __shared__ __align__(8) uint64_t s_bar[kPrepStages];
+
+    // dynamic shared memory: [stages x {alleles, quals} x kStageBytes] [cnt: (cap + 1) u32] [cur: (cap + 1) u16, packed]
+    uint8_t* const stage = prep_dyn;
+    uint32_t* const cnt_s = (uint32_t*)(prep_dyn + kPrepStages * 2 * kStageBytes);
+    uint32_t* const cur_s = cnt_s + (a.smem_cap + 1u);
+    const bool in_smem = N <= a.smem_cap;
+    // bulk copies need 16-byte aligned global addresses: true for the library's staging buffers, checked for callers' pointers
+    const bool aligned = ((((uintptr_t)a.alleles) | ((uintptr_t)a.quals)) & 15u) == 0;
+    const uint64_t bulk_limit = a.n_cells_total & ~15ull;            // no bulk copy may read past the arrays
 
     if (tid < 8) s_presence[tid] = 0;
-    if (tid == 0) { s_qsum = 0; s_status = HP_BLOCK_OK; s_maxspan = 0; s_maxact = 0; }
+    if (tid == 0) {
+        s_qsum = 0; s_status = HP_BLOCK_OK; s_maxspan = 0; s_maxact = 0;
+        for (uint32_t k = 0; k < kPrepStages; k++) mbar_init(&s_bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t* cnt = in_smem ? cnt_s : a.act_off + v0 + b;            // N + 1 entries
+    uint32_t* cur = a.act_cur + v0 + b;                              // (global fallback only)
+    if (in_smem) {
+        for (uint32_t i = tid; i <= N; i += kPrepThreads) cnt_s[i] = 0;
+        for (uint32_t i = tid; i <= N / 2; i += kPrepThreads) cur_s[i] = 0;
+    }
     __syncthreads();
 
-    uint32_t* cnt = a.act_off + v0 + b;   // N + 1 entries
-    uint32_t* cur = a.act_cur + v0 + b;
+    // ---- tile pipeline ----------------------------------------------------------------------------------------------
+    const uint32_t n_tiles = (R + kPrepThreads - 1) / kPrepThreads;
+    uint32_t phase_bits = 0;                                         // bit s = parity the next wait on stage s expects
+    struct Tile { uint64_t as; uint32_t bulk, span; bool staged; };
+    auto tile_of = [&](uint32_t t) {
+        Tile ti;
+        const uint64_t ra = r0 + (uint64_t)t * kPrepThreads, rb = min(ra + (uint64_t)kPrepThreads, r1);
+        const uint64_t cs = a.cell_off[ra], ce = a.cell_off[rb];
+        ti.as = cs & ~15ull;
+        const uint64_t ae = (ce + 15ull) & ~15ull;
+        ti.span = (uint32_t)min(ae - ti.as, (uint64_t)0xffffffffu);
+        ti.staged = aligned && ce >= cs && (ae - ti.as) <= kStageBytes;
+        const uint64_t be = min(ae, bulk_limit);
+        ti.bulk = (ti.staged && be > ti.as) ? (uint32_t)(be - ti.as) : 0u;
+        return ti;
+    };
+    auto issue = [&](uint32_t t) {                                   // every thread calls it; thread 0 drives the copy engine
+        const Tile ti = tile_of(t);
+        if (!ti.staged) return;
+        const uint32_t s = t % kPrepStages;
+        uint8_t* sa = stage + (size_t)s * 2 * kStageBytes;
+        uint8_t* sq = sa + kStageBytes;
+        if (tid == 0 && ti.bulk) {
+            fence_proxy_async();                                     // the stage was read through the generic proxy before
+            mbar_expect_tx(&s_bar[s], 2u * ti.bulk);
+            bulk_g2s(sa, a.alleles + ti.as, ti.bulk, &s_bar[s]);
+            bulk_g2s(sq, a.quals + ti.as, ti.bulk, &s_bar[s]);
+        }
+        // the last (< 16 byte) piece of the arrays cannot be bulk-copied: plain loads
+        const uint64_t tail0 = ti.as + ti.bulk, tail1 = min(ti.as + (uint64_t)ti.span, a.n_cells_total);
+        if (tail0 + (uint64_t)tid < tail1 && tid < 16) {
+            sa[ti.bulk + tid] = a.alleles[tail0 + tid];
+            sq[ti.bulk + tid] = a.quals[tail0 + tid];
+        }
+    };
+    auto wait_tile = [&](uint32_t t, const Tile& ti) {
+        const uint32_t s = t % kPrepStages;
+        if (ti.bulk) {
+            while (!mbar_try_wait(&s_bar[s], (phase_bits >> s) & 1u)) {}
+            phase_bits ^= 1u << s;
+        }
+        __syncthreads();                                             // the plain-load tail, and a common starting line
+    };
 
     // ---- pass 1: validate, count coverage, collect the set of quality values ----
     {
@@ -66,27 +158,41 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
         int status = HP_BLOCK_OK;
         uint32_t maxspan = 0;
         if (N == 0) status = HP_BLOCK_ASSERT;
-        for (uint64_t r = r0 + tid; r < r1; r += kPrepThreads) {
-            const uint32_t s = a.read_start[r], e = a.read_end[r];
-            const uint64_t c = a.cell_off[r];
-            if (e < s || e > N || a.cell_off[r + 1] - c != (uint64_t)(e - s)) { status = HP_BLOCK_ASSERT; continue; }
-            maxspan = max(maxspan, e - s);
-            ReadMeta rm;
-            rm.start = s; rm.end = e; rm.word_idx = (uint32_t)(c / 64 + r); rm.cell_rel = (uint32_t)(c - c0);
-            a.rmeta[r] = rm;
-            for (uint32_t i = 0; i < e - s; i++) {
-                const uint8_t al = a.alleles[c + i];
-                const uint8_t q = a.quals[c + i];
-                const uint32_t p = s + i;
-                if (al > 3) status = HP_BLOCK_ASSERT;
-                if (a.ignored[v0 + p]) {
-                    if (al != HP_ALLELE_NOOVERLAP && status == HP_BLOCK_OK) status = HP_BLOCK_IGNORED_NOT_NOOVERLAP;
-                } else {
-                    pres[q >> 5] |= 1u << (q & 31);
-                    qsum += q;
+        if (n_tiles) issue(0);
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            if (t + 1 < n_tiles) issue(t + 1);
+            const Tile ti = tile_of(t);
+            wait_tile(t, ti);
+            const uint64_t r = r0 + (uint64_t)t * kPrepThreads + tid;
+            if (r < r1) {
+                const uint32_t s = a.read_start[r], e = a.read_end[r];
+                const uint64_t c = a.cell_off[r];
+                if (e < s || e > N || a.cell_off[r + 1] - c != (uint64_t)(e - s) ||
+                    (ti.staged && (c < ti.as || c + (e - s) > ti.as + ti.span))) status = HP_BLOCK_ASSERT;
+                else {
+                    maxspan = max(maxspan, e - s);
+                    ReadMeta rm;
+                    rm.start = s; rm.end = e; rm.word_idx = (uint32_t)(c / 64 + r); rm.cell_rel = (uint32_t)(c - c0);
+                    a.rmeta[r] = rm;
+                    const uint8_t* sa = stage + (size_t)(t % kPrepStages) * 2 * kStageBytes;
+                    const uint8_t* pa = ti.staged ? sa + (c - ti.as) : a.alleles + c;
+                    const uint8_t* pq = ti.staged ? sa + kStageBytes + (c - ti.as) : a.quals + c;
+                    for (uint32_t i = 0; i < e - s; i++) {
+                        const uint8_t al = pa[i];
+                        const uint8_t q = pq[i];
+                        const uint32_t p = s + i;
+                        if (al > 3) status = HP_BLOCK_ASSERT;
+                        if (a.ignored[v0 + p]) {
+                            if (al != HP_ALLELE_NOOVERLAP && status == HP_BLOCK_OK) status = HP_BLOCK_IGNORED_NOT_NOOVERLAP;
+                        } else {
+                            pres[q >> 5] |= 1u << (q & 31);
+                            qsum += q;
+                        }
+                        atomicAdd(&cnt[p], 1u);
+                    }
                 }
-                atomicAdd(&cnt[p], 1u);
             }
+            __syncthreads();                                         // stage t % 2 is free again
         }
         for (int k = 0; k < 8; k++) if (pres[k]) atomicOr(&s_presence[k], pres[k]);
         if (qsum) atomicAdd(&s_qsum, qsum);
@@ -113,7 +219,7 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
     const uint32_t lo = min(N + 1, tid * chunk), hi = min(N + 1, lo + chunk);
     {
         uint32_t sum = 0, mx = 0;
-        for (uint32_t i = lo; i < hi; i++) { const uint32_t x = __ldcg(&cnt[i]); sum += x; mx = max(mx, x); }
+        for (uint32_t i = lo; i < hi; i++) { const uint32_t x = in_smem ? cnt_s[i] : __ldcg(&cnt[i]); sum += x; mx = max(mx, x); }
         s_partial[tid] = sum;
         if (mx) atomicMax(&s_maxact, mx);
     }
@@ -125,44 +231,69 @@ __global__ void __launch_bounds__(kPrepThreads) astar_prep_kernel(PrepArgs a) {
     __syncthreads();
     {
         uint32_t run = s_partial[tid];
-        for (uint32_t i = lo; i < hi; i++) { uint32_t x = __ldcg(&cnt[i]); __stcg(&cnt[i], run); run += x; }
+        if (in_smem) for (uint32_t i = lo; i < hi; i++) { uint32_t x = cnt_s[i]; cnt_s[i] = run; run += x; }
+        else for (uint32_t i = lo; i < hi; i++) { uint32_t x = __ldcg(&cnt[i]); __stcg(&cnt[i], run); run += x; }
     }
     __syncthreads();
+    if (in_smem) {
+        uint32_t* aoff = a.act_off + v0 + b;
+        for (uint32_t i = tid; i <= N; i += kPrepThreads) aoff[i] = cnt_s[i];
+    }
 
     if (tid == 0 && s_maxact >= 0xffffu && s_status == HP_BLOCK_OK) s_status = HP_BLOCK_TOO_DENSE;
     __syncthreads();
     // ---- pass 2: bit planes, active lists and column records ----
     if (s_status == HP_BLOCK_OK) {
-        for (uint64_t r = r0 + tid; r < r1; r += kPrepThreads) {
-            const uint32_t s = a.read_start[r], e = a.read_end[r];
-            const uint64_t c = a.cell_off[r];
-            uint64_t* rec = a.planes + (uint64_t)(c / 64 + r) * HP_PLANE_STRIDE;
-            uint64_t w[HP_PLANE_STRIDE];
+        if (n_tiles) issue(0);
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            if (t + 1 < n_tiles) issue(t + 1);
+            const Tile ti = tile_of(t);
+            wait_tile(t, ti);
+            const uint64_t r = r0 + (uint64_t)t * kPrepThreads + tid;
+            if (r < r1) {
+                const uint32_t s = a.read_start[r], e = a.read_end[r];
+                const uint64_t c = a.cell_off[r];
+                const uint8_t* sa = stage + (size_t)(t % kPrepStages) * 2 * kStageBytes;
+                const uint8_t* pa = ti.staged ? sa + (c - ti.as) : a.alleles + c;
+                const uint8_t* pq = ti.staged ? sa + kStageBytes + (c - ti.as) : a.quals + c;
+                uint64_t* rec = a.planes + (uint64_t)(c / 64 + r) * HP_PLANE_STRIDE;
+                uint64_t w[HP_PLANE_STRIDE];
 #pragma unroll
-            for (int k = 0; k < (int)HP_PLANE_STRIDE; k++) w[k] = 0;
-            uint32_t prev_slot = 0xffffu;            // slot of this read in the previous column's active list
-            for (uint32_t i = 0; i < e - s; i++) {
-                const uint8_t al = a.alleles[c + i];
-                const uint32_t p = s + i;
-                // quality of an ignored column can never be charged (the haplotype is Ambiguous there): drop it
-                const uint32_t q = a.ignored[v0 + p] ? 0u : (uint32_t)s_div[a.quals[c + i]];
-                const uint64_t bit = 1ull << (i & 63);
-                if (al & 1) w[0] |= bit;          // allele bit (meaningful for 0/1; 3 sets it too but nb masks it)
-                if (al >= 2) w[1] |= bit;         // non-binary: mismatches both 0 and 1
+                for (int k = 0; k < (int)HP_PLANE_STRIDE; k++) w[k] = 0;
+                uint32_t prev_slot = 0xffffu;        // slot of this read in the previous column's active list
+                for (uint32_t i = 0; i < e - s; i++) {
+                    const uint8_t al = pa[i];
+                    const uint8_t qraw = pq[i];
+                    const uint32_t p = s + i;
+                    // quality of an ignored column can never be charged (the haplotype is Ambiguous there): drop it
+                    const uint32_t q = a.ignored[v0 + p] ? 0u : (uint32_t)s_div[qraw];
+                    const uint64_t bit = 1ull << (i & 63);
+                    if (al & 1) w[0] |= bit;          // allele bit (meaningful for 0/1; 3 sets it too but nb masks it)
+                    if (al >= 2) w[1] |= bit;         // non-binary: mismatches both 0 and 1
 #pragma unroll
-                for (int k = 0; k < 8; k++) if (q >> k & 1u) w[2 + k] |= bit;
-                const uint32_t slot = atomicAdd(&cur[p], 1u);
-                const uint64_t at = c0 + __ldcg(&cnt[p]) + slot;
-                a.act_idx[at] = (uint32_t)(r - r0);
-                // column record: qual | allele<<8 | ends<<10 | carry<<16 (carry = slot in column p-1, 0xffff = read starts here)
-                a.col[at] = (uint32_t)a.quals[c + i] | ((uint32_t)al << 8) | ((i + 1 == e - s) ? (1u << 10) : 0u) | (prev_slot << 16);
-                prev_slot = slot;
-                if ((i & 63) == 63 || i + 1 == e - s) {
+                    for (int k = 0; k < 8; k++) if (q >> k & 1u) w[2 + k] |= bit;
+                    uint32_t slot, off;
+                    if (in_smem) {
+                        const uint32_t sh = (p & 1u) * 16u;
+                        slot = (atomicAdd(&cur_s[p >> 1], 1u << sh) >> sh) & 0xffffu;     // maxact < 0xffff: no carry across halves
+                        off = cnt_s[p];
+                    } else {
+                        slot = atomicAdd(&cur[p], 1u);
+                        off = __ldcg(&cnt[p]);
+                    }
+                    const uint64_t at = c0 + off + slot;
+                    a.act_idx[at] = (uint32_t)(r - r0);
+                    // column record: qual | allele<<8 | ends<<10 | carry<<16 (carry = slot in column p-1, 0xffff = read starts here)
+                    a.col[at] = (uint32_t)qraw | ((uint32_t)al << 8) | ((i + 1 == e - s) ? (1u << 10) : 0u) | (prev_slot << 16);
+                    prev_slot = slot;
+                    if ((i & 63) == 63 || i + 1 == e - s) {
 #pragma unroll
-                    for (int k = 0; k < (int)HP_PLANE_STRIDE; k++) { rec[k] = w[k]; w[k] = 0; }
-                    rec += HP_PLANE_STRIDE;
+                        for (int k = 0; k < (int)HP_PLANE_STRIDE; k++) { rec[k] = w[k]; w[k] = 0; }
+                        rec += HP_PLANE_STRIDE;
+                    }
                 }
             }
+            __syncthreads();
         }
     }
     if (tid == 0) {
@@ -2194,6 +2325,26 @@ __global__ void __launch_bounds__(kMaxTeam * 32, HP_CTAS_PER_SM) astar_solve_ker
 
 }  // namespace hp
 
+// Test aid: score_planes (= ReadSegment::score_partial_haplotype for h1 and h2, read_segments.rs:177-206) of every read of
+// block 0 against two haplotypes given as bit masks (bit j = allele at haplotype position j), problem offset and length.
+namespace hp {
+__global__ void score_planes_debug_kernel(AstarArgs a, uint64_t h1, uint64_t h2, int offset, int L, uint32_t* s1, uint32_t* s2) {
+    const BlkMeta m = a.meta[0];
+    auto hap = [&](int which, int i0) { return shift_signed(which ? h2 : h1, i0); };
+    for (uint32_t r = threadIdx.x; r < m.n_reads; r += blockDim.x) {
+        const ReadMeta rm = a.rmeta[m.read_base + r];
+        uint32_t x1, x2;
+        score_planes(a, m, rm, offset - (int)rm.start, L, hap, x1, x2);
+        s1[r] = x1; s2[r] = x2;
+    }
+}
+cudaError_t launch_score_planes_debug(const AstarArgs& a, uint64_t h1, uint64_t h2, int offset, int L, uint32_t* s1, uint32_t* s2,
+                                      cudaStream_t stream) {
+    score_planes_debug_kernel<<<1, 128, 0, stream>>>(a, h1, h2, offset, L, s1, s2);
+    return cudaGetLastError();
+}
+}  // namespace hp
+
 // ---- host-side launchers (called from hp_api.cu) ---------------------------------------------------------------
 namespace hp {
 
@@ -2209,9 +2360,14 @@ uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl) 
     return ((slab_bytes_for(qcap, hap_words) + spill + 255) & ~255ull);
 }
 
-cudaError_t launch_astar_prep(const PrepArgs& pa, cudaStream_t stream) {
+// smem_cap (variants per block whose coverage counters fit shared memory) is chosen here from the largest block of the batch.
+cudaError_t launch_astar_prep(PrepArgs pa, uint32_t max_block_vars, cudaStream_t stream) {
     if (pa.n_blocks == 0) return cudaSuccess;
-    astar_prep_kernel<<<pa.n_blocks, kPrepThreads, 0, stream>>>(pa);
+    pa.smem_cap = std::min<uint32_t>(std::max<uint32_t>(max_block_vars, 64u), 8190u) | 1u;     // odd: (cap + 1) u32 + (cap + 1) u16 stay 4-aligned
+    const size_t smem = (size_t)kPrepStages * 2 * kStageBytes + 4ull * (pa.smem_cap + 1) + 2ull * (pa.smem_cap + 1);
+    cudaError_t e = cudaFuncSetAttribute(astar_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    astar_prep_kernel<<<pa.n_blocks, kPrepThreads, smem, stream>>>(pa);
     return cudaGetLastError();
 }
 

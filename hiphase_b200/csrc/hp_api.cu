@@ -191,7 +191,8 @@ int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_
     pa.ignored = batch->ignored;
     pa.meta = (BlkMeta*)L->meta.ptr; pa.rmeta = (ReadMeta*)L->rmeta.ptr; pa.planes = (uint64_t*)L->planes.ptr;
     pa.act_off = (uint32_t*)L->act_off.ptr; pa.act_cur = (uint32_t*)L->act_cur.ptr; pa.act_idx = (uint32_t*)L->act_idx.ptr; pa.col = (uint32_t*)L->col.ptr;
-    HP_CUDA(ctx, launch_astar_prep(pa, stream));
+    pa.n_cells_total = n_cells; pa.smem_cap = 0;
+    HP_CUDA(ctx, launch_astar_prep(pa, max_block_vars, stream));
     ctx->launches++;
 
     uint32_t* class_info = (uint32_t*)((uint8_t*)L->ticket.ptr + 256);
@@ -331,6 +332,27 @@ int hp_ctx_set_lanes(hp_ctx* ctx, int lanes) {
 int hp_debug_set_team(hp_ctx* ctx, int team) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->force_team = team; return HP_OK; }
 // bit 0: build the WFA graphs on the host (A/B aid); bit 1: no workspace hint (exercises the regrow path)
 int hp_debug_wfa_build_mode(hp_ctx* ctx, int mode) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->wfa_host_build = (mode & 1) != 0; ctx->wfa_no_hint = (mode & 2) != 0; return HP_OK; }
+// Test aid (not in the public header): scores every read of block 0 of the batch last solved on this context with the device's
+// bit-plane scorer (score_planes) against haplotypes h1 / h2 (bit j = allele at haplotype position j) over
+// [offset, offset + len): the device counterpart of ReadSegment::score_partial_haplotype (read_segments.rs:177-206).
+int hp_debug_score_partial(hp_ctx* ctx, uint64_t h1, uint64_t h2, uint32_t offset, uint32_t len, uint32_t n_reads,
+                           uint32_t* s1, uint32_t* s2) {
+    if (!ctx || !s1 || !s2 || len > 64 || n_reads == 0) return HP_ERR_INVALID_INPUT;
+    AstarLane* L = (size_t)ctx->last_lane < ctx->lanes.size() ? ctx->lanes[ctx->last_lane] : nullptr;
+    if (!L || !L->meta.ptr || !L->planes.ptr) return fail(ctx, HP_ERR_INVALID_INPUT, "no solved batch on this context");
+    HP_CUDA(ctx, cudaSetDevice(ctx->device));
+    HP_CUDA(ctx, cudaStreamSynchronize(L->stream));
+    if (!ctx->stage_out.reserve(8ull * n_reads)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "debug buffer allocation failed");
+    AstarArgs a{};
+    a.meta = (const BlkMeta*)L->meta.ptr; a.rmeta = (const ReadMeta*)L->rmeta.ptr; a.planes = (const uint64_t*)L->planes.ptr;
+    uint32_t* d1 = (uint32_t*)ctx->stage_out.ptr; uint32_t* d2 = d1 + n_reads;
+    HP_CUDA(ctx, cudaMemsetAsync(d1, 0xff, 8ull * n_reads, L->stream));
+    HP_CUDA(ctx, launch_score_planes_debug(a, h1, h2, (int)offset, (int)len, d1, d2, L->stream));
+    HP_CUDA(ctx, cudaMemcpyAsync(s1, d1, 4ull * n_reads, cudaMemcpyDeviceToHost, L->stream));
+    HP_CUDA(ctx, cudaMemcpyAsync(s2, d2, 4ull * n_reads, cudaMemcpyDeviceToHost, L->stream));
+    HP_CUDA(ctx, cudaStreamSynchronize(L->stream));
+    return HP_OK;
+}
 int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
 int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
     if (!ctx || !out || n_blocks > ctx->dbg_blocks) return HP_ERR_INVALID_INPUT;

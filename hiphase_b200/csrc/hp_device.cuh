@@ -91,6 +91,8 @@ struct PrepArgs {
     uint32_t* act_cur;   // zero-initialised cursors
     uint32_t* act_idx;
     uint32_t* col;
+    uint64_t n_cells_total;   // length of alleles / quals (bulk copies never read past it)
+    uint32_t smem_cap;        // blocks with at most this many variants keep their coverage counters in shared memory
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

@@ -173,3 +173,62 @@ def test_full_c2_properties(ctx):
         v0, v1 = int(batch.var_off[i]), int(batch.var_off[i + 1])
         s0 = int(sub.var_off[k])
         assert np.array_equal(out.h1[v0:v1], ref.h1[s0:s0 + v1 - v0]) and out.stats[i] == ref.stats[k]
+
+
+# ---- parity corners named by the round-1 review ----------------------------------------------------------------------
+@pytest.mark.parametrize("n_var", [1023, 1024, 1500, 2000])
+def test_large_noisy_blocks_prune_across_the_length_count_boundary(ctx, n_var):
+    """Noisy blocks (p_err 0.15) with more than 1023 variants: the tracker's length counts no longer fit the shared-memory
+    window (lencnt_cap_s) AND the main queue prunes (astar_phaser.rs:171-231, 545-582).  The C3 straggler class."""
+    blocks = []
+    for k in range(2):
+        rng = np.random.default_rng(7000 + n_var + k)
+        blocks.append(synth.gen_block(rng, n_var, int(30 * n_var / 12.0), synth._normal_span(12, 4, 2, 40), 0.15, 0.03, 0.01))
+    batch = A.BlockBatch.from_blocks(blocks)
+    assert int(np.diff(batch.var_off.astype(np.int64)).min()) == n_var
+    out, ref = run_both(ctx, batch)
+    assert (ref.stats["pruned_solutions"] > 0).all()
+
+
+def test_c3_stream_stratified_500(ctx):
+    """500 blocks of the C3 stream (every 20th of the 10 000 bench.py times), bit-exact incl. H[] and the work counters."""
+    batch = synth.stream_blocks(np.arange(7, 10000, 20, dtype=np.uint64))
+    out, ref = run_both(ctx, batch)
+    assert (ref.stats["pruned_solutions"] > 0).sum() >= 3
+
+
+def test_score_planes_known_answers(ctx):
+    """The device's bit-plane scorer against the reference's own known answers for score_haplotype /
+    score_partial_haplotype (read_segments.rs:230-275: 6 / 0 / 28 and the partial sums 27, 25, 22, 18, 13, 7)."""
+    import ctypes as C
+    from helpers import golden
+    g = golden("read_segments.json")
+    L = lib.lib()
+    L.hp_debug_score_partial.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, A.u32p, A.u32p]
+    for key in ("score_haplotype", "score_partial_haplotype"):
+        case = g[key]
+        al, ql = np.array(case["alleles"], np.uint8), np.array(case["quals"], np.uint8)
+        setpos = np.flatnonzero(al < 2)
+        s, e = int(setpos[0]), int(setpos[-1]) + 1                      # ReadSegment::new clipping (read_segments.rs:40-62)
+        block = {"n_var": len(al), "reads": [(s, al[s:e], ql[s:e])]}
+        batch = A.BlockBatch.from_blocks([block])
+        ctx.astar_solve_batch(batch)                                     # leaves the prep products of this block on the lane
+        checked = 0
+        for c in case["cases"]:
+            hap = np.array(c["hap"], np.uint8)
+            if (hap >= 2).any():
+                # an Ambiguous haplotype allele only occurs at ignored variants, whose quality the prep kernel drops:
+                # that case is covered through hp_post_solve_batch (score_haplotype) in test_post_solve.py
+                continue
+            bits = sum(int(x) << j for j, x in enumerate(hap))
+            inv = sum((1 - int(x)) << j for j, x in enumerate(hap))
+            s1 = np.zeros(1, np.uint32); s2 = np.zeros(1, np.uint32)
+            rc = L.hp_debug_score_partial(ctx.handle, bits, inv, c["offset"], len(hap), 1, A.ptr(s1, A.u32p), A.ptr(s2, A.u32p))
+            assert rc == 0
+            assert int(s1[0]) == c["score"], (key, c, int(s1[0]))
+            # the complementary haplotype mismatches exactly the other binary cells
+            tot = int(ql[max(s, c["offset"]):min(e, c["offset"] + len(hap))][al[max(s, c["offset"]):min(e, c["offset"] + len(hap))] < 2].sum())
+            nb = int(ql[max(s, c["offset"]):min(e, c["offset"] + len(hap))][al[max(s, c["offset"]):min(e, c["offset"] + len(hap))] >= 2].sum())
+            assert int(s1[0]) + int(s2[0]) == tot + 2 * nb
+            checked += 1
+        assert checked >= 2
