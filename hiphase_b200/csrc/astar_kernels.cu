@@ -744,6 +744,12 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         pay[idx] = make_uint4((uint32_t)h1, (uint32_t)(h1 >> 32), (uint32_t)h2, (uint32_t)(h2 >> 32) | (tag << 24));
     };
 
+    // A sub-solve whose dive never breaks (the best child stays the queue minimum all the way to the clip: ~95 % of them on
+    // HiFi-like data) never reads what it pushed.  So the first attempt is LAZY: siblings are not stored, only their
+    // minimum key is tracked; if the dive would break, the sub-solve starts over with a real queue.  Same results.
+    const uint64_t c_pops = w.pops, c_evals = w.evals, c_lp = w.sum_lp, c_cells = w.cells;
+    bool lazy = true;
+restart:
     // queue state
     uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
@@ -773,6 +779,11 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
     for (;;) {
         if (kCount) tq = clock64();
         if (qmin < mk64(cur_total, cur_lo)) {
+            if (lazy) {                                                  // start over, this time keeping the siblings
+                lazy = false;
+                if (kCount) { w.pops = c_pops; w.evals = c_evals; w.sum_lp = c_lp; w.cells = c_cells; }
+                goto restart;
+            }
             if (kCount) w.ns_real++;
             // ---- the dive broke: cur goes back to the queue, then a real pop of the entry whose key is qmin ----
             {
@@ -865,7 +876,11 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         uint32_t s1[K], s2[K], wv[K];
         if (cur_src == SRC_CACHE) {
 #pragma unroll
-            for (int k = 0; k < K; k++) { s1[k] = cur_x1 ? nA1[k] : nA0[k]; s2[k] = cur_x2 ? nB1[k] : nB0[k]; wv[k] = nW[k]; }
+            for (int k = 0; k < K; k++) {
+                // slots beyond the column's coverage hold nothing (warp-uniform test): their work is skipped below as well
+                if (k == 0 || a_cur > 32u * k) { s1[k] = cur_x1 ? nA1[k] : nA0[k]; s2[k] = cur_x2 ? nB1[k] : nB0[k]; wv[k] = nW[k]; }
+                else { s1[k] = 0; s2[k] = 0; wv[k] = 0; }
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < K; k++) { s1[k] = 0; s2[k] = 0; wv[k] = 0; }
@@ -888,6 +903,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
         uint64_t cells = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
+            if (k > 0 && a_cur <= 32u * k) { A0[k] = A1[k] = B0[k] = B1[k] = 0; continue; }      // empty slot: contributes nothing
             const uint32_t c = colc[k];
             const uint32_t q = bad_col ? 0u : (c & 0xffu);
             const uint32_t al = (c >> 8) & 3u;
@@ -925,6 +941,12 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
             const uint32_t a_next = o_p2 - o_p1;
 #pragma unroll
             for (int k = 0; k < K; k++) {
+                if (k > 0 && a_next <= 32u * k) {                        // the next column has no read in this slot
+                    nA0[k] = nA1[k] = nB0[k] = nB1[k] = nW[k] = 0;
+                    colc[k] = kEmpty;
+                    coln[k] = colnn[k];
+                    continue;
+                }
                 const uint32_t cn = (lane + 32u * k < a_next) ? coln[k] : kEmpty;
                 const uint32_t carry = cn >> 16, sl = carry & 31u;
                 uint32_t g0 = __shfl_sync(HP_FULL_MASK, A0[0], sl), g1 = __shfl_sync(HP_FULL_MASK, A1[0], sl);
@@ -932,6 +954,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                 uint32_t gw = kCount ? __shfl_sync(HP_FULL_MASK, wv[0], sl) : 0u;
 #pragma unroll
                 for (int kk = 1; kk < K; kk++) {
+                    if (a_cur <= 32u * kk) continue;                     // nothing to carry out of an empty slot
                     const uint32_t u0 = __shfl_sync(HP_FULL_MASK, A0[kk], sl), u1 = __shfl_sync(HP_FULL_MASK, A1[kk], sl);
                     const uint32_t u2 = __shfl_sync(HP_FULL_MASK, B0[kk], sl), u3 = __shfl_sync(HP_FULL_MASK, B1[kk], sl);
                     const uint32_t uw = kCount ? __shfl_sync(HP_FULL_MASK, wv[kk], sl) : 0u;
@@ -949,7 +972,7 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
 
         // ---- push the siblings of the best child: candidate c is handled by lane (rr + c) & 31, into its own stripe.
         //      The entry keeps the PARENT's haplotypes and the candidate slot as a tag. ----
-        {
+        if (!lazy) {
             const uint32_t c = (lane - rr) & 31u;
             const bool mine = c < 4u && ((present >> c) & 1u) && c != best;
             const uint32_t rsel = (c & 2u) ? r1 : r0;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-block cycles on the C3 stream (first n blocks), per team size: total work vs the slowest chain.
-usage: python profiles/stream_cycles.py [n_blocks] [out_prefix]"""
+usage: python profiles/stream_cycles.py [n_blocks] [out_prefix|-] [teams, e.g. 1,2]"""
 import ctypes as C, sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -11,7 +11,7 @@ batch = synth.config_c3_stream(nb)
 nvar = np.diff(batch.var_off.astype(np.int64))
 _, noisy = synth.stream_headers(0, nb)
 L = lib.lib()
-for team in (1, 2, 4):
+for team in ([int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else (1, 2, 4)):
     ctx = lib.Context(device=0)
     ctx.set_team(team)
     for _ in range(2):
@@ -29,6 +29,6 @@ for team in (1, 2, 4):
           % (team, kms, dt * 1e3, ctx.last_kernel_ms(), tot.sum(), d[:, 0].sum(), d[:, 1].sum(), tot.max(), tot[noisy == 0].sum(), tot[noisy == 1].sum()))
     print("   top blocks [id, N, noisy, Mcycles]:", [(int(k), int(nvar[k]), int(noisy[k]), round(tot[k] / 1e6)) for k in top[:12]])
     print("   blocks over 50 / 100 / 200 Mcycles:", int((tot > 50e6).sum()), int((tot > 100e6).sum()), int((tot > 200e6).sum()))
-    if prefix:
+    if prefix and prefix != '-':
         np.save("%s_team%d.npy" % (prefix, team), d)
     ctx.close()
