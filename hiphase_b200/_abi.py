@@ -33,6 +33,8 @@ HP_COMM_ID_BYTES = 128
 HP_WFA_OK = 0
 HP_WFA_MAX_EDIT_DISTANCE = 1
 HP_WFA_SKIPPED = 2
+HP_WFA_WORKSPACE_OVERFLOW = 3
+HP_WFA_GRAPH_TOO_LARGE = 4
 
 # VariantType (src/data_types/variants.rs:8-31)
 VT_SNV, VT_INSERTION, VT_DELETION, VT_INDEL, VT_SV_INSERTION, VT_SV_DELETION = 0, 1, 2, 3, 4, 5

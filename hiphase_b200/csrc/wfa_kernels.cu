@@ -9,8 +9,8 @@
 // extension + union of the sets that reach it".  Extension only depends on (node, diagonal, offset), so here a wave
 // is extended when it is PUSHED and immediately reduced into its (node, diagonal) slot of a per-warp open-addressing
 // hash table in HBM/L2: slot = {max-front record, and for each of the two live ED generations: end offset +
-// traversed-node bitset}.  Per ED the warp walks the active nodes in topological order (a 1024-bit node mask lives
-// in registers, one word per lane); lanes = the node's live diagonals.  Pushes are issued in phases
+// traversed-node bitset}.  Per ED the warp walks the active nodes in topological order (a 1024- or 4096-bit node mask lives
+// in registers, one or four words per lane); lanes = the node's live diagonals.  Pushes are issued in phases
 // (diag-1, diag, diag+1, then one phase per child) so that no two lanes of a phase touch the same slot.
 // Results do not depend on the visiting order of diagonals (everything cross-diagonal is a max or a set union).
 #include <algorithm>
@@ -78,7 +78,7 @@ struct WfaArgs {
     uint64_t* out_counters;        // optional [n_jobs * 4]
 };
 
-constexpr uint32_t kWfaMaxNodes = 1024;          // node activity mask: one 32-bit word per lane
+constexpr uint32_t kWfaMaxNodes = 4096;          // node activity mask: MW 32-bit words per lane (kernel variants MW = 1, 4)
 constexpr uint32_t kNil = 0xffffffffu;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr int kWfaWarps = 8;
@@ -241,6 +241,7 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
     if (c.used > c.cap / 2) c.overflow = true;
 }
 
+template <int MW>
 __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gwarp = blockIdx.x * kWfaWarps + (threadIdx.x >> 5);
@@ -260,7 +261,8 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
         c.n_cmp = c.n_waves = c.n_setops = 0;
         const uint32_t n_nodes = job.n_nodes;
         const uint32_t sw = (n_nodes + 63) / 64;
-        if (status == HP_WFA_OK && (n_nodes == 0 || n_nodes > kWfaMaxNodes || sw > a.set_words_max)) status = HP_WFA_WORKSPACE_OVERFLOW;
+        if (status == HP_WFA_OK && n_nodes > 1024u * MW) status = HP_WFA_GRAPH_TOO_LARGE;
+        if (status == HP_WFA_OK && (n_nodes == 0 || sw > a.set_words_max)) status = HP_WFA_WORKSPACE_OVERFLOW;
 
         // output row defaults: NoOverlap / 0 (read_parsing.rs:790, 803)
         for (uint32_t i = lane; i < job.row_len; i += 32) { a.out_alleles[job.row_off + i] = HP_ALLELE_NOOVERLAP; a.out_quals[job.row_off + i] = 0; }
@@ -283,8 +285,10 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
             }
             __syncwarp();
 
-            // node activity masks: lane l owns nodes [32l, 32l+32)
-            uint32_t act_cur = 0, act_next = 0;
+            // node activity masks: word w of lane l owns nodes [1024w + 32l, 1024w + 32l + 32)
+            uint32_t act_cur[MW], act_next[MW];
+#pragma unroll
+            for (int w = 0; w < MW; w++) { act_cur[w] = 0; act_next[w] = 0; }
             uint32_t n_items_next = 0;             // items appended to the next generation's list so far (uniform)
 
             // ---- initial wave: node 0, diagonal 0, offset 0, set {0} (wfa_graph.rs:366-378) ----
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
                 __syncwarp();
                 bool first; uint32_t slot;
                 wfa_push(c, lane == 0, 0u, 0, 0u, seed, 0u, 0u, 0, first, slot);
-                if (lane == 0) { c.s.items[0][0] = slot; c.s.seg_start[0][0] = 0; c.s.seg_len[0][0] = 1; act_cur = 1u; }
+                if (lane == 0) { c.s.items[0][0] = slot; c.s.seg_start[0][0] = 0; c.s.seg_len[0][0] = 1; act_cur[0] = 1u; }
                 c.used = 1;
                 __syncwarp();
             }
@@ -306,12 +310,18 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
                 n_items_next = 0;
                 // ---- nodes with pending waves, ascending (wfa_graph.rs:406) ----
                 for (;;) {
-                    const uint32_t lanes_with = __ballot_sync(HP_FULL_MASK, act_cur != 0);
-                    if (lanes_with == 0) break;
-                    const uint32_t wl = __ffs(lanes_with) - 1;
-                    const uint32_t word = __shfl_sync(HP_FULL_MASK, act_cur, wl);
-                    const uint32_t n = wl * 32 + (__ffs(word) - 1);
-                    if (lane == wl) act_cur &= act_cur - 1;                 // clear the lowest set bit
+                    uint32_t n = kNil;
+#pragma unroll
+                    for (int w = 0; w < MW; w++) {
+                        if (n != kNil) continue;
+                        const uint32_t lanes_with = __ballot_sync(HP_FULL_MASK, act_cur[w] != 0);
+                        if (lanes_with == 0) continue;
+                        const uint32_t wl = __ffs(lanes_with) - 1;
+                        const uint32_t word = __shfl_sync(HP_FULL_MASK, act_cur[w], wl);
+                        n = 1024u * w + wl * 32 + (__ffs(word) - 1);
+                        if (lane == wl) act_cur[w] &= act_cur[w] - 1;      // clear the lowest set bit
+                    }
+                    if (n == kNil) break;
 
                     const WfaNode nd = c.nodes[n];
                     const uint32_t node_len = nd.len;
@@ -413,7 +423,8 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
                                 const uint32_t pos = n_items_next + __popc(fm & ((1u << lane) - 1u));
                                 if (first && pos < c.cap) c.s.items[gn][pos] = slot;
                                 n_items_next += __popc(fm);
-                                if (lane == (n >> 5)) act_next |= 1u << (n & 31);
+#pragma unroll
+                                for (int w = 0; w < MW; w++) if ((n >> 10) == (uint32_t)w && lane == ((n >> 5) & 31u)) act_next[w] |= 1u << (n & 31);
                             }
                             __syncwarp();
                         }
@@ -432,7 +443,8 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
                                         if (first) ch[2 + __popc(fm & ((1u << lane) - 1u))] = slot;
                                         if (lane == 0) { ch[0] = c.s.late_head[child]; ch[1] = __popc(fm); c.s.late_head[child] = chunk; }
                                     } else c.overflow = true;
-                                    if (lane == (child >> 5)) act_cur |= 1u << (child & 31);
+#pragma unroll
+                                    for (int w = 0; w < MW; w++) if ((child >> 10) == (uint32_t)w && lane == ((child >> 5) & 31u)) act_cur[w] |= 1u << (child & 31);
                                 }
                                 __syncwarp();
                             }
@@ -448,11 +460,13 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
                 if (c.overflow) { status = HP_WFA_WORKSPACE_OVERFLOW; break; }
                 // ---- next edit distance (:633-648) ----
                 ed++;
-                act_cur = act_next; act_next = 0;
+                uint32_t any_next = 0;
+#pragma unroll
+                for (int w = 0; w < MW; w++) { act_cur[w] = act_next[w]; any_next |= act_next[w]; act_next[w] = 0; }
                 c.n_chunks = 0;
                 if ((uint64_t)farthest > a.prune_distance) min_prog = farthest - (uint32_t)a.prune_distance;
                 if (ed > a.max_edit_distance) { status = HP_WFA_MAX_EDIT_DISTANCE; score = a.max_edit_distance; break; }
-                if (__ballot_sync(HP_FULL_MASK, act_cur != 0) == 0) { status = HP_WFA_WORKSPACE_OVERFLOW; break; }   // cannot happen
+                if (__ballot_sync(HP_FULL_MASK, any_next != 0) == 0) { status = HP_WFA_WORKSPACE_OVERFLOW; break; }   // cannot happen
             }
         }
         if (lane == 0) {
@@ -875,7 +889,9 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     a.out_counters = out->counters ? (uint64_t*)carve(32ull * nj) : nullptr;
 
     WFA_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    wfa_align_kernel<<<n_ctas, kWfaWarps * 32, 0, st>>>(a);
+    // node masks: one word per lane up to 1024 nodes, four words (4096 nodes) for batches with a larger graph
+    if (max_nodes <= 1024u) wfa_align_kernel<1><<<n_ctas, kWfaWarps * 32, 0, st>>>(a);
+    else wfa_align_kernel<4><<<n_ctas, kWfaWarps * 32, 0, st>>>(a);
     WFA_CUDA(ctx, cudaGetLastError());
     WFA_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->launches++; ctx->timing_pending = true;
@@ -1090,7 +1106,8 @@ int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
       FlatGraphs fg;
       uint64_t rows = 0;
       DevBuilt dev;
-      const bool on_device = !ctx->wfa_host_build;
+      // retries (wave table overflow, or a graph the device builder's fixed-size lists cannot hold) build on the host
+      const bool on_device = !ctx->wfa_host_build && attempt == 0;
       if (on_device) {
         if (!di.ready) {
             // workspace hint: ~3 nodes per variant in a window (exact sizes come from the count pass)
@@ -1211,7 +1228,8 @@ int hp_wfa_graph_align(hp_ctx* ctx, uint32_t n_nodes, const uint8_t* seq, const 
         if (st != HP_WFA_WORKSPACE_OVERFLOW) break;
         cap = std::min<uint32_t>(cap * 8, 1u << 24);
     }
-    if (st == HP_WFA_WORKSPACE_OVERFLOW) return wfa_fail(ctx, HP_ERR_UNSUPPORTED, "graph too large for the WFA workspace (more than 1024 nodes or wave table overflow)");
+    if (st == HP_WFA_WORKSPACE_OVERFLOW) return wfa_fail(ctx, HP_ERR_UNSUPPORTED, "wave table overflow after four workspace enlargements");
+    if (st == HP_WFA_GRAPH_TOO_LARGE) return wfa_fail(ctx, HP_ERR_UNSUPPORTED, "graph has more than 4096 nodes (outside the kernel's range)");
     *status = st; *score = sc;
     if (traversed) memcpy(traversed, trav.data(), 8ull * tw);
     return HP_OK;

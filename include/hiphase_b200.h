@@ -56,8 +56,10 @@ extern "C" {
 #define HP_WFA_OK                  0
 #define HP_WFA_MAX_EDIT_DISTANCE   1   /* WFAGraphError::MaxEditDistance, src/wfa_graph.rs:645-648              */
 #define HP_WFA_SKIPPED             2   /* job overlaps no het variant (read_parsing.rs:703-712)                 */
-#define HP_WFA_WORKSPACE_OVERFLOW  3   /* wave table outgrew its slab (retried transparently up to 4x) or the   */
-                                       /* graph has more than 1024 nodes (outside the kernel's range)           */
+#define HP_WFA_WORKSPACE_OVERFLOW  3   /* internal: wave table outgrew its slab (retried transparently up to 4x) */
+#define HP_WFA_GRAPH_TOO_LARGE     4   /* graph has more than 4096 nodes (> ~1300 variants in one read window):  */
+                                       /* outside the kernel's range, NOT retried; the caller routes the read to */
+                                       /* local realignment (hp_realign_block_batch does), as for MaxEditDistance */
 
 /* AlleleType, src/data_types/read_segments.rs:5-16 */
 #define HP_ALLELE_REFERENCE  0

@@ -132,3 +132,65 @@ def test_graph_build_modes_agree(mode):
     _assert_wfa_parity(out, ref)
     assert np.array_equal(out.n_nodes, ref.n_nodes) and np.array_equal(out.traversed, ref.traversed)
     c.close()
+
+
+def _dense_snv_batch(n_het, n_reads, seed, spacing=3, p_err=0.004):
+    """One window with n_het SNVs every `spacing` bases (3 nodes per variant: > 1024 nodes from 342 variants on) and reads
+    drawn from the two haplotypes with a few errors."""
+    rng = np.random.default_rng(seed)
+    L = n_het * spacing + 40
+    ref = rng.integers(0, 4, L)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    hets, truth = [], rng.integers(0, 2, n_het)
+    for i in range(n_het):
+        pos = 20 + i * spacing
+        alt = (int(ref[pos]) + 1 + int(rng.integers(0, 3))) % 4
+        hets.append({"type": "snv", "pos": pos, "ref_len": 1, "a0": bytes([acgt[ref[pos]]]), "a1": bytes([acgt[alt]])})
+    reads = []
+    for r in range(n_reads):
+        h = r & 1
+        seq = ref.copy()
+        for i, v in enumerate(hets):
+            if truth[i] ^ h:
+                seq[v["pos"]] = b"ACGT".index(v["a1"])
+        flip = rng.random(L) < p_err
+        seq[flip] = (seq[flip] + 1) % 4
+        reads.append(bytes(acgt[seq]))
+    return wfa_batch_single(bytes(acgt[ref]), hets, [], 0, L, reads)
+
+
+@pytest.mark.parametrize("n_het,words", [(360, 32), (1200, 64)], ids=["1082-nodes", "3602-nodes"])
+def test_graphs_with_more_than_1024_nodes(ctx, n_het, words):
+    """The reference's WFAGraph has no node limit (wfa_graph.rs:24-68); the kernel's node mask is one word per lane up to
+    1024 nodes and four words per lane up to 4096 (round-1 review: these jobs used to be refused)."""
+    batch = _dense_snv_batch(n_het, 6, seed=n_het)
+    ref = O.wfa_align(batch, threads=6, trav_words=words)
+    assert int(ref.n_nodes.max()) > 1024 and (ref.status == A.HP_WFA_OK).all()
+    out = ctx.wfa_align_batch(batch, trav_words=words)
+    _assert_wfa_parity(out, ref)
+
+
+def test_graph_beyond_the_kernel_range_reports_its_own_status(ctx):
+    batch = _dense_snv_batch(1400, 2, seed=5)                       # 4202 nodes
+    out = ctx.wfa_align_batch(batch, trav_words=1)
+    assert out.status.tolist() == [A.HP_WFA_GRAPH_TOO_LARGE] * 2
+
+
+def test_device_builder_overflow_falls_back_to_the_host_builder(ctx):
+    """More than 64 ALT branches open at one position (nested deletions): the device builder's fixed lists overflow and the
+    job is rebuilt on the host in the retry pass instead of being refused."""
+    rng = np.random.default_rng(3)
+    L = 400
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = rng.integers(0, 4, L)
+    refb = bytes(acgt[ref])
+    hets = []
+    for i in range(70):                                              # 70 deletions, all spanning position 200
+        pos = 100 + i
+        rl = 150 - i + (i % 3)
+        hets.append({"type": "deletion", "pos": pos, "ref_len": rl, "a0": refb[pos:pos + rl], "a1": refb[pos:pos + 1]})
+    reads = [refb, refb[:100] + refb[249:]]
+    batch = wfa_batch_single(refb, hets, [], 0, L, reads)
+    ref_out = O.wfa_align(batch, threads=2, trav_words=4)
+    out = ctx.wfa_align_batch(batch, trav_words=4)
+    _assert_wfa_parity(out, ref_out)
