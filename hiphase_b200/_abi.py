@@ -448,3 +448,73 @@ class Assembled:
         return BlockBatch(rows.var_off, self.read_off, self.read_start[:nr], self.read_end[:nr], self.cell_off[:nr + 1],
                           self.alleles[:nc], self.quals[:nc], np.zeros(nv, np.uint8) if ignored is None else ignored,
                           np.ones(nv, np.uint8) if is_snv is None else is_snv)
+
+
+# ---- realignment pipeline (read_parsing.rs:545-629) ------------------------------------------------------------------
+HP_MAP_GLOBAL, HP_MAP_LOCAL_FAILED, HP_MAP_LOCAL_DISABLED, HP_MAP_SKIPPED = 0, 1, 2, 3
+
+
+class hp_realign_batch(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint32), ("map_off", u64p), ("map_group", u32p), ("n_groups", u32p), ("var_off", u64p),
+                ("wfa_het_base", u32p), ("wfa", hp_wfa_batch), ("local", hp_local_batch), ("global_failure_minimum", C.c_uint32),
+                ("global_failure_ratio", C.c_double), ("min_matched_alleles", C.c_uint32)]
+
+
+class hp_realign_out(C.Structure):
+    _fields_ = [("map_mode", u8p), ("map_score", u32p), ("block_disabled_at", u32p), ("block_failures", u32p),
+                ("block_parsed", u32p), ("assembled", hp_assembled)]
+
+
+class RealignBatch:
+    """numpy side of hp_realign_batch: one WfaBatch job and one LocalBatch job per mapping, mappings grouped by block in BAM
+    order, read-name groups per block."""
+
+    def __init__(self, wfa, local, map_off, map_group, n_groups, var_off, wfa_het_base, global_failure_minimum=50,
+                 global_failure_ratio=0.5, min_matched_alleles=2):
+        self.wfa, self.local = wfa, local
+        self.map_off = _np(map_off, np.uint64); self.map_group = _np(map_group, np.uint32)
+        self.n_groups = _np(n_groups, np.uint32); self.var_off = _np(var_off, np.uint64)
+        self.wfa_het_base = _np(wfa_het_base, np.uint32)
+        self.global_failure_minimum = int(global_failure_minimum)
+        self.global_failure_ratio = float(global_failure_ratio)
+        self.min_matched_alleles = int(min_matched_alleles)
+        self.n_blocks = len(self.n_groups)
+        self.n_maps = int(self.map_off[-1])
+
+    def as_struct(self):
+        return hp_realign_batch(self.n_blocks, ptr(self.map_off, u64p), ptr(self.map_group, u32p), ptr(self.n_groups, u32p),
+                                ptr(self.var_off, u64p), ptr(self.wfa_het_base, u32p), self.wfa.as_struct(), self.local.as_struct(),
+                                self.global_failure_minimum, self.global_failure_ratio, self.min_matched_alleles)
+
+
+class RealignOut:
+    def __init__(self, batch):
+        nm, nb = max(batch.n_maps, 1), batch.n_blocks
+        self.map_mode = np.full(nm, 255, np.uint8); self.map_score = np.zeros(nm, np.uint32)
+        self.block_disabled_at = np.zeros(nb, np.uint32); self.block_failures = np.zeros(nb, np.uint32)
+        self.block_parsed = np.zeros(nb, np.uint32)
+        ng = max(int(batch.n_groups.sum()), 1)
+        nvar = np.diff(batch.var_off.astype(np.int64))
+        self.cell_capacity = max(int((batch.n_groups.astype(np.int64) * nvar).sum()), 1)
+        self.read_off = np.zeros(nb + 1, np.uint64)
+        self.read_start = np.zeros(ng, np.uint32); self.read_end = np.zeros(ng, np.uint32)
+        self.cell_off = np.zeros(ng + 1, np.uint64)
+        self.alleles = np.full(self.cell_capacity, 255, np.uint8); self.quals = np.full(self.cell_capacity, 255, np.uint8)
+        self.group_class = np.full(ng, 255, np.uint8); self.group_num_set = np.zeros(ng, np.uint32)
+        self._s = hp_realign_out(ptr(self.map_mode, u8p), ptr(self.map_score, u32p), ptr(self.block_disabled_at, u32p),
+                                 ptr(self.block_failures, u32p), ptr(self.block_parsed, u32p),
+                                 hp_assembled(ptr(self.read_off, u64p), ptr(self.read_start, u32p), ptr(self.read_end, u32p),
+                                              ptr(self.cell_off, u64p), ptr(self.alleles, u8p), ptr(self.quals, u8p), self.cell_capacity,
+                                              ptr(self.group_class, u8p), ptr(self.group_num_set, u32p), 0, 0))
+        self._batch = batch
+
+    def as_struct(self):
+        return self._s
+
+    def block_batch(self, ignored=None, is_snv=None):
+        """The assembled reads as a BlockBatch ready for astar_solve_batch."""
+        a = self._s.assembled
+        nr, nc, nv = int(a.n_reads), int(a.n_cells), int(self._batch.var_off[-1])
+        return BlockBatch(self._batch.var_off, self.read_off, self.read_start[:nr], self.read_end[:nr], self.cell_off[:nr + 1],
+                          self.alleles[:nc], self.quals[:nc], np.zeros(nv, np.uint8) if ignored is None else ignored,
+                          np.ones(nv, np.uint8) if is_snv is None else is_snv)

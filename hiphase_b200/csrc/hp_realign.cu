@@ -1,0 +1,175 @@
+// hp_realign.cu -- the realignment pipeline of a batch of phase blocks (host orchestration over the CUDA entry points).
+//
+// Replaces the read loop of load_full_read_segments (src/read_parsing.rs:545-629): global realignment per mapping, the
+// MaxEditDistance -> local_realignment fallback (:564-575), the order-dependent switch-off of global realignment for the rest
+// of a block (:593-600), and the collapse / filter that builds the read segments (:612-629).
+//
+// The rule is sequential per block, but a mapping's result does not depend on the order -- only WHICH of its two results is
+// used does.  So the device work is batched: (1) graph-WFA for every mapping, (2) local realignment for the WFA failures,
+// (3) a host replay of the counters finds each block's switch-off point, (4) local realignment for every mapping behind a
+// switch-off point that does not have a local row yet, (5) rows -> hp_assemble_blocks.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hiphase_b200.h"
+#include "hp_host.h"
+
+using namespace hp;
+
+extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, hp_realign_out* out) {
+    if (!ctx || !in || !out || !out->map_mode || !out->block_disabled_at) return HP_ERR_INVALID_INPUT;
+    const uint32_t nb = in->n_blocks;
+    if (nb == 0) return HP_OK;
+    if (!in->map_off || !in->map_group || !in->n_groups || !in->var_off || !in->wfa_het_base) return HP_ERR_INVALID_INPUT;
+    const uint64_t nm64 = in->map_off[nb];
+    if (nm64 != in->wfa.n_jobs || nm64 != in->local.n_jobs) return fail(ctx, HP_ERR_INVALID_INPUT, "wfa / local batches must hold one job per mapping");
+    const uint32_t nm = (uint32_t)nm64;
+    const hp_wfa_batch& W = in->wfa;
+    const hp_local_batch& L = in->local;
+    for (uint32_t b = 0; b < nb; b++) {
+        if (in->map_off[b + 1] < in->map_off[b] || in->var_off[b + 1] < in->var_off[b]) return fail(ctx, HP_ERR_INVALID_INPUT, "offsets must be non-decreasing");
+        const uint64_t n_var = in->var_off[b + 1] - in->var_off[b];
+        for (uint64_t j = in->map_off[b]; j < in->map_off[b + 1]; j++) {
+            if (in->map_group[j] >= in->n_groups[b]) return fail(ctx, HP_ERR_INVALID_INPUT, "read-name group out of range, mapping " + std::to_string(j));
+            if ((uint64_t)(L.var_hi[j] - L.var_lo[j]) != n_var) return fail(ctx, HP_ERR_INVALID_INPUT, "local job " + std::to_string(j) + " must cover all het variants of its block");
+            if (W.het_lo[j] < in->wfa_het_base[b] || (uint64_t)W.het_hi[j] > in->wfa_het_base[b] + n_var || W.het_hi[j] < W.het_lo[j])
+                return fail(ctx, HP_ERR_INVALID_INPUT, "WFA job " + std::to_string(j) + " leaves the het variants of its block");
+        }
+    }
+    if (nm == 0) {
+        for (uint32_t b = 0; b < nb; b++) {
+            out->block_disabled_at[b] = 0xffffffffu;
+            if (out->block_failures) out->block_failures[b] = 0;
+            if (out->block_parsed) out->block_parsed[b] = 0;
+        }
+    }
+
+    // ---- (1) graph-WFA for every mapping ----
+    const uint64_t w_cells = nm ? W.row_off[nm] : 0, l_cells = nm ? L.row_off[nm] : 0;
+    std::vector<int32_t> w_status(nm, HP_WFA_SKIPPED), l_status(nm, 0);
+    std::vector<uint32_t> w_score(nm, 0);
+    std::vector<uint8_t> w_al(w_cells + 1), w_q(w_cells + 1), l_al(l_cells + 1), l_q(l_cells + 1);
+    if (nm) {
+        hp_wfa_out wo{};
+        wo.status = w_status.data(); wo.score = w_score.data(); wo.alleles = w_al.data(); wo.quals = w_q.data();
+        int rc = hp_wfa_align_batch(ctx, &W, &wo);
+        if (rc != HP_OK) return rc;
+    }
+    hp_local_out lo{};
+    lo.alleles = l_al.data(); lo.quals = l_q.data(); lo.status = l_status.data();
+    std::vector<uint8_t> have_local(nm, 0);
+    auto run_local = [&](std::vector<uint32_t>& sel) -> int {
+        if (sel.empty()) return HP_OK;
+        int rc = local_realign_select(ctx, &L, &lo, sel.data(), (uint32_t)sel.size());
+        if (rc != HP_OK) return rc;
+        for (uint32_t j : sel) {
+            have_local[j] = 1;
+            if (l_status[j] != HP_LOCAL_OK)
+                return fail(ctx, HP_ERR_UNSUPPORTED, "local realignment of mapping " + std::to_string(j) + " failed with job status " +
+                            std::to_string(l_status[j]) + " (the reference panics here, read_parsing.rs:320-322, 452-454)");
+        }
+        return HP_OK;
+    };
+    // ---- (2) local realignment where graph-WFA gave up (:564-575) ----
+    auto wfa_failed = [&](uint32_t j) { return w_status[j] == HP_WFA_MAX_EDIT_DISTANCE || w_status[j] == HP_WFA_GRAPH_TOO_LARGE; };
+    {
+        std::vector<uint32_t> sel;
+        for (uint32_t j = 0; j < nm; j++) {
+            if (w_status[j] == HP_WFA_WORKSPACE_OVERFLOW) return fail(ctx, HP_ERR_UNSUPPORTED, "graph-WFA workspace overflow, mapping " + std::to_string(j));
+            if (wfa_failed(j)) sel.push_back(j);
+        }
+        int rc = run_local(sel);
+        if (rc != HP_OK) return rc;
+    }
+    // a local row is "skipped" when no variant got a binary allele (num_overlaps == 0, :492)
+    auto local_skipped = [&](uint32_t j) {
+        for (uint64_t c = L.row_off[j]; c < L.row_off[j + 1]; c++) if (l_al[c] < 2) return false;
+        return true;
+    };
+    // ---- (3) replay up to each block's switch-off point (:583-600) ----
+    std::vector<uint32_t> late;
+    for (uint32_t b = 0; b < nb; b++) {
+        double failures = 0.0, parsed = 0.0;
+        uint32_t disabled_at = 0xffffffffu;
+        for (uint64_t j = in->map_off[b]; j < in->map_off[b + 1]; j++) {
+            if (disabled_at != 0xffffffffu) { if (!have_local[j]) late.push_back((uint32_t)j); continue; }
+            bool skipped, local;
+            if (wfa_failed((uint32_t)j)) { local = true; skipped = local_skipped((uint32_t)j); }
+            else { local = false; skipped = w_status[j] == HP_WFA_SKIPPED; }
+            if (skipped) continue;
+            parsed += 1.0;
+            if (local) failures += 1.0;
+            if (failures >= (double)in->global_failure_minimum && failures / parsed >= in->global_failure_ratio)
+                disabled_at = (uint32_t)(j - in->map_off[b]);
+        }
+        out->block_disabled_at[b] = disabled_at;
+    }
+    // ---- (4) local realignment behind the switch-off points (:551-554) ----
+    {
+        int rc = run_local(late);
+        if (rc != HP_OK) return rc;
+    }
+    // ---- (5) final modes, counters, rows ----
+    const uint32_t max_ed = ctx->params.wfa_max_edit_distance;
+    std::vector<uint64_t> group_off(nb + 1, 0);
+    for (uint32_t b = 0; b < nb; b++) group_off[b + 1] = group_off[b] + in->n_groups[b];
+    const uint64_t n_groups = group_off[nb];
+    std::vector<uint64_t> group_rows(n_groups + 1, 0);
+    for (uint32_t b = 0; b < nb; b++) {
+        double failures = 0.0, parsed = 0.0;
+        const uint32_t dis = out->block_disabled_at[b];
+        for (uint64_t j = in->map_off[b]; j < in->map_off[b + 1]; j++) {
+            const uint32_t k = (uint32_t)(j - in->map_off[b]);
+            uint8_t mode;
+            uint32_t score;
+            if (dis != 0xffffffffu && k > dis) { mode = HP_MAP_LOCAL_DISABLED; score = max_ed; }
+            else if (wfa_failed((uint32_t)j)) { mode = HP_MAP_LOCAL_FAILED; score = w_score[j]; }
+            else { mode = HP_MAP_GLOBAL; score = w_score[j]; }
+            const bool skipped = mode == HP_MAP_GLOBAL ? w_status[j] == HP_WFA_SKIPPED : local_skipped((uint32_t)j);
+            if (skipped) { mode = HP_MAP_SKIPPED; if (w_status[j] == HP_WFA_SKIPPED && !(dis != 0xffffffffu && k > dis)) score = 0xffffffffu; }   // usize::MAX, :712
+            else {
+                parsed += 1.0;
+                if (mode != HP_MAP_GLOBAL) failures += 1.0;
+                group_rows[group_off[b] + in->map_group[j] + 1]++;
+            }
+            out->map_mode[j] = mode;
+            if (out->map_score) out->map_score[j] = score;
+        }
+        if (out->block_failures) out->block_failures[b] = (uint32_t)failures;
+        if (out->block_parsed) out->block_parsed[b] = (uint32_t)parsed;
+    }
+    for (uint64_t g = 0; g < n_groups; g++) group_rows[g + 1] += group_rows[g];
+    const uint64_t n_rows = group_rows[n_groups];
+    std::vector<uint32_t> row_start(n_rows + 1);
+    std::vector<uint64_t> row_src(n_rows + 1), row_len(n_rows + 1), row_cell_off(n_rows + 1, 0);
+    std::vector<uint8_t> row_is_local(n_rows + 1);
+    {
+        std::vector<uint64_t> cur(group_rows.begin(), group_rows.end() - 1);
+        for (uint32_t b = 0; b < nb; b++)
+            for (uint64_t j = in->map_off[b]; j < in->map_off[b + 1]; j++) {
+                if (out->map_mode[j] == HP_MAP_SKIPPED) continue;
+                const uint64_t r = cur[group_off[b] + in->map_group[j]]++;          // mappings of a group stay in BAM order
+                if (out->map_mode[j] == HP_MAP_GLOBAL) {
+                    row_start[r] = W.het_lo[j] - in->wfa_het_base[b]; row_src[r] = W.row_off[j]; row_len[r] = W.row_off[j + 1] - W.row_off[j]; row_is_local[r] = 0;
+                } else {
+                    row_start[r] = 0; row_src[r] = L.row_off[j]; row_len[r] = L.row_off[j + 1] - L.row_off[j]; row_is_local[r] = 1;
+                }
+            }
+    }
+    for (uint64_t r = 0; r < n_rows; r++) row_cell_off[r + 1] = row_cell_off[r] + row_len[r];
+    std::vector<uint8_t> r_al(row_cell_off[n_rows] + 1), r_q(row_cell_off[n_rows] + 1);
+    for (uint64_t r = 0; r < n_rows; r++) {
+        if (!row_len[r]) continue;
+        memcpy(&r_al[row_cell_off[r]], (row_is_local[r] ? l_al.data() : w_al.data()) + row_src[r], row_len[r]);
+        memcpy(&r_q[row_cell_off[r]], (row_is_local[r] ? l_q.data() : w_q.data()) + row_src[r], row_len[r]);
+    }
+    hp_rows_batch rows{};
+    rows.n_blocks = nb; rows.var_off = in->var_off; rows.group_off = group_off.data(); rows.group_row_off = group_rows.data();
+    rows.row_start = row_start.data(); rows.row_cell_off = row_cell_off.data(); rows.alleles = r_al.data(); rows.quals = r_q.data();
+    rows.min_matched_alleles = in->min_matched_alleles;
+    return hp_assemble_blocks(ctx, &rows, &out->assembled);
+}

@@ -569,3 +569,63 @@ def config_local(n_blocks=8, first_block=0, full_rows=False, **kw):
     read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])])
     return LocalBatch(variant_table(allv), var_lo, var_hi, read_pos, seg_off, sr, sd, sl,
                       np.concatenate(reads), np.concatenate(quals), read_off)
+
+
+# ---- realignment pipeline batches: the same mappings as graph-WFA jobs AND local-realignment jobs ---------------------
+def config_realign(n_blocks=4, first_block=0, p_pair=0.15, **kw):
+    """Blocks of gen_local_block with, per mapping, its global-realignment job (plan_global_realignment: window, overlapped
+    hets, aligned read slice; truncated alleles) and its local-realignment job (all hets of the block; full alleles).
+    A fraction p_pair of the mappings shares its read name with the previous mapping (supplementary alignments -> collapse).
+    Returns (RealignBatch kwargs dict, vtypes per block)."""
+    from ._abi import LocalBatch, WfaBatch
+    from .read_parsing import AlignedRead, plan_global_realignment
+    from .variants import variant_table
+    allv = []
+    wt = {k: [] for k in ("position", "ref_len", "allele0_off", "allele0_len", "allele1_off", "allele1_len", "index_allele0", "vtype", "ignored")}
+    blob, blob_len = [], 0
+    refs, ref_base = [], 0
+    var_lo, var_hi, read_pos, seg_off, sr, sd, sl, l_reads, l_quals = [], [], [], [0], [], [], [], [], []
+    rs, re, hl, hh, w_reads = [], [], [], [], []
+    map_off, map_group, n_groups, var_off, het_base, vtypes = [0], [], [], [0], [], []
+    for b in range(first_block, first_block + n_blocks):
+        rng = np.random.default_rng(block_seed(8, b))
+        blk = gen_local_block(rng, p_ignored=0.0, **kw)
+        vs = blk["variants"]
+        base = len(allv)
+        allv.extend(vs)
+        het_base.append(base)
+        for v in vs:
+            a0, a1 = v.get_truncated_allele0(), v.get_truncated_allele1()
+            wt["position"].append(v.position() + ref_base); wt["ref_len"].append(v.get_ref_len())
+            wt["allele0_off"].append(blob_len); wt["allele0_len"].append(len(a0)); blob.append(np.frombuffer(a0, np.uint8)); blob_len += len(a0)
+            wt["allele1_off"].append(blob_len); wt["allele1_len"].append(len(a1)); blob.append(np.frombuffer(a1, np.uint8)); blob_len += len(a1)
+            wt["index_allele0"].append(v.index_allele0); wt["vtype"].append(int(v.get_type())); wt["ignored"].append(0)
+        vpos = [v.position() for v in vs]
+        g = -1
+        for (lo, hi, rp, segs, seq, q) in blk["jobs"]:
+            if g < 0 or rng.random() >= p_pair:
+                g += 1
+            map_group.append(g)
+            var_lo.append(base); var_hi.append(base + len(vs)); read_pos.append(rp)
+            for (a, r, n) in segs:
+                sr.append(a); sd.append(r); sl.append(n)
+            seg_off.append(len(sr))
+            l_reads.append(seq); l_quals.append(q)
+            plan = plan_global_realignment(AlignedRead(rp, segs, seq.tobytes(), q), vpos, [])
+            if plan is None:
+                rs.append(ref_base); re.append(ref_base); hl.append(base); hh.append(base); w_reads.append(np.zeros(0, np.uint8))
+            else:
+                rs.append(plan["ref_start"] + ref_base); re.append(plan["ref_end"] + ref_base)
+                hl.append(base + plan["het_lo"]); hh.append(base + plan["het_hi"])
+                w_reads.append(seq[plan["read_start"]:plan["read_end"]])
+        map_off.append(len(map_group)); n_groups.append(g + 1); var_off.append(var_off[-1] + len(vs))
+        vtypes.append([int(v.get_type()) for v in vs])
+        refs.append(blk["reference"]); ref_base += len(blk["reference"])
+    wt["allele_bytes"] = np.concatenate(blob) if blob else np.zeros(1, np.uint8)
+    nm = len(map_group)
+    w_off = np.concatenate([[0], np.cumsum([len(r) for r in w_reads])])
+    wfa = WfaBatch(wt, np.concatenate(refs), rs, re, hl, hh, [0] * nm, [0] * nm,
+                   np.concatenate(w_reads) if w_off[-1] else np.zeros(1, np.uint8), w_off)
+    l_off = np.concatenate([[0], np.cumsum([len(r) for r in l_reads])])
+    local = LocalBatch(variant_table(allv), var_lo, var_hi, read_pos, seg_off, sr, sd, sl, np.concatenate(l_reads), np.concatenate(l_quals), l_off)
+    return dict(wfa=wfa, local=local, map_off=map_off, map_group=map_group, n_groups=n_groups, var_off=var_off, wfa_het_base=het_base), vtypes

@@ -435,6 +435,45 @@ typedef struct hp_assembled {
 /* Host buffers in / out.  Returns HP_ERR_INVALID_INPUT if cell_capacity is too small or a row leaves its block. */
 int hp_assemble_blocks(hp_ctx* ctx, const hp_rows_batch* rows, hp_assembled* out);
 
+/* ---- realignment pipeline of a batch of phase blocks: replaces the read loop of load_full_read_segments
+ *      (src/read_parsing.rs:545-629).  For every mapping of a block, in BAM order: global realignment (graph-WFA); where it
+ *      reports MaxEditDistance the read falls back to local_realignment (:564-575); once a block has seen at least
+ *      global_failure_minimum such fallbacks and they make up global_failure_ratio of the reads parsed so far, global
+ *      realignment is switched off for the REST of the block (:593-600) -- an order-dependent rule, replayed here exactly;
+ *      then ReadSegment::new / collapse per read name / the min-matched-alleles filter (:612-629).  The assembled reads plug
+ *      straight into hp_astar_solve_batch.  The GPU runs graph-WFA for all mappings at once, local realignment for the
+ *      mappings that need it (two selections: the WFA failures, then everything behind a block's switch-off point). ---- */
+#define HP_MAP_GLOBAL          0   /* row of global_realignment                                                        */
+#define HP_MAP_LOCAL_FAILED    1   /* graph-WFA reported MaxEditDistance (or HP_WFA_GRAPH_TOO_LARGE): local_realignment */
+#define HP_MAP_LOCAL_DISABLED  2   /* global realignment was already switched off for the block: local_realignment     */
+#define HP_MAP_SKIPPED         3   /* the mapping overlaps no allele (ReadStats::skipped_reads == 1): no ReadSegment     */
+
+typedef struct hp_realign_batch {
+    uint32_t        n_blocks;
+    const uint64_t* map_off;          /* [n_blocks+1] mappings of block b (bam records that passed the filter), BAM order */
+    const uint32_t* map_group;        /* [n_maps] read-name group of the mapping, block-relative in [0, n_groups[b])      */
+    const uint32_t* n_groups;         /* [n_blocks]                                                                       */
+    const uint64_t* var_off;          /* [n_blocks+1] het variants of the blocks (= the matrix columns)                   */
+    const uint32_t* wfa_het_base;     /* [n_blocks] index of the block's first het variant in wfa.variants                */
+    hp_wfa_batch    wfa;              /* job j = mapping j (n_jobs = n_maps)                                              */
+    hp_local_batch  local;            /* job j = mapping j; [var_lo, var_hi) = ALL het variants of its block (:568)       */
+    uint32_t        global_failure_minimum;   /* --global-failure-count, default 50 (cli.rs:207-212)                     */
+    double          global_failure_ratio;     /* --max-global-failure-ratio, default 0.5 (cli.rs:200-205)                */
+    uint32_t        min_matched_alleles;      /* --min-matched-alleles, default 2                                        */
+} hp_realign_batch;
+
+typedef struct hp_realign_out {
+    uint8_t*     map_mode;            /* [n_maps] HP_MAP_*                                                               */
+    uint32_t*    map_score;           /* optional [n_maps] wfa_score as the reference records it (:556, :572, :558)       */
+    uint32_t*    block_disabled_at;   /* [n_blocks] block-relative index of the mapping that tripped the rule, UINT32_MAX = never */
+    uint32_t*    block_failures;      /* optional [n_blocks] num_global_failures at the end of the block                  */
+    uint32_t*    block_parsed;        /* optional [n_blocks] total_parsed                                                 */
+    hp_assembled assembled;           /* caller-sized: sum n_groups reads; cell_capacity >= sum over groups of the block's n_var */
+} hp_realign_out;
+
+/* Host buffers in / out.  A local-realignment job the reference would panic on returns HP_ERR_UNSUPPORTED. */
+int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* batch, hp_realign_out* out);
+
 /* ---- packed phase-block container + stats writer ----------------------------------------
  * The wire / on-disk form of a block batch, "HPB200" v1 (layout in csrc/hp_pack.cu): what a front end that still owns
  * VCF / BAM decoding (the HiPhase Rust code up to src/phaser.rs:541, or any other reader) writes, and what the batch

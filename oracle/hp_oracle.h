@@ -95,6 +95,9 @@ int hpo_graph_edit_distance(const hpo_graph* g, const uint8_t* read, uint64_t re
 /* whole batch: graph build + alignment + allele/qual rows (read_parsing.rs:769-851). */
 int hpo_wfa_align_batch(const hp_params* params, const hp_wfa_batch* batch, hp_wfa_out* out, int threads);
 
+/* ---- the read loop of load_full_read_segments (src/read_parsing.rs:545-629), one mapping at a time in BAM order ---- */
+int hpo_realign_block_batch(const hp_params* params, const hp_realign_batch* batch, hp_realign_out* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -209,3 +209,12 @@ def assemble_blocks(rows):
     rs = rows.as_struct()
     out.rc = lib().hpo_assemble_blocks(C.byref(rs), C.byref(out.as_struct()))
     return out
+
+
+def realign_block_batch(batch, params=None):
+    """The read loop of load_full_read_segments (read_parsing.rs:545-629), one mapping at a time."""
+    params = params or A.default_params()
+    out = A.RealignOut(batch)
+    bs = batch.as_struct()
+    out.rc = lib().hpo_realign_block_batch(C.byref(params), C.byref(bs), C.byref(out.as_struct()))
+    return out

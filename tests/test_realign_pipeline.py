@@ -1,0 +1,90 @@
+"""The realignment pipeline entry (hp_realign_block_batch): graph-WFA -> MaxEditDistance -> local realignment, the
+order-dependent switch-off of global realignment for the rest of a block, collapse and filter -- against the oracle's
+mapping-by-mapping restatement of load_full_read_segments (src/read_parsing.rs:545-629)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from hiphase_b200 import _abi as A
+from hiphase_b200 import lib, synth
+
+
+def _batch(n_blocks, first_block, fail_min, ratio, **kw):
+    d, vtypes = synth.config_realign(n_blocks, first_block, **kw)
+    return A.RealignBatch(global_failure_minimum=fail_min, global_failure_ratio=ratio, **d), vtypes
+
+
+def _same(out, ref):
+    assert np.array_equal(out.map_mode, ref.map_mode), (np.bincount(out.map_mode, minlength=4), np.bincount(ref.map_mode, minlength=4))
+    assert np.array_equal(out.block_disabled_at, ref.block_disabled_at)
+    assert np.array_equal(out.block_failures, ref.block_failures) and np.array_equal(out.block_parsed, ref.block_parsed)
+    a, b = out.as_struct().assembled, ref.as_struct().assembled
+    assert int(a.n_reads) == int(b.n_reads) and int(a.n_cells) == int(b.n_cells)
+    nr, nc = int(b.n_reads), int(b.n_cells)
+    assert np.array_equal(out.read_off, ref.read_off)
+    assert np.array_equal(out.read_start[:nr], ref.read_start[:nr]) and np.array_equal(out.read_end[:nr], ref.read_end[:nr])
+    assert np.array_equal(out.cell_off[:nr + 1], ref.cell_off[:nr + 1])
+    assert np.array_equal(out.alleles[:nc], ref.alleles[:nc]) and np.array_equal(out.quals[:nc], ref.quals[:nc])
+    assert np.array_equal(out.group_class, ref.group_class)
+
+
+SMALL = dict(window=9000, n_var=18, n_reads=40, read_lo=1500, read_hi=4000, sv_max=300)
+
+
+def test_oracle_replays_the_switch_off_rule():
+    """Known-answer scenario for the rule itself (read_parsing.rs:593-600): with max_edit_distance 8 roughly half of the reads
+    fail graph-WFA; with global-failure-count 5 / ratio 0.3 the block trips and every later mapping is local."""
+    params = A.hp_params(1000, 3, 500, 8)
+    batch, _ = _batch(2, 0, 5, 0.3, err=0.004, **SMALL)
+    ref = O.realign_block_batch(batch, params)
+    assert ref.rc == 0
+    for b in range(batch.n_blocks):
+        m0, m1 = int(batch.map_off[b]), int(batch.map_off[b + 1])
+        mode = ref.map_mode[m0:m1]
+        d = int(ref.block_disabled_at[b])
+        assert d != 0xffffffff, "the scenario is meant to trip the rule"
+        assert mode[d] == A.HP_MAP_LOCAL_FAILED                                  # the mapping that trips it is itself a failure
+        assert not (mode[:d + 1] == A.HP_MAP_LOCAL_DISABLED).any()
+        assert np.isin(mode[d + 1:], (A.HP_MAP_LOCAL_DISABLED, A.HP_MAP_SKIPPED)).all()
+        # replay of the counters from the modes alone
+        fails = parsed = 0
+        for k, md in enumerate(mode[:d + 1]):
+            if md == A.HP_MAP_SKIPPED:
+                continue
+            parsed += 1; fails += md == A.HP_MAP_LOCAL_FAILED
+            tripped = fails >= 5 and fails / parsed >= 0.3
+            assert tripped == (k == d)
+    # with the reference defaults (50 / 0.5) this block never trips
+    batch2, _ = _batch(1, 0, 50, 0.5, err=0.004, **SMALL)
+    ref2 = O.realign_block_batch(batch2, params)
+    assert ref2.rc == 0 and int(ref2.block_disabled_at[0]) == 0xffffffff and (ref2.map_mode == A.HP_MAP_LOCAL_FAILED).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fail_min,ratio,max_ed", [(5, 0.3, 8), (50, 0.5, 8), (3, 0.9, 6), (1, 0.0, 500)])
+def test_gpu_pipeline_matches_the_oracle(fail_min, ratio, max_ed):
+    params = A.hp_params(1000, 3, 500, max_ed)
+    ctx = lib.Context(params, device=0)
+    batch, vtypes = _batch(3, 10, fail_min, ratio, err=0.004, **SMALL)
+    ref = O.realign_block_batch(batch, params)
+    assert ref.rc == 0
+    out = ctx.realign_block_batch(batch)
+    _same(out, ref)
+    # ... and the assembled reads phase identically
+    is_snv = np.concatenate([(np.array(v) == 0).astype(np.uint8) for v in vtypes])
+    got = ctx.astar_solve_batch(out.block_batch(is_snv=is_snv))
+    exp = O.astar_solve(ref.block_batch(is_snv=is_snv), params, want_heuristic=False, want_counters=False)
+    assert np.array_equal(got.h1, exp.h1) and np.array_equal(got.h2, exp.h2) and np.array_equal(got.stats, exp.stats)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_trips_at_fifty_failures():
+    """The reference defaults (--global-failure-count 50, --max-global-failure-ratio 0.5) on a block with enough failing reads."""
+    params = A.hp_params(1000, 3, 500, 6)
+    ctx = lib.Context(params, device=0)
+    batch, _ = _batch(1, 20, 50, 0.5, err=0.006, window=9000, n_var=18, n_reads=160, read_lo=1500, read_hi=4000, sv_max=300)
+    ref = O.realign_block_batch(batch, params)
+    assert ref.rc == 0 and int(ref.block_disabled_at[0]) != 0xffffffff and int(ref.block_failures[0]) >= 50
+    _same(ctx.realign_block_batch(batch), ref)
+    ctx.close()
