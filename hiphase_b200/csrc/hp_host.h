@@ -112,5 +112,4 @@ struct hp_ctx {
 
 namespace hp {
 int fail(hp_ctx* ctx, int code, const std::string& msg);
-int local_realign_select(hp_ctx* ctx, const hp_local_batch* b, hp_local_out* out, const uint32_t* sel, uint32_t n_sel);
 }

@@ -9,6 +9,9 @@
 // (3) a host replay of the counters finds each block's switch-off point, (4) local realignment for every mapping behind a
 // switch-off point that does not have a local row yet, (5) rows -> hp_assemble_blocks.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,6 +51,10 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         }
     }
 
+    const bool timing = getenv("HP_DBG_REALIGN_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     // ---- (1) graph-WFA for every mapping ----
     const uint64_t w_cells = nm ? W.row_off[nm] : 0, l_cells = nm ? L.row_off[nm] : 0;
     std::vector<int32_t> w_status(nm, HP_WFA_SKIPPED), l_status(nm, 0);
@@ -59,18 +66,51 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         int rc = hp_wfa_align_batch(ctx, &W, &wo);
         if (rc != HP_OK) return rc;
     }
-    hp_local_out lo{};
-    lo.alleles = l_al.data(); lo.quals = l_q.data(); lo.status = l_status.data();
+    const auto t1 = now();
     std::vector<uint8_t> have_local(nm, 0);
+    // Local realignment of the selected mappings only: their jobs are gathered into a compact batch on the host (a few percent
+    // of the reads on HiFi data), so neither the copy to the device nor the validation touches the other reads.
     auto run_local = [&](std::vector<uint32_t>& sel) -> int {
         if (sel.empty()) return HP_OK;
-        int rc = local_realign_select(ctx, &L, &lo, sel.data(), (uint32_t)sel.size());
+        const size_t ns = sel.size();
+        std::vector<uint32_t> c_lo(ns), c_hi(ns), c_sd, c_sl;
+        std::vector<int64_t> c_pos(ns), c_sr;
+        std::vector<uint64_t> c_seg_off(ns + 1, 0), c_read_off(ns + 1, 0), c_row_off(ns + 1, 0);
+        uint64_t n_seg = 0, n_rd = 0;
+        for (size_t k = 0; k < ns; k++) { const uint32_t j = sel[k]; n_seg += L.seg_off[j + 1] - L.seg_off[j]; n_rd += L.read_off[j + 1] - L.read_off[j]; }
+        c_sr.reserve(n_seg); c_sd.reserve(n_seg); c_sl.reserve(n_seg);
+        std::vector<uint8_t> c_rb(n_rd + 1), c_rq(n_rd + 1);
+        for (size_t k = 0; k < ns; k++) {
+            const uint32_t j = sel[k];
+            c_lo[k] = L.var_lo[j]; c_hi[k] = L.var_hi[j]; c_pos[k] = L.read_pos[j];
+            for (uint64_t q = L.seg_off[j]; q < L.seg_off[j + 1]; q++) { c_sr.push_back(L.seg_ref_start[q]); c_sd.push_back(L.seg_read_start[q]); c_sl.push_back(L.seg_len[q]); }
+            c_seg_off[k + 1] = c_sr.size();
+            const uint64_t rl = L.read_off[j + 1] - L.read_off[j];
+            if (rl) { memcpy(&c_rb[c_read_off[k]], L.read_bytes + L.read_off[j], rl); memcpy(&c_rq[c_read_off[k]], L.read_quals + L.read_off[j], rl); }
+            c_read_off[k + 1] = c_read_off[k] + rl;
+            c_row_off[k + 1] = c_row_off[k] + (L.row_off[j + 1] - L.row_off[j]);
+        }
+        c_sr.push_back(0); c_sd.push_back(0); c_sl.push_back(0);
+        hp_local_batch cb = L;
+        cb.n_jobs = (uint32_t)ns;
+        cb.var_lo = c_lo.data(); cb.var_hi = c_hi.data(); cb.read_pos = c_pos.data(); cb.seg_off = c_seg_off.data();
+        cb.seg_ref_start = c_sr.data(); cb.seg_read_start = c_sd.data(); cb.seg_len = c_sl.data();
+        cb.read_bytes = c_rb.data(); cb.read_quals = c_rq.data(); cb.read_off = c_read_off.data(); cb.row_off = c_row_off.data();
+        std::vector<uint8_t> o_al(c_row_off[ns] + 1), o_q(c_row_off[ns] + 1);
+        std::vector<int32_t> o_st(ns, -1);
+        hp_local_out co{};
+        co.alleles = o_al.data(); co.quals = o_q.data(); co.status = o_st.data();
+        int rc = hp_local_realign_batch(ctx, &cb, &co);
         if (rc != HP_OK) return rc;
-        for (uint32_t j : sel) {
+        for (size_t k = 0; k < ns; k++) {
+            const uint32_t j = sel[k];
             have_local[j] = 1;
-            if (l_status[j] != HP_LOCAL_OK)
+            l_status[j] = o_st[k];
+            if (o_st[k] != HP_LOCAL_OK)
                 return fail(ctx, HP_ERR_UNSUPPORTED, "local realignment of mapping " + std::to_string(j) + " failed with job status " +
-                            std::to_string(l_status[j]) + " (the reference panics here, read_parsing.rs:320-322, 452-454)");
+                            std::to_string(o_st[k]) + " (the reference panics here, read_parsing.rs:320-322, 452-454)");
+            const uint64_t n = c_row_off[k + 1] - c_row_off[k];
+            if (n) { memcpy(&l_al[L.row_off[j]], &o_al[c_row_off[k]], n); memcpy(&l_q[L.row_off[j]], &o_q[c_row_off[k]], n); }
         }
         return HP_OK;
     };
@@ -90,6 +130,7 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         for (uint64_t c = L.row_off[j]; c < L.row_off[j + 1]; c++) if (l_al[c] < 2) return false;
         return true;
     };
+    const auto t2 = now();
     // ---- (3) replay up to each block's switch-off point (:583-600) ----
     std::vector<uint32_t> late;
     for (uint32_t b = 0; b < nb; b++) {
@@ -113,6 +154,7 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         int rc = run_local(late);
         if (rc != HP_OK) return rc;
     }
+    const auto t3 = now();
     // ---- (5) final modes, counters, rows ----
     const uint32_t max_ed = ctx->params.wfa_max_edit_distance;
     std::vector<uint64_t> group_off(nb + 1, 0);
@@ -171,5 +213,8 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
     rows.n_blocks = nb; rows.var_off = in->var_off; rows.group_off = group_off.data(); rows.group_row_off = group_rows.data();
     rows.row_start = row_start.data(); rows.row_cell_off = row_cell_off.data(); rows.alleles = r_al.data(); rows.quals = r_q.data();
     rows.min_matched_alleles = in->min_matched_alleles;
-    return hp_assemble_blocks(ctx, &rows, &out->assembled);
+    const auto t4 = now();
+    const int rc_asm = hp_assemble_blocks(ctx, &rows, &out->assembled);
+    if (timing) fprintf(stderr, "[hp_realign] %u mappings: wfa %.1f ms, local(failed) %.1f, replay+local(late) %.1f, rows %.1f, assemble %.1f\n", nm, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
+    return rc_asm;
 }

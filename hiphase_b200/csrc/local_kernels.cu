@@ -46,8 +46,6 @@ struct LocalArgs {
     const uint8_t* read_quals;
     const uint64_t* read_off;
     const uint64_t* row_off;
-    const uint32_t* sel;   // optional: the jobs to run (n_sel of them); NULL = all n_jobs
-    uint32_t n_sel;
     // outputs
     uint8_t* alleles;
     uint8_t* quals;
@@ -252,10 +250,9 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_realign_kernel(LocalAr
     for (;;) {
         if (lane == 0) job_s[warp] = atomicAdd(a.ticket, 1u);
         __syncwarp();
-        const uint32_t t = job_s[warp];
+        const uint32_t j = job_s[warp];
         __syncwarp();
-        if (t >= (a.sel ? a.n_sel : a.n_jobs)) break;
-        const uint32_t j = a.sel ? a.sel[t] : t;
+        if (j >= a.n_jobs) break;
         Segs sg;
         const uint64_t s0 = a.seg_off[j];
         sg.ref = a.seg_ref + s0; sg.rd = a.seg_read + s0; sg.len = a.seg_len + s0; sg.n = (uint32_t)(a.seg_off[j + 1] - s0);
@@ -520,11 +517,9 @@ namespace {
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 }
 
-// Runs the jobs sel[0..n_sel) of the batch (sel == NULL: all of them).  Rows and statuses of the other jobs are unspecified
-// in *out (the arrays are copied back whole).  hp_realign_block_batch uses the selection: local realignment is only needed where graph-WFA gave up.
-int hp::local_realign_select(hp_ctx* ctx, const hp_local_batch* b, hp_local_out* out, const uint32_t* sel, uint32_t n_sel) {
+extern "C" int hp_local_realign_batch(hp_ctx* ctx, const hp_local_batch* b, hp_local_out* out) {
     if (!ctx || !b || !out || !out->alleles || !out->quals || !out->status) return HP_ERR_INVALID_INPUT;
-    if (b->n_jobs == 0 || (sel && n_sel == 0)) return HP_OK;
+    if (b->n_jobs == 0) return HP_OK;
     auto fail = [&](int code, const std::string& msg) { ctx->err = msg; return code; };
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaSetDevice failed");
     const hp_variant_table& t = b->variants;
@@ -554,7 +549,7 @@ int hp::local_realign_select(hp_ctx* ctx, const hp_local_batch* b, hp_local_out*
     }
     const size_t in_bytes = al256(8 * (size_t)nvt) + al256(4 * (size_t)nvt) * 5 + al256(8 * (size_t)nvt) * 2 + al256(nvt) * 2 + al256(t.n_allele_bytes) +
                             al256(4 * (size_t)nj) * 2 + al256(8 * (size_t)nj) + al256(8 * ((size_t)nj + 1)) * 3 +
-                            al256(8 * n_segs) + al256(4 * n_segs) * 2 + al256(n_read) * 2 + al256(4 * (size_t)n_sel) + 4096;
+                            al256(8 * n_segs) + al256(4 * n_segs) * 2 + al256(n_read) * 2 + 4096;
     const size_t out_bytes = al256(n_cells) * 3 + al256(8 * n_cells) + al256(4 * (size_t)nj) + al256(4 * n_cells) * 4 + al256(8 * n_cells) + 4096;
     if (!ctx->stage_in.reserve(in_bytes) || !ctx->stage_out.reserve(out_bytes) || !ctx->ticket.reserve(256))
         return fail(HP_ERR_OUT_OF_MEMORY, "staging allocation failed");
@@ -591,13 +586,7 @@ int hp::local_realign_select(hp_ctx* ctx, const hp_local_batch* b, hp_local_out*
     a.del_end = (int64_t*)carve(8 * n_cells);
     a.ticket = (uint32_t*)ctx->ticket.ptr;
     ok &= cudaMemsetAsync(a.ticket, 0, 4, st) == cudaSuccess;
-    a.sel = nullptr; a.n_sel = 0;
-    if (sel) {
-        for (uint32_t k = 0; k < n_sel; k++) if (sel[k] >= nj) return fail(HP_ERR_INVALID_INPUT, "selected job out of range");
-        a.sel = (const uint32_t*)up(sel, 4 * (size_t)n_sel); a.n_sel = n_sel;
-    }
-    const uint64_t n_run = sel ? n_sel : nj;
-    const int grid = (int)std::min<uint64_t>((n_run + kLocalWarps - 1) / kLocalWarps, (uint64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<uint64_t>(((uint64_t)nj + kLocalWarps - 1) / kLocalWarps, (uint64_t)ctx->sm_count * 8);
     if (ctx->ev0) { cudaEventRecord(ctx->ev0, st); }
     local_realign_kernel<<<grid, kLocalWarps * 32, 0, st>>>(a);
     if (ctx->ev1) { cudaEventRecord(ctx->ev1, st); ctx->timing_pending = true; }
@@ -613,10 +602,6 @@ int hp::local_realign_select(hp_ctx* ctx, const hp_local_batch* b, hp_local_out*
     ok &= cudaStreamSynchronize(st) == cudaSuccess;
     if (!ok) { cudaGetLastError(); return fail(HP_ERR_CUDA, "local realignment launch or copy failed"); }
     return HP_OK;
-}
-
-extern "C" int hp_local_realign_batch(hp_ctx* ctx, const hp_local_batch* b, hp_local_out* out) {
-    return hp::local_realign_select(ctx, b, out, nullptr, 0);
 }
 
 extern "C" int hp_edit_distance_batch(hp_ctx* ctx, uint32_t n_pairs, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* a_off,

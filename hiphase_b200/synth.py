@@ -436,14 +436,20 @@ def extend_with_reference(variants, ref, reference_buffer=15):
 
 
 def gen_local_block(rng, window=30000, n_var=40, n_reads=60, read_lo=4000, read_hi=15000, err=0.003, sv_max=1500,
-                    reference_buffer=15, p_ignored=0.02):
+                    reference_buffer=15, p_ignored=0.02, n_hom=0, p_noisy=0.0, err_noisy=0.05):
     """One block for local realignment: reference window, het variants (with reference prefix / postfix), reads sampled
     from the two haplotypes and their alignments (gap-free aligned segments, the M/=/X runs of a CIGAR).
-    Returns dict(variants=[Variant], jobs=[(var_lo, var_hi, read_pos, segs[(ref, read, len)], seq, quals)])."""
+    n_hom extra homozygous variants are carried by every read (they only matter to the graph of global realignment);
+    a fraction p_noisy of the reads is drawn with error rate err_noisy.
+    Returns dict(variants=[Variant] (hets), homs=[Variant], jobs=[(var_lo, var_hi, read_pos, segs[(ref, read, len)], seq, quals)])."""
     from .variants import Variant
     ref = _rand_seq(rng, window)
-    pos = np.sort(rng.choice(np.arange(100, window - sv_max - 300), n_var, replace=False))
-    vs, phase = [], []
+    n_all = n_var + n_hom
+    pos = np.sort(rng.choice(np.arange(100, window - sv_max - 300), n_all, replace=False))
+    is_hom = np.zeros(n_all, bool)
+    if n_hom:
+        is_hom[rng.choice(n_all, n_hom, replace=False)] = True
+    allv, phase = [], []
     for p in (int(x) for x in pos):
         u = rng.random()
         if u < 0.6:
@@ -472,8 +478,10 @@ def gen_local_block(rng, window=30000, n_var=40, n_reads=60, read_lo=4000, read_
                 v = Variant(0, _VT_SVINS, p, 1, ref[p:p + 1].tobytes(), ref[p:p + 1].tobytes() + _rand_seq(rng, L).tobytes())
             else:
                 v = Variant(0, _VT_SVDEL, p, L + 1, ref[p:p + L + 1].tobytes(), ref[p:p + 1].tobytes())
-        vs.append(v); phase.append(int(rng.integers(0, 2)))
-    raw = [(v.get_allele0(), v.get_allele1()) for v in vs]      # alleles before the reference extension
+        allv.append(v); phase.append(int(rng.integers(0, 2)))
+    raw = [(v.get_allele0(), v.get_allele1()) for v in allv]      # alleles before the reference extension
+    vs = [v for v, h in zip(allv, is_hom) if not h]
+    homs = [v for v, h in zip(allv, is_hom) if h]
     extend_with_reference(vs, ref, reference_buffer)
     for v in vs:
         if rng.random() < p_ignored:
@@ -483,10 +491,11 @@ def gen_local_block(rng, window=30000, n_var=40, n_reads=60, read_lo=4000, read_
     jobs = []
     for _ in range(n_reads):
         h = int(rng.integers(0, 2))
+        e_rate = err_noisy if (p_noisy > 0 and rng.random() < p_noisy) else err
         ln = int(rng.integers(read_lo, read_hi + 1))
         s = int(rng.integers(0, max(1, window - ln)))
         e = min(window, s + ln)
-        seq, segs = [], []
+        seq, segs = [], []              # seq: list of uint8 chunks
         rd = 0                          # read cursor
         run = None                      # open aligned run [ref_start, read_start, len]
 
@@ -496,40 +505,48 @@ def gen_local_block(rng, window=30000, n_var=40, n_reads=60, read_lo=4000, read_
                 segs.append(tuple(run))
             run = None
 
-        def emit_match(lo, hi):
+        def add_run(ref_pos, cnt):
             nonlocal rd, run
+            if cnt <= 0:
+                return
+            if run is None:
+                run = [ref_pos, rd, 0]
+            run[2] += cnt
+            seq.append(ref[ref_pos:ref_pos + cnt]); rd += cnt
+
+        def emit_match(lo, hi):
+            nonlocal rd
             n = hi - lo
             if n <= 0:
                 return
             r = rng.random(n)
-            for i in range(n):
-                x = r[i]
-                if x < err / 3:                      # deletion error: reference base without a read base
-                    close()
-                    continue
-                if x < 2 * err / 3:                  # insertion error before this base
-                    close()
-                    seq.append(int(_BASES[rng.integers(0, 4)])); rd += 1
-                if run is None:
-                    run = [lo + i, rd, 0]
-                run[2] += 1
-                seq.append(int(ref[lo + i])); rd += 1
+            start = 0
+            for ev in np.flatnonzero(r < 2 * e_rate / 3):
+                ev = int(ev)
+                add_run(lo + start, ev - start)
+                close()
+                if r[ev] < e_rate / 3:                # deletion error: reference base without a read base
+                    start = ev + 1
+                else:                                 # insertion error before this base
+                    seq.append(_BASES[rng.integers(0, 4, 1)]); rd += 1
+                    start = ev
+            add_run(lo + start, n - start)
 
         cur = s
-        for k, v in enumerate(vs):
+        for k, v in enumerate(allv):
             p, rl = v.position(), v.get_ref_len()
             if p < cur or p + rl > e:
                 continue
             emit_match(cur, p)
-            al = np.frombuffer(raw[k][1] if phase[k] == h else raw[k][0], np.uint8)
+            al = np.frombuffer(raw[k][1] if (is_hom[k] or phase[k] == h) else raw[k][0], np.uint8)
             m = min(len(al), rl)
             if run is None:
                 run = [p, rd, 0]
             run[2] += m
-            seq.extend(int(x) for x in al[:m]); rd += m
+            seq.append(al[:m]); rd += m
             if len(al) > m:                          # insertion
                 close()
-                seq.extend(int(x) for x in al[m:]); rd += len(al) - m
+                seq.append(al[m:]); rd += len(al) - m
             elif rl > m:                             # deletion
                 close()
             cur = p + rl
@@ -537,14 +554,14 @@ def gen_local_block(rng, window=30000, n_var=40, n_reads=60, read_lo=4000, read_
         close()
         if not segs:
             continue
-        seq = np.array(seq, np.uint8)
-        sub = rng.random(len(seq)) < err / 3
+        seq = np.concatenate(seq).astype(np.uint8)
+        sub = rng.random(len(seq)) < e_rate / 3
         seq[sub] = _BASES[rng.integers(0, 4, int(sub.sum()))]
         q = rng.integers(15, 60, len(seq)).astype(np.uint8)
         low = rng.random(len(seq)) < 0.03
         q[low] = rng.integers(0, 10, int(low.sum()))
         jobs.append((int(np.searchsorted(vpos, s)), int(np.searchsorted(vpos, e)), segs[0][0], segs, seq, q))
-    return dict(variants=vs, jobs=jobs, reference=ref)
+    return dict(variants=vs, homs=homs, jobs=jobs, reference=ref)
 
 
 def config_local(n_blocks=8, first_block=0, full_rows=False, **kw):
@@ -585,7 +602,7 @@ def config_realign(n_blocks=4, first_block=0, p_pair=0.15, **kw):
     blob, blob_len = [], 0
     refs, ref_base = [], 0
     var_lo, var_hi, read_pos, seg_off, sr, sd, sl, l_reads, l_quals = [], [], [], [0], [], [], [], [], []
-    rs, re, hl, hh, w_reads = [], [], [], [], []
+    rs, re, hl, hh, ml, mh, w_reads = [], [], [], [], [], [], []
     map_off, map_group, n_groups, var_off, het_base, vtypes = [0], [], [], [0], [], []
     for b in range(first_block, first_block + n_blocks):
         rng = np.random.default_rng(block_seed(8, b))
@@ -593,7 +610,8 @@ def config_realign(n_blocks=4, first_block=0, p_pair=0.15, **kw):
         vs = blk["variants"]
         base = len(allv)
         allv.extend(vs)
-        het_base.append(base)
+        wbase = len(wt["position"])                                 # the WFA table interleaves per block: hets, then homs
+        het_base.append(wbase)
         for v in vs:
             a0, a1 = v.get_truncated_allele0(), v.get_truncated_allele1()
             wt["position"].append(v.position() + ref_base); wt["ref_len"].append(v.get_ref_len())
@@ -601,6 +619,15 @@ def config_realign(n_blocks=4, first_block=0, p_pair=0.15, **kw):
             wt["allele1_off"].append(blob_len); wt["allele1_len"].append(len(a1)); blob.append(np.frombuffer(a1, np.uint8)); blob_len += len(a1)
             wt["index_allele0"].append(v.index_allele0); wt["vtype"].append(int(v.get_type())); wt["ignored"].append(0)
         vpos = [v.position() for v in vs]
+        homs = blk.get("homs", [])
+        hom_first = len(wt["position"])
+        for v in homs:                                               # hom calls follow the block's hets in the WFA table
+            a0, a1 = v.get_allele0(), v.get_allele1()
+            wt["position"].append(v.position() + ref_base); wt["ref_len"].append(v.get_ref_len())
+            wt["allele0_off"].append(blob_len); wt["allele0_len"].append(len(a0)); blob.append(np.frombuffer(a0, np.uint8)); blob_len += len(a0)
+            wt["allele1_off"].append(blob_len); wt["allele1_len"].append(len(a1)); blob.append(np.frombuffer(a1, np.uint8)); blob_len += len(a1)
+            wt["index_allele0"].append(v.index_allele0); wt["vtype"].append(int(v.get_type())); wt["ignored"].append(0)
+        hpos = [v.position() for v in homs]
         g = -1
         for (lo, hi, rp, segs, seq, q) in blk["jobs"]:
             if g < 0 or rng.random() >= p_pair:
@@ -611,12 +638,14 @@ def config_realign(n_blocks=4, first_block=0, p_pair=0.15, **kw):
                 sr.append(a); sd.append(r); sl.append(n)
             seg_off.append(len(sr))
             l_reads.append(seq); l_quals.append(q)
-            plan = plan_global_realignment(AlignedRead(rp, segs, seq.tobytes(), q), vpos, [])
+            plan = plan_global_realignment(AlignedRead(rp, segs, seq.tobytes(), q), vpos, hpos)
             if plan is None:
-                rs.append(ref_base); re.append(ref_base); hl.append(base); hh.append(base); w_reads.append(np.zeros(0, np.uint8))
+                rs.append(ref_base); re.append(ref_base); hl.append(wbase); hh.append(wbase); ml.append(hom_first); mh.append(hom_first)
+                w_reads.append(np.zeros(0, np.uint8))
             else:
                 rs.append(plan["ref_start"] + ref_base); re.append(plan["ref_end"] + ref_base)
-                hl.append(base + plan["het_lo"]); hh.append(base + plan["het_hi"])
+                hl.append(wbase + plan["het_lo"]); hh.append(wbase + plan["het_hi"])
+                ml.append(hom_first + plan["hom_lo"]); mh.append(hom_first + plan["hom_hi"])
                 w_reads.append(seq[plan["read_start"]:plan["read_end"]])
         map_off.append(len(map_group)); n_groups.append(g + 1); var_off.append(var_off[-1] + len(vs))
         vtypes.append([int(v.get_type()) for v in vs])
@@ -624,8 +653,61 @@ def config_realign(n_blocks=4, first_block=0, p_pair=0.15, **kw):
     wt["allele_bytes"] = np.concatenate(blob) if blob else np.zeros(1, np.uint8)
     nm = len(map_group)
     w_off = np.concatenate([[0], np.cumsum([len(r) for r in w_reads])])
-    wfa = WfaBatch(wt, np.concatenate(refs), rs, re, hl, hh, [0] * nm, [0] * nm,
+    wfa = WfaBatch(wt, np.concatenate(refs), rs, re, hl, hh, ml, mh,
                    np.concatenate(w_reads) if w_off[-1] else np.zeros(1, np.uint8), w_off)
     l_off = np.concatenate([[0], np.cumsum([len(r) for r in l_reads])])
     local = LocalBatch(variant_table(allv), var_lo, var_hi, read_pos, seg_off, sr, sd, sl, np.concatenate(l_reads), np.concatenate(l_quals), l_off)
     return dict(wfa=wfa, local=local, map_off=map_off, map_group=map_group, n_groups=n_groups, var_off=var_off, wfa_het_base=het_base), vtypes
+
+
+def merge_realign(pieces):
+    """Concatenates config_realign results (generated piecewise, e.g. by a process pool) into one: [(kwargs, vtypes)] -> same."""
+    from ._abi import LocalBatch, WfaBatch
+    if len(pieces) == 1:
+        return pieces[0]
+    cat = np.concatenate
+    vkeys = ("ref_len", "allele0_len", "allele1_len", "index_allele0", "vtype", "ignored")
+    wt = {k: [] for k in vkeys + ("position", "allele0_off", "allele1_off", "allele_bytes")}
+    lt = {k: [] for k in vkeys + ("position", "allele0_off", "allele1_off", "allele_bytes", "prefix_len", "postfix_len")}
+    w = {k: [] for k in ("reference", "ref_start", "ref_end", "het_lo", "het_hi", "hom_lo", "hom_hi", "read_bytes", "read_off")}
+    l = {k: [] for k in ("var_lo", "var_hi", "read_pos", "seg_off", "seg_ref_start", "seg_read_start", "seg_len", "read_bytes", "read_quals", "read_off")}
+    map_off, map_group, n_groups, var_off, het_base, vtypes = [np.zeros(1, np.uint64)], [], [], [np.zeros(1, np.uint64)], [], []
+    o = dict(ref=0, wab=0, wnv=0, wrb=0, lab=0, lnv=0, lseg=0, lrb=0, nm=0, nvar=0)
+    for d, vt in pieces:
+        W, L = d["wfa"], d["local"]
+        for k in vkeys:
+            wt[k].append(getattr(W, k)); lt[k].append(getattr(L, k))
+        wt["position"].append(W.position + o["ref"]); lt["position"].append(L.position)
+        wt["allele0_off"].append(W.allele0_off + np.uint64(o["wab"])); wt["allele1_off"].append(W.allele1_off + np.uint64(o["wab"]))
+        lt["allele0_off"].append(L.allele0_off + np.uint64(o["lab"])); lt["allele1_off"].append(L.allele1_off + np.uint64(o["lab"]))
+        wt["allele_bytes"].append(W.allele_bytes); lt["allele_bytes"].append(L.allele_bytes)
+        lt["prefix_len"].append(L.prefix_len); lt["postfix_len"].append(L.postfix_len)
+        w["reference"].append(W.reference)
+        w["ref_start"].append(W.ref_start + np.uint64(o["ref"])); w["ref_end"].append(W.ref_end + np.uint64(o["ref"]))
+        for k in ("het_lo", "het_hi", "hom_lo", "hom_hi"):
+            w[k].append(getattr(W, k) + np.uint32(o["wnv"]))
+        w["read_bytes"].append(W.read_bytes[: int(W.read_off[-1])]); w["read_off"].append(W.read_off[:-1] + np.uint64(o["wrb"]))
+        l["var_lo"].append(L.var_lo + np.uint32(o["lnv"])); l["var_hi"].append(L.var_hi + np.uint32(o["lnv"]))
+        l["read_pos"].append(L.read_pos)
+        l["seg_off"].append(L.seg_off[:-1] + np.uint64(o["lseg"]))
+        for k in ("seg_ref_start", "seg_read_start", "seg_len"):
+            l[k].append(getattr(L, k)[: int(L.seg_off[-1])])
+        l["read_bytes"].append(L.read_bytes[: int(L.read_off[-1])]); l["read_quals"].append(L.read_quals[: int(L.read_off[-1])])
+        l["read_off"].append(L.read_off[:-1] + np.uint64(o["lrb"]))
+        mo, vo = np.asarray(d["map_off"], np.uint64), np.asarray(d["var_off"], np.uint64)
+        map_off.append(mo[1:] + np.uint64(o["nm"])); var_off.append(vo[1:] + np.uint64(o["nvar"]))
+        map_group.append(np.asarray(d["map_group"], np.uint32)); n_groups.append(np.asarray(d["n_groups"], np.uint32))
+        het_base.append(np.asarray(d["wfa_het_base"], np.uint32) + np.uint32(o["wnv"]))
+        vtypes.extend(vt)
+        o["ref"] += len(W.reference); o["wab"] += len(W.allele_bytes); o["wnv"] += len(W.position); o["wrb"] += int(W.read_off[-1])
+        o["lab"] += len(L.allele_bytes); o["lnv"] += len(L.position); o["lseg"] += int(L.seg_off[-1]); o["lrb"] += int(L.read_off[-1])
+        o["nm"] += int(mo[-1]); o["nvar"] += int(vo[-1])
+    wtab = {k: cat(v) for k, v in wt.items()}
+    ltab = {k: cat(v) for k, v in lt.items()}
+    wfa = WfaBatch(wtab, cat(w["reference"]), cat(w["ref_start"]), cat(w["ref_end"]), cat(w["het_lo"]), cat(w["het_hi"]), cat(w["hom_lo"]),
+                   cat(w["hom_hi"]), cat(w["read_bytes"]), cat(w["read_off"] + [np.array([o["wrb"]], np.uint64)]))
+    local = LocalBatch(ltab, cat(l["var_lo"]), cat(l["var_hi"]), cat(l["read_pos"]), cat(l["seg_off"] + [np.array([o["lseg"]], np.uint64)]),
+                       cat(l["seg_ref_start"]), cat(l["seg_read_start"]), cat(l["seg_len"]), cat(l["read_bytes"]), cat(l["read_quals"]),
+                       cat(l["read_off"] + [np.array([o["lrb"]], np.uint64)]))
+    return dict(wfa=wfa, local=local, map_off=cat(map_off), map_group=cat(map_group), n_groups=cat(n_groups), var_off=cat(var_off),
+                wfa_het_base=cat(het_base)), vtypes

@@ -28,7 +28,7 @@ def _same(out, ref):
     assert np.array_equal(out.group_class, ref.group_class)
 
 
-SMALL = dict(window=9000, n_var=18, n_reads=40, read_lo=1500, read_hi=4000, sv_max=300)
+SMALL = dict(window=9000, n_var=18, n_hom=8, n_reads=40, read_lo=1500, read_hi=4000, sv_max=300)
 
 
 def test_oracle_replays_the_switch_off_rule():
