@@ -98,6 +98,7 @@ struct hp_ctx {
     hp::DevBuf wfa_ws, wfa_in, wfa_out, wfa_graph;
     bool wfa_no_hint = false;               // test aid: start with an unsized graph workspace (exercises the regrow path)
     bool wfa_host_build = false;            // debug / A-B aid: build the graphs on the host instead of on the device
+    uint64_t wfa_layout[4] = {0, 0, 0, 0};  // {workspace pointer, slab bytes, table cap, warps} the hash keys were last zeroed for
     uint32_t wfa_table_cap = 1u << 15;      // (node, diagonal) hash slots per warp; grown 8x on overflow
     std::vector<int32_t> wfa_h_status;
     std::vector<uint32_t> wfa_h_score, wfa_h_nodes;

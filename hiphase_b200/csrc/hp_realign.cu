@@ -100,8 +100,10 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         std::vector<int32_t> o_st(ns, -1);
         hp_local_out co{};
         co.alleles = o_al.data(); co.quals = o_q.data(); co.status = o_st.data();
+        const auto tl0 = std::chrono::steady_clock::now();
         int rc = hp_local_realign_batch(ctx, &cb, &co);
         if (rc != HP_OK) return rc;
+        if (getenv("HP_DBG_REALIGN_TIMING")) fprintf(stderr, "[hp_realign]   local call on %zu jobs: %.1f ms (kernel %.2f ms)\n", ns, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count(), hp_last_kernel_ms(ctx));
         for (size_t k = 0; k < ns; k++) {
             const uint32_t j = sel[k];
             have_local[j] = 1;

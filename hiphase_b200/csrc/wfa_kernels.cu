@@ -67,6 +67,7 @@ struct WfaArgs {
     uint32_t table_cap;            // hash slots per warp (power of two)
     uint32_t set_words_max;        // set words the slab layout was sized for
     uint32_t* ticket;
+    uint32_t* epochs;              // [warps of the launch] job counter of each warp's table (persists across launches)
     // outputs
     int32_t*  out_status;
     uint32_t* out_score;
@@ -138,6 +139,7 @@ struct WfaCtx {
     const WfaArgs* a;
     WfaSlab s;
     uint32_t lane, cap, sw, stride;
+    uint32_t epoch;                // this warp's job counter (tags the hash keys)
     const WfaNode* nodes;          // this job's nodes
     const uint8_t* read;
     uint32_t read_len;
@@ -162,10 +164,22 @@ __device__ __forceinline__ uint64_t ld64_unaligned(const uint8_t* p) {
     return (lo >> sh) | (__ldg(q + 1) << (64u - sh));
 }
 
-__device__ __forceinline__ uint64_t wfa_key(uint32_t node, int32_t diag) { return ((uint64_t)node << 32) | (uint32_t)diag; }
-__device__ __forceinline__ uint32_t wfa_hash(uint64_t k) {
+// key = epoch (20 bits) | node (12 bits) | diagonal (32 bits).  The epoch is the warp's job counter: keys left behind by earlier
+// jobs read as EMPTY, so the table is never cleared between jobs (it is zeroed once when the workspace is laid out; epochs
+// start at 1).  The slot index keeps blocks of neighbouring diagonals of a node together (the live diagonals of a node are a contiguous
+// range and the lanes of a batch walk them roughly in order), so a batch touches a few runs of slots instead of 32 random lines.
+constexpr uint32_t kEpochShift = 44, kEpochMax = 0xffffeu;
+__device__ __forceinline__ uint64_t wfa_key(uint32_t epoch, uint32_t node, int32_t diag) {
+    return ((uint64_t)epoch << kEpochShift) | ((uint64_t)node << 32) | (uint32_t)diag;
+}
+#ifndef HP_WFA_HASH_BLOCK
+#define HP_WFA_HASH_BLOCK 4
+#endif
+__device__ __forceinline__ uint32_t wfa_hash(uint32_t node, int32_t diag) {
+    // blocks of 2^HP_WFA_HASH_BLOCK neighbouring diagonals of a node stay together, the blocks are scattered uniformly
+    uint64_t k = ((uint64_t)node << 32) | (uint32_t)(diag >> HP_WFA_HASH_BLOCK);
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 29;
-    return (uint32_t)k;
+    return ((uint32_t)k << HP_WFA_HASH_BLOCK) | ((uint32_t)diag & ((1u << HP_WFA_HASH_BLOCK) - 1u));
 }
 
 // Pushes one wave per participating lane (act) of this warp into generation tag `gen_tag` (parity gp) of slot
@@ -200,15 +214,16 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
             off += adv; pos += adv; c.n_cmp += adv;
         }
         // ---- find or insert the slot ----
-        const uint64_t key = wfa_key(node, diag);
-        uint32_t h = wfa_hash(key) & (c.cap - 1);
+        const uint64_t key = wfa_key(c.epoch, node, diag);
+        uint32_t h = wfa_hash(node, diag) & (c.cap - 1);
         uint32_t slot = kNil;
         bool created = false;
         for (uint32_t probe = 0; probe < c.cap; probe++) {
             unsigned long long k = c.s.keys[h];
-            if (k == kEmptyKey) {
-                k = atomicCAS(&c.s.keys[h], kEmptyKey, (unsigned long long)key);
-                if (k == kEmptyKey) { slot = h; created = true; break; }
+            if ((uint32_t)(k >> kEpochShift) != c.epoch) {                   // empty: never used, or left by an earlier job
+                const unsigned long long seen = k;
+                k = atomicCAS(&c.s.keys[h], seen, (unsigned long long)key);
+                if (k == seen) { slot = h; created = true; break; }
             }
             if (k == key) { slot = h; break; }
             h = (h + 1) & (c.cap - 1);
@@ -279,7 +294,14 @@ __global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
             const uint32_t sink = n_nodes - 1;
             const uint32_t max_chunks = c.cap / 8;
 
-            for (uint32_t i = lane; i < c.cap; i += 32) c.s.keys[i] = kEmptyKey;
+            // a fresh epoch instead of a table clear (the clear only happens when the 20-bit counter wraps)
+            {
+                uint32_t e = 0;
+                if (lane == 0) { e = a.epochs[gwarp] + 1u; if (e > kEpochMax) e = 0; a.epochs[gwarp] = e ? e : 1u; }
+                e = __shfl_sync(HP_FULL_MASK, e, 0);
+                if (e == 0) { for (uint32_t i = lane; i < c.cap; i += 32) c.s.keys[i] = 0ull; e = 1u; }
+                c.epoch = e;
+            }
             for (uint32_t i = lane; i < n_nodes; i += 32) {
                 c.s.seg_len[0][i] = 0; c.s.seg_len[1][i] = 0; c.s.late_head[i] = kNil;
             }
@@ -871,11 +893,23 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     a.table_cap = table_cap; a.set_words_max = sw_max;
     a.slab_bytes = wfa_slab_bytes(table_cap, sw_max);
-    if (!ctx->wfa_ws.reserve(a.slab_bytes * (uint64_t)n_ctas * kWfaWarps + 256))
+    const uint64_t n_warps = (uint64_t)n_ctas * kWfaWarps;
+    const uint64_t epoch_bytes = (4 * n_warps + 255) & ~255ull;
+    if (!ctx->wfa_ws.reserve(a.slab_bytes * n_warps + 256 + epoch_bytes))
         return wfa_fail(ctx, HP_ERR_OUT_OF_MEMORY, "WFA workspace allocation failed");
-    a.slabs = (uint8_t*)ctx->wfa_ws.ptr + 256;
     a.ticket = (uint32_t*)ctx->wfa_ws.ptr;
+    a.epochs = (uint32_t*)((uint8_t*)ctx->wfa_ws.ptr + 256);
+    a.slabs = (uint8_t*)ctx->wfa_ws.ptr + 256 + epoch_bytes;
     WFA_CUDA(ctx, cudaMemsetAsync(a.ticket, 0, 256, st));
+    // the hash keys are epoch-tagged and never cleared per job: zero them (and the epochs) whenever the tables move
+    {
+        const uint64_t layout[4] = {(uint64_t)(uintptr_t)ctx->wfa_ws.ptr, a.slab_bytes, (uint64_t)table_cap, n_warps};
+        if (memcmp(layout, ctx->wfa_layout, sizeof(layout)) != 0) {
+            WFA_CUDA(ctx, cudaMemsetAsync(a.epochs, 0, epoch_bytes, st));
+            WFA_CUDA(ctx, cudaMemset2DAsync(a.slabs, a.slab_bytes, 0, (size_t)table_cap * 8, n_warps, st));
+            memcpy(ctx->wfa_layout, layout, sizeof(layout));
+        }
+    }
 
     const uint32_t tw = out->traversed ? out->trav_words : 0;
     const size_t out_bytes = al(4ull * nj) * 3 + al(n_rows) * 2 + al(8ull * nj * tw) + al(32ull * nj) + 4096;
