@@ -43,3 +43,31 @@ def wfa_batch_single(reference, hets, homs, ref_start, ref_end, reads):
     return A.WfaBatch(vt, ref, [ref_start] * n, [ref_end] * n, [0] * n, [len(hets)] * n, [len(hets)] * n,
                       [len(hets) + len(homs)] * n, np.concatenate(rb) if n and sum(len(x) for x in rb) else np.zeros(0, np.uint8),
                       read_off)
+
+
+# ---- fixtures dumped from genuine HiPhase (tools/reference_dump) -------------------------------------------------------
+REFERENCE_BLOCKS = os.path.join(GOLDEN, "reference_blocks")
+
+
+def write_reference_result(path, h1, h2, stats7):
+    """The `.ref` format of tools/reference_dump/hiphase_dump_blocks.patch (used by the self-test of the harness)."""
+    h1 = np.asarray(h1, np.uint8); h2 = np.asarray(h2, np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"HPREF1\0\0" + np.uint64(len(h1)).tobytes() + h1.tobytes() + h2.tobytes() + np.asarray(stats7, "<u8").tobytes())
+
+
+def read_reference_result(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"HPREF1\0\0", "not a HiPhase reference dump: " + path
+    n = int(np.frombuffer(raw, "<u8", 1, 8)[0])
+    assert len(raw) == 16 + 2 * n + 56, "truncated reference dump: " + path
+    h1 = np.frombuffer(raw, np.uint8, n, 16); h2 = np.frombuffer(raw, np.uint8, n, 16 + n)
+    return h1, h2, np.frombuffer(raw, "<u8", 7, 16 + 2 * n)
+
+
+def reference_fixtures(directory=REFERENCE_BLOCKS):
+    """[(path.hpb, path.ref)] of the blocks dumped from the Rust binary, sorted."""
+    if not os.path.isdir(directory):
+        return []
+    stems = sorted(f[:-4] for f in os.listdir(directory) if f.endswith(".hpb") and os.path.exists(os.path.join(directory, f[:-4] + ".ref")))
+    return [(os.path.join(directory, s + ".hpb"), os.path.join(directory, s + ".ref")) for s in stems]
