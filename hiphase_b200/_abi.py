@@ -518,3 +518,42 @@ class RealignOut:
         return BlockBatch(self._batch.var_off, self.read_off, self.read_start[:nr], self.read_end[:nr], self.cell_off[:nr + 1],
                           self.alleles[:nc], self.quals[:nc], np.zeros(nv, np.uint8) if ignored is None else ignored,
                           np.ones(nv, np.uint8) if is_snv is None else is_snv)
+
+
+# ---- CIGAR projection of global realignment (read_parsing.rs:672-742) ---------------------------------------------------
+class hp_plan_batch(C.Structure):
+    _fields_ = [("n_maps", C.c_uint32), ("map_block", u32p), ("seg_off", u64p), ("seg_ref_start", i64p), ("seg_read_start", u32p),
+                ("seg_len", u32p), ("n_blocks", C.c_uint32), ("het_first", u32p), ("het_pos", i64p), ("hom_first", u32p), ("hom_pos", i64p)]
+
+
+class hp_plan_out(C.Structure):
+    _fields_ = [("ref_start", u64p), ("ref_end", u64p), ("het_lo", u32p), ("het_hi", u32p), ("hom_lo", u32p), ("hom_hi", u32p),
+                ("read_start", u32p), ("read_end", u32p)]
+
+
+class PlanBatch:
+    def __init__(self, map_block, seg_off, seg_ref_start, seg_read_start, seg_len, het_first, het_pos, hom_first, hom_pos):
+        self.map_block = _np(map_block, np.uint32); self.seg_off = _np(seg_off, np.uint64)
+        self.seg_ref_start = _np(seg_ref_start, np.int64); self.seg_read_start = _np(seg_read_start, np.uint32)
+        self.seg_len = _np(seg_len, np.uint32)
+        self.het_first = _np(het_first, np.uint32); self.het_pos = _np(het_pos, np.int64)
+        self.hom_first = _np(hom_first, np.uint32); self.hom_pos = _np(hom_pos, np.int64)
+        self.n_maps, self.n_blocks = len(self.map_block), len(self.het_first) - 1
+
+    def as_struct(self):
+        return hp_plan_batch(self.n_maps, ptr(self.map_block, u32p), ptr(self.seg_off, u64p), ptr(self.seg_ref_start, i64p),
+                             ptr(self.seg_read_start, u32p), ptr(self.seg_len, u32p), self.n_blocks, ptr(self.het_first, u32p),
+                             ptr(self.het_pos, i64p), ptr(self.hom_first, u32p), ptr(self.hom_pos, i64p))
+
+
+class PlanOut:
+    FIELDS = ("ref_start", "ref_end", "het_lo", "het_hi", "hom_lo", "hom_hi", "read_start", "read_end")
+
+    def __init__(self, batch):
+        n = max(batch.n_maps, 1)
+        self.ref_start = np.zeros(n, np.uint64); self.ref_end = np.zeros(n, np.uint64)
+        for f in self.FIELDS[2:]:
+            setattr(self, f, np.zeros(n, np.uint32))
+
+    def as_struct(self):
+        return hp_plan_out(ptr(self.ref_start, u64p), ptr(self.ref_end, u64p), *[ptr(getattr(self, f), u32p) for f in self.FIELDS[2:]])

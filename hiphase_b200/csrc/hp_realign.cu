@@ -220,3 +220,91 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
     if (timing) fprintf(stderr, "[hp_realign] %u mappings: wfa %.1f ms, local(failed) %.1f, replay+local(late) %.1f, rows %.1f, assemble %.1f\n", nm, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
     return rc_asm;
 }
+
+
+// =================================================================================================================
+// CIGAR projection of global realignment (read_parsing.rs:672-742) on the device: one thread per mapping.
+// =================================================================================================================
+namespace {
+
+__global__ void wfa_plan_kernel(hp_plan_batch b, hp_plan_out o, int* bad) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.n_maps) return;
+    const uint64_t s0 = b.seg_off[j], s1 = b.seg_off[j + 1];
+    const uint32_t blk = b.map_block[j];
+    if (s1 <= s0 || blk >= b.n_blocks) { atomicExch(bad, (int)j + 1); return; }              // assert!(max_position >= min_position)
+    const int64_t min_position = b.seg_ref_start[s0];                                         // :677-685 (segments ascend)
+    const int64_t max_position = b.seg_ref_start[s1 - 1] + (int64_t)b.seg_len[s1 - 1] - 1;
+    auto lower = [](const int64_t* p, uint32_t lo, uint32_t hi, int64_t v) {                  // first index with p[i] >= v
+        while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (p[mid] < v) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    // aligned_range.contains(position): min <= position <= max (:692-701)
+    const uint32_t h0 = b.het_first[blk], h1 = b.het_first[blk + 1];
+    const uint32_t het_lo = lower(b.het_pos, h0, h1, min_position), het_hi = lower(b.het_pos, h0, h1, max_position + 1);
+    const uint32_t m0 = b.hom_first[blk], m1 = b.hom_first[blk + 1];
+    const uint32_t hom_lo = lower(b.hom_pos, m0, m1, min_position), hom_hi = lower(b.hom_pos, m0, m1, max_position + 1);
+    const bool no_het = het_hi <= het_lo, no_hom = hom_hi <= hom_lo;       // no overlap: the empty range at the block's first call
+    o.ref_start[j] = (uint64_t)min_position; o.ref_end[j] = (uint64_t)(max_position + 1);
+    o.het_lo[j] = no_het ? h0 : het_lo; o.het_hi[j] = no_het ? h0 : het_hi;
+    o.hom_lo[j] = no_hom ? m0 : hom_lo; o.hom_hi[j] = no_hom ? m0 : hom_hi;                   // unwrap_or(0) / last stays 0 (:718-729)
+    o.read_start[j] = b.seg_read_start[s0];                                                   // :737-741
+    o.read_end[j] = b.seg_read_start[s1 - 1] + b.seg_len[s1 - 1];
+}
+
+}  // namespace
+
+extern "C" int hp_wfa_plan_batch(hp_ctx* ctx, const hp_plan_batch* in, hp_plan_out* out) {
+    if (!ctx || !in || !out || !out->ref_start || !out->ref_end || !out->het_lo || !out->het_hi || !out->hom_lo || !out->hom_hi ||
+        !out->read_start || !out->read_end) return HP_ERR_INVALID_INPUT;
+    const uint32_t nm = in->n_maps, nb = in->n_blocks;
+    if (nm == 0) return HP_OK;
+    if (!in->map_block || !in->seg_off || !in->het_first || !in->hom_first) return HP_ERR_INVALID_INPUT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HP_ERR_CUDA, "cudaSetDevice failed");
+    const uint64_t ns = in->seg_off[nm];
+    const uint64_t nh = in->het_first[nb], nhm = in->hom_first[nb];
+    for (uint32_t b = 0; b < nb; b++) {
+        if (in->het_first[b + 1] < in->het_first[b] || in->hom_first[b + 1] < in->hom_first[b]) return fail(ctx, HP_ERR_INVALID_INPUT, "call ranges must be non-decreasing");
+        for (uint32_t k = in->het_first[b]; k + 1 < in->het_first[b + 1]; k++) if (in->het_pos[k] > in->het_pos[k + 1]) return fail(ctx, HP_ERR_INVALID_INPUT, "het positions of a block must ascend");
+        for (uint32_t k = in->hom_first[b]; k + 1 < in->hom_first[b + 1]; k++) if (in->hom_pos[k] > in->hom_pos[k + 1]) return fail(ctx, HP_ERR_INVALID_INPUT, "hom positions of a block must ascend");
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t in_bytes = al(4ull * nm) + al(8ull * (nm + 1)) + al(8 * ns) + al(4 * ns) * 2 + al(4ull * (nb + 1)) * 2 + al(8 * nh) + al(8 * nhm) + 4096;
+    const size_t out_bytes = al(8ull * nm) * 2 + al(4ull * nm) * 6 + 4096;
+    if (!ctx->stage_in.reserve(in_bytes) || !ctx->stage_out.reserve(out_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "staging allocation failed");
+    cudaStream_t st = ctx->stream;
+    uint8_t* p = (uint8_t*)ctx->stage_in.ptr;
+    bool ok = true;
+    auto up = [&](const void* src, size_t bytes) { uint8_t* d = p; p += al(bytes); if (bytes) ok &= cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess; return d; };
+    hp_plan_batch d = *in;
+    d.map_block = (const uint32_t*)up(in->map_block, 4ull * nm); d.seg_off = (const uint64_t*)up(in->seg_off, 8ull * (nm + 1));
+    d.seg_ref_start = (const int64_t*)up(in->seg_ref_start, 8 * ns); d.seg_read_start = (const uint32_t*)up(in->seg_read_start, 4 * ns);
+    d.seg_len = (const uint32_t*)up(in->seg_len, 4 * ns);
+    d.het_first = (const uint32_t*)up(in->het_first, 4ull * (nb + 1)); d.het_pos = (const int64_t*)up(in->het_pos, 8 * nh);
+    d.hom_first = (const uint32_t*)up(in->hom_first, 4ull * (nb + 1)); d.hom_pos = (const int64_t*)up(in->hom_pos, 8 * nhm);
+    uint8_t* q = (uint8_t*)ctx->stage_out.ptr;
+    auto carve = [&](size_t bytes) { uint8_t* r = q; q += al(bytes); return r; };
+    hp_plan_out o;
+    o.ref_start = (uint64_t*)carve(8ull * nm); o.ref_end = (uint64_t*)carve(8ull * nm);
+    o.het_lo = (uint32_t*)carve(4ull * nm); o.het_hi = (uint32_t*)carve(4ull * nm); o.hom_lo = (uint32_t*)carve(4ull * nm); o.hom_hi = (uint32_t*)carve(4ull * nm);
+    o.read_start = (uint32_t*)carve(4ull * nm); o.read_end = (uint32_t*)carve(4ull * nm);
+    int* bad = (int*)carve(4);
+    ok &= cudaMemsetAsync(bad, 0, 4, st) == cudaSuccess;
+    wfa_plan_kernel<<<(nm + 255) / 256, 256, 0, st>>>(d, o, bad);
+    ok &= cudaGetLastError() == cudaSuccess;
+    ctx->launches++;
+    int h_bad = 0;
+    ok &= cudaMemcpyAsync(out->ref_start, o.ref_start, 8ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->ref_end, o.ref_end, 8ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->het_lo, o.het_lo, 4ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->het_hi, o.het_hi, 4ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->hom_lo, o.hom_lo, 4ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->hom_hi, o.hom_hi, 4ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->read_start, o.read_start, 4ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(out->read_end, o.read_end, 4ull * nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaStreamSynchronize(st) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return fail(ctx, HP_ERR_CUDA, "CIGAR projection launch or copy failed"); }
+    if (h_bad) return fail(ctx, HP_ERR_INVALID_INPUT, "mapping " + std::to_string(h_bad - 1) + " has no aligned segment or an invalid block (the reference asserts, read_parsing.rs:686)");
+    return HP_OK;
+}

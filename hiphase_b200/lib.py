@@ -19,7 +19,7 @@ EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destr
            "hp_pack_get_blocks", "hp_pack_close", "hp_pack_last_error", "hp_write_phase_stats",
            "hp_ctx_set_lanes", "hp_astar_submit", "hp_astar_poll", "hp_astar_wait", "hp_host_alloc", "hp_host_free",
            "hp_host_register", "hp_host_unregister", "hp_block_costs", "hp_lpt_partition", "hp_comm_unique_id",
-           "hp_comm_init", "hp_comm_destroy", "hp_comm_allgather", "hp_comm_gather_results", "hp_realign_block_batch")
+           "hp_comm_init", "hp_comm_destroy", "hp_comm_allgather", "hp_comm_gather_results", "hp_realign_block_batch", "hp_wfa_plan_batch")
 
 _LIB = None
 
@@ -86,6 +86,7 @@ def lib():
         L.hp_comm_init.argtypes = [C.c_void_p, A.u8p, C.c_int, C.c_int]
         L.hp_comm_destroy.argtypes = [C.c_void_p]
         L.hp_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.hp_wfa_plan_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_plan_batch), C.POINTER(A.hp_plan_out)]
         L.hp_realign_block_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_realign_batch), C.POINTER(A.hp_realign_out)]
         L.hp_comm_gather_results.argtypes = [C.c_void_p, C.c_uint64, A.u64p, A.u64p, C.POINTER(A.hp_astar_out), C.c_uint64,
                                              A.u64p, C.c_int, C.POINTER(A.hp_astar_out)]
@@ -328,6 +329,13 @@ class Context:
         out = A.RealignOut(batch)
         bs = batch.as_struct()
         self.check(lib().hp_realign_block_batch(self._h, C.byref(bs), C.byref(out.as_struct())))
+        return out
+
+    def wfa_plan_batch(self, batch):
+        """hp_wfa_plan_batch: the CIGAR projection of global realignment for a PlanBatch.  Returns a PlanOut."""
+        out = A.PlanOut(batch)
+        bs = batch.as_struct()
+        self.check(lib().hp_wfa_plan_batch(self._h, C.byref(bs), C.byref(out.as_struct())))
         return out
 
     def astar_solve_device(self, dev_batch_struct, n_vars, n_reads, n_cells, max_block_vars, dev_out_struct, stream):

@@ -474,6 +474,38 @@ typedef struct hp_realign_out {
 /* Host buffers in / out.  A local-realignment job the reference would panic on returns HP_ERR_UNSUPPORTED. */
 int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* batch, hp_realign_out* out);
 
+/* ---- CIGAR projection of global realignment on the device: the pre-WFA half of global_realignment
+ *      (src/read_parsing.rs:672-742).  For mapping j with aligned segments [seg_off[j], seg_off[j+1]) (the gap-free M/=/X runs
+ *      of aligned_pairs(), ascending) against the het / hom calls of its block (positions ascending):
+ *        ref_start / ref_end   min_position, max_position + 1                                   (:677-689, :773-774)
+ *        het_lo / het_hi       first_overlap, last_overlap: calls with min <= position <= max   (:692-701), table indices
+ *        hom_lo / hom_hi       first_hom_overlap (0 -> hom_first when none), last_hom_overlap   (:718-729)
+ *        read_start / read_end the read slice aligned against: read[read_start .. read_end)     (:737-741)
+ *      het_lo == het_hi marks a mapping that overlaps no het call (the short circuit at :703-712).  These are exactly the
+ *      per-job fields of hp_wfa_batch.  A mapping without aligned segments is HP_ERR_INVALID_INPUT (assert at :686). ---- */
+typedef struct hp_plan_batch {
+    uint32_t        n_maps;
+    const uint32_t* map_block;        /* [n_maps] block of the mapping                                                  */
+    const uint64_t* seg_off;          /* [n_maps+1]                                                                     */
+    const int64_t*  seg_ref_start;    /* [n_segs]                                                                       */
+    const uint32_t* seg_read_start;   /* [n_segs]                                                                       */
+    const uint32_t* seg_len;          /* [n_segs]                                                                       */
+    uint32_t        n_blocks;
+    const uint32_t* het_first;        /* [n_blocks+1] het calls of block b = table entries [het_first[b], het_first[b+1]) */
+    const int64_t*  het_pos;          /* [het_first[n_blocks]] Variant::position(), ascending inside a block             */
+    const uint32_t* hom_first;        /* [n_blocks+1]                                                                   */
+    const int64_t*  hom_pos;          /* [hom_first[n_blocks]]                                                          */
+} hp_plan_batch;
+
+typedef struct hp_plan_out {
+    uint64_t* ref_start;  uint64_t* ref_end;      /* [n_maps]                                                            */
+    uint32_t* het_lo;     uint32_t* het_hi;       /* [n_maps] indices into het_pos                                       */
+    uint32_t* hom_lo;     uint32_t* hom_hi;       /* [n_maps] indices into hom_pos                                       */
+    uint32_t* read_start; uint32_t* read_end;     /* [n_maps]                                                            */
+} hp_plan_out;
+
+int hp_wfa_plan_batch(hp_ctx* ctx, const hp_plan_batch* batch, hp_plan_out* out);
+
 /* ---- packed phase-block container + stats writer ----------------------------------------
  * The wire / on-disk form of a block batch, "HPB200" v1 (layout in csrc/hp_pack.cu): what a front end that still owns
  * VCF / BAM decoding (the HiPhase Rust code up to src/phaser.rs:541, or any other reader) writes, and what the batch

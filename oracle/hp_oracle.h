@@ -97,6 +97,8 @@ int hpo_wfa_align_batch(const hp_params* params, const hp_wfa_batch* batch, hp_w
 
 /* ---- the read loop of load_full_read_segments (src/read_parsing.rs:545-629), one mapping at a time in BAM order ---- */
 int hpo_realign_block_batch(const hp_params* params, const hp_realign_batch* batch, hp_realign_out* out);
+/* the pre-WFA half of global_realignment (src/read_parsing.rs:672-742) */
+int hpo_wfa_plan_batch(const hp_plan_batch* batch, hp_plan_out* out);
 
 #ifdef __cplusplus
 }

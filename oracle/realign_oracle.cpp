@@ -3,6 +3,7 @@
 // (hpo_wfa_align_batch on a one-job view = read_parsing.rs:653-867) and local_realignment (hpo_local_realign_batch on a
 // one-job view = read_parsing.rs:121-503).  One mapping at a time, in BAM order, exactly like the reference: nothing is batched
 // or reordered here, so the order-dependent switch-off rule (:593-600) is exercised the way the reference runs it.
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -123,4 +124,40 @@ extern "C" int hpo_realign_block_batch(const hp_params* params, const hp_realign
     rows.row_start = row_start.data(); rows.row_cell_off = row_cell_off.data(); rows.alleles = al.data(); rows.quals = q.data();
     rows.min_matched_alleles = in->min_matched_alleles;
     return hpo_assemble_blocks(&rows, &out->assembled);
+}
+
+
+// The pre-WFA half of global_realignment, src/read_parsing.rs:672-742, per mapping: aligned pairs -> min / max position, the
+// overlapped het / hom calls and the aligned slice of the read.  Loops over every aligned pair and every call like the reference.
+extern "C" int hpo_wfa_plan_batch(const hp_plan_batch* b, hp_plan_out* o) {
+    for (uint32_t j = 0; j < b->n_maps; j++) {
+        int64_t min_position = INT64_MAX, max_position = INT64_MIN;                          // :675-676
+        int64_t read_at_min = 0, read_at_max = 0;
+        for (uint64_t s = b->seg_off[j]; s < b->seg_off[j + 1]; s++)
+            for (uint32_t k = 0; k < b->seg_len[s]; k++) {                                   // for bp in read.aligned_pairs() (:677-684)
+                const int64_t ref_index = b->seg_ref_start[s] + k, segment_index = (int64_t)b->seg_read_start[s] + k;
+                if (ref_index < min_position) { min_position = ref_index; read_at_min = segment_index; }
+                if (ref_index > max_position) { max_position = ref_index; read_at_max = segment_index; }
+            }
+        if (!(max_position >= min_position)) return 1;                                       // :686
+        const uint32_t blk = b->map_block[j];
+        bool have_first = false; uint32_t first_overlap = b->het_first[blk], last_overlap = b->het_first[blk];
+        for (uint32_t i = b->het_first[blk]; i < b->het_first[blk + 1]; i++)                 // :692-701
+            if (b->het_pos[i] >= min_position && b->het_pos[i] < max_position + 1) {
+                if (!have_first) { first_overlap = i; have_first = true; }
+                last_overlap = i + 1;
+            }
+        if (!have_first) last_overlap = first_overlap;
+        bool have_hom = false; uint32_t first_hom = b->hom_first[blk], last_hom = b->hom_first[blk];
+        for (uint32_t i = b->hom_first[blk]; i < b->hom_first[blk + 1]; i++)                 // :718-729
+            if (b->hom_pos[i] >= min_position && b->hom_pos[i] < max_position + 1) {
+                if (!have_hom) { first_hom = i; have_hom = true; }
+                last_hom = i + 1;
+            }
+        if (!have_hom) last_hom = first_hom;
+        o->ref_start[j] = (uint64_t)min_position; o->ref_end[j] = (uint64_t)(max_position + 1);
+        o->het_lo[j] = first_overlap; o->het_hi[j] = last_overlap; o->hom_lo[j] = first_hom; o->hom_hi[j] = last_hom;
+        o->read_start[j] = (uint32_t)read_at_min; o->read_end[j] = (uint32_t)read_at_max + 1;  // :737-741
+    }
+    return 0;
 }

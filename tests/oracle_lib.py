@@ -218,3 +218,10 @@ def realign_block_batch(batch, params=None):
     bs = batch.as_struct()
     out.rc = lib().hpo_realign_block_batch(C.byref(params), C.byref(bs), C.byref(out.as_struct()))
     return out
+
+
+def wfa_plan_batch(batch):
+    out = A.PlanOut(batch)
+    bs = batch.as_struct()
+    out.rc = lib().hpo_wfa_plan_batch(C.byref(bs), C.byref(out.as_struct()))
+    return out

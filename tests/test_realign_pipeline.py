@@ -88,3 +88,53 @@ def test_gpu_pipeline_trips_at_fifty_failures():
     assert ref.rc == 0 and int(ref.block_disabled_at[0]) != 0xffffffff and int(ref.block_failures[0]) >= 50
     _same(ctx.realign_block_batch(batch), ref)
     ctx.close()
+
+
+# ---- CIGAR projection (the pre-WFA half of global_realignment, read_parsing.rs:672-742) --------------------------------
+def _plan_inputs(n_blocks, seed0, **kw):
+    map_block, seg_off, sr, sd, sl, het_first, het_pos, hom_first, hom_pos, reads = [], [0], [], [], [], [0], [], [0], [], []
+    for b in range(n_blocks):
+        blk = synth.gen_local_block(np.random.default_rng(seed0 + b), p_ignored=0.0, **kw)
+        het_pos += [v.position() for v in blk["variants"]]; het_first.append(len(het_pos))
+        hom_pos += [v.position() for v in blk["homs"]]; hom_first.append(len(hom_pos))
+        for (lo, hi, rp, segs, seq, q) in blk["jobs"]:
+            map_block.append(b)
+            for (a, r, n) in segs:
+                sr.append(a); sd.append(r); sl.append(n)
+            seg_off.append(len(sr)); reads.append((rp, segs, seq, q))
+    return A.PlanBatch(map_block, seg_off, sr, sd, sl, het_first, het_pos, hom_first, hom_pos), reads
+
+
+def test_plan_oracle_matches_the_python_mirror():
+    from hiphase_b200.read_parsing import AlignedRead, plan_global_realignment
+    pb, reads = _plan_inputs(3, 900, window=9000, n_var=12, n_hom=9, n_reads=30, read_lo=300, read_hi=3000, sv_max=300)
+    ref = O.wfa_plan_batch(pb)
+    assert ref.rc == 0
+    skipped = 0
+    for j, (rp, segs, seq, q) in enumerate(reads):
+        b = int(pb.map_block[j])
+        h0, m0 = int(pb.het_first[b]), int(pb.hom_first[b])
+        plan = plan_global_realignment(AlignedRead(rp, segs, seq.tobytes(), q), pb.het_pos[h0:int(pb.het_first[b + 1])].tolist(),
+                                       pb.hom_pos[m0:int(pb.hom_first[b + 1])].tolist())
+        if plan is None:
+            assert ref.het_lo[j] == ref.het_hi[j]; skipped += 1
+            continue
+        got = dict(ref_start=int(ref.ref_start[j]), ref_end=int(ref.ref_end[j]), het_lo=int(ref.het_lo[j]) - h0, het_hi=int(ref.het_hi[j]) - h0,
+                   hom_lo=int(ref.hom_lo[j]) - m0 if ref.hom_hi[j] > ref.hom_lo[j] else 0, hom_hi=int(ref.hom_hi[j]) - m0 if ref.hom_hi[j] > ref.hom_lo[j] else 0,
+                   read_start=int(ref.read_start[j]), read_end=int(ref.read_end[j]))
+        assert got == plan, (j, got, plan)
+    assert skipped > 0 and skipped < len(reads)
+
+
+@pytest.mark.gpu
+def test_gpu_plan_matches_the_oracle():
+    ctx = lib.Context(device=0)
+    pb, _ = _plan_inputs(4, 950, window=9000, n_var=12, n_hom=9, n_reads=60, read_lo=300, read_hi=3000, sv_max=300)
+    ref = O.wfa_plan_batch(pb)
+    out = ctx.wfa_plan_batch(pb)
+    for f in A.PlanOut.FIELDS:
+        assert np.array_equal(getattr(out, f), getattr(ref, f)), f
+    with pytest.raises(lib.HiPhaseB200Error):                           # a mapping without aligned pairs: the reference asserts
+        bad = A.PlanBatch([0], [0, 0], [], [], [], [0, 1], [5], [0, 0], [])
+        ctx.wfa_plan_batch(bad)
+    ctx.close()
