@@ -19,7 +19,8 @@ EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destr
            "hp_pack_get_blocks", "hp_pack_close", "hp_pack_last_error", "hp_write_phase_stats",
            "hp_ctx_set_lanes", "hp_astar_submit", "hp_astar_poll", "hp_astar_wait", "hp_host_alloc", "hp_host_free",
            "hp_host_register", "hp_host_unregister", "hp_block_costs", "hp_lpt_partition", "hp_comm_unique_id",
-           "hp_comm_init", "hp_comm_destroy", "hp_comm_allgather", "hp_comm_gather_results", "hp_realign_block_batch", "hp_wfa_plan_batch")
+           "hp_comm_init", "hp_comm_destroy", "hp_comm_allgather", "hp_comm_gather_results", "hp_realign_block_batch", "hp_wfa_plan_batch",
+           "hp_service_create", "hp_service_solve_one", "hp_service_counters", "hp_service_destroy")
 
 _LIB = None
 
@@ -86,6 +87,12 @@ def lib():
         L.hp_comm_init.argtypes = [C.c_void_p, A.u8p, C.c_int, C.c_int]
         L.hp_comm_destroy.argtypes = [C.c_void_p]
         L.hp_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.hp_service_create.argtypes = [C.POINTER(A.hp_params), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.hp_service_solve_one.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, A.u32p, A.u32p, A.u64p, A.u8p, A.u8p, A.u8p, A.u8p, A.u8p, A.u8p,
+                                           C.POINTER(A.hp_phase_stats)]
+        L.hp_service_counters.argtypes = [C.c_void_p, A.u64p, A.u64p]
+        L.hp_service_destroy.argtypes = [C.c_void_p]
+        L.hp_service_destroy.restype = None
         L.hp_wfa_plan_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_plan_batch), C.POINTER(A.hp_plan_out)]
         L.hp_realign_block_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_realign_batch), C.POINTER(A.hp_realign_out)]
         L.hp_comm_gather_results.argtypes = [C.c_void_p, C.c_uint64, A.u64p, A.u64p, C.POINTER(A.hp_astar_out), C.c_uint64,
@@ -156,6 +163,44 @@ class PinnedArena:
         for p in self._ptrs:
             lib().hp_host_free(p)
         self._ptrs = []
+
+
+class BlockService:
+    """hp_service: the blocking, thread-safe one-block call (the reference's astar_solver call shape) on top of batched launches."""
+
+    def __init__(self, params=None, device=0, max_batch_blocks=0, linger_us=0):
+        self._h = C.c_void_p()
+        rc = lib().hp_service_create(C.byref(params) if params is not None else None, int(device), int(max_batch_blocks), int(linger_us), C.byref(self._h))
+        if rc != A.HP_OK:
+            raise HiPhaseB200Error(rc, (lib().hp_last_error(None) or b"").decode())
+
+    def solve_one(self, block_batch, b=0):
+        """Block b of a BlockBatch -> (h1, h2, stats record); callable from many threads at once."""
+        import numpy as np
+        v0, v1 = int(block_batch.var_off[b]), int(block_batch.var_off[b + 1])
+        r0, r1 = int(block_batch.read_off[b]), int(block_batch.read_off[b + 1])
+        h1 = np.zeros(v1 - v0, np.uint8); h2 = np.zeros(v1 - v0, np.uint8)
+        st = A.hp_phase_stats()
+        rs = np.ascontiguousarray(block_batch.read_start[r0:r1]); re = np.ascontiguousarray(block_batch.read_end[r0:r1])
+        co = np.ascontiguousarray(block_batch.cell_off[r0:r1 + 1])
+        ig = np.ascontiguousarray(block_batch.ignored[v0:v1]); sn = np.ascontiguousarray(block_batch.is_snv[v0:v1])
+        rc = lib().hp_service_solve_one(self._h, v1 - v0, r1 - r0, A.ptr(rs, A.u32p), A.ptr(re, A.u32p), A.ptr(co, A.u64p),
+                                        A.ptr(block_batch.alleles, A.u8p), A.ptr(block_batch.quals, A.u8p), A.ptr(ig, A.u8p), A.ptr(sn, A.u8p),
+                                        A.ptr(h1, A.u8p), A.ptr(h2, A.u8p), C.byref(st))
+        if rc != A.HP_OK:
+            raise HiPhaseB200Error(rc, "hp_service_solve_one")
+        return h1, h2, st
+
+    def counters(self):
+        import numpy as np
+        a = np.zeros(1, np.uint64); b = np.zeros(1, np.uint64)
+        lib().hp_service_counters(self._h, A.ptr(a, A.u64p), A.ptr(b, A.u64p))
+        return int(a[0]), int(b[0])
+
+    def close(self):
+        if self._h:
+            lib().hp_service_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 class Context:

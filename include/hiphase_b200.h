@@ -172,6 +172,26 @@ int hp_astar_solve_one(hp_ctx* ctx, uint32_t n_var, uint32_t n_reads,
 
 
 /*
+ * Block service: the per-block call surface of the reference on top of batched launches.  HiPhase calls astar_solver from
+ * up to --threads pool workers, one phase block each (src/main.rs:385-408, src/phaser.rs:541-543); a GPU wants many blocks per
+ * launch.  A service owns one context and a dispatcher thread: hp_service_solve_one is thread-safe and BLOCKING with the
+ * argument list of hp_astar_solve_one; blocks that arrive while the device is busy (or within linger_us of each other) are
+ * packed into one batch and go out through hp_astar_submit on the context's lanes, so a long block of one batch does not hold
+ * up the blocks that arrive after it.  One service per GPU, shared by all worker threads.
+ */
+typedef struct hp_service hp_service;
+int  hp_service_create(const hp_params* params /* NULL = defaults */, int device, uint32_t max_batch_blocks /* 0 = 4096 */,
+                       uint32_t linger_us /* how long the dispatcher waits for more blocks once one is pending; 0 = 200 */,
+                       hp_service** out);
+int  hp_service_solve_one(hp_service* svc, uint32_t n_var, uint32_t n_reads,
+                          const uint32_t* read_start, const uint32_t* read_end, const uint64_t* cell_off,
+                          const uint8_t* alleles, const uint8_t* quals, const uint8_t* ignored, const uint8_t* is_snv,
+                          uint8_t* h1, uint8_t* h2, hp_phase_stats* stats);
+/* batches launched / blocks solved so far (how well the calls were packed) */
+int  hp_service_counters(const hp_service* svc, uint64_t* n_batches, uint64_t* n_blocks);
+void hp_service_destroy(hp_service* svc);
+
+/*
  * Streaming entry: the reference keeps 40 x threads jobs in flight and streams results back (src/main.rs:328, 344-355).
  * hp_astar_submit enqueues H2D + kernels + D2H of one batch on one of the context's lanes (own stream and workspaces;
  * hp_ctx_set_lanes, default 4) and returns without waiting; batches in flight on different lanes share the GPU, so the

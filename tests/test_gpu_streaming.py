@@ -107,3 +107,41 @@ def test_gather_results_single_rank_reorders_by_block_index():
     ref = O.astar_solve(ordered, threads=8, want_heuristic=False, want_counters=False)
     _check(allo, ref)
     ctx.close()
+
+
+def test_block_service_packs_concurrent_one_block_calls():
+    """hp_service_solve_one from many threads at once (the reference calls astar_solver from --threads pool workers, one block
+    each: src/main.rs:385-408): every caller gets its own block's result, and the calls were packed into fewer launches."""
+    import threading
+    batch = synth.config_c3_stream(160, first_block=2000)
+    ref = O.astar_solve(batch, threads=8, want_heuristic=False, want_counters=False)
+    svc = lib.BlockService(device=0, linger_us=500)
+    results = [None] * batch.n_blocks
+    errors = []
+
+    def worker(t, n_threads):
+        try:
+            for b in range(t, batch.n_blocks, n_threads):
+                results[b] = svc.solve_one(batch, b)
+        except Exception as e:           # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=worker, args=(t, 32)) for t in range(32)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for b in range(batch.n_blocks):
+        v0, v1 = int(batch.var_off[b]), int(batch.var_off[b + 1])
+        h1, h2, st = results[b]
+        assert np.array_equal(h1, ref.h1[v0:v1]) and np.array_equal(h2, ref.h2[v0:v1])
+        assert tuple(getattr(st, n) for n, _ in A.hp_phase_stats._fields_) == tuple(int(x) for x in ref.stats[b])
+    n_batches, n_blocks = svc.counters()
+    assert n_blocks == batch.n_blocks and n_batches < n_blocks
+    # a block the reference would panic on comes back as an error to its caller only
+    bad = A.BlockBatch.from_blocks([{"n_var": 4, "reads": [(0, [0, 1, 0, 1], [5, 5, 5, 5])], "ignored": [0, 1, 0, 0]}])
+    with pytest.raises(lib.HiPhaseB200Error):
+        svc.solve_one(bad, 0)
+    h1, h2, st = svc.solve_one(batch, 3)
+    assert np.array_equal(h1, ref.h1[int(batch.var_off[3]):int(batch.var_off[4])])
+    svc.close()
