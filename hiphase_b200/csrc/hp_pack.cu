@@ -117,8 +117,9 @@ extern "C" int hp_pack_open(const char* path, hp_packed** out) {
     auto find = [&](const char* name, uint32_t es, uint64_t want, bool required, const void** ptr) -> bool {
         for (uint32_t i = 0; i < h.n_sections; i++) {
             if (strncmp(tab[i].name, name, 16) != 0) continue;
+            // (division, not es * want: a corrupt count must not wrap the product)
             if (tab[i].elem_size != es || tab[i].count != want || (tab[i].offset & 63) || tab[i].offset > (uint64_t)sz ||
-                (uint64_t)es * want > (uint64_t)sz - tab[i].offset) return false;
+                want > ((uint64_t)sz - tab[i].offset) / es) return false;
             *ptr = p->bytes.data() + tab[i].offset;
             return true;
         }
@@ -133,13 +134,18 @@ extern "C" int hp_pack_open(const char* path, hp_packed** out) {
     if (var_off[0] != 0 || read_off[0] != 0) return fail("offsets must start at 0");
     for (uint32_t i = 0; i < nb; i++) if (var_off[i + 1] < var_off[i] || read_off[i + 1] < read_off[i]) return fail("offsets must be non-decreasing");
     const uint64_t nv = var_off[nb], nr = read_off[nb];
+    if (nv > (uint64_t)sz || nr > (uint64_t)sz / 4) return fail("variant / read counts exceed the file size");
     if (!find("read_start", 4, nr, true, &rs) || !find("read_end", 4, nr, true, &re) || !find("cell_off", 8, nr + 1, true, &co)) return fail("read sections");
     const uint64_t* cell_off = (const uint64_t*)co;
     if (cell_off[0] != 0) return fail("cell_off must start at 0");
     const uint32_t* rstart = (const uint32_t*)rs;
     const uint32_t* rend = (const uint32_t*)re;
-    for (uint64_t r = 0; r < nr; r++)
-        if (rend[r] < rstart[r] || cell_off[r + 1] - cell_off[r] != (uint64_t)(rend[r] - rstart[r])) return fail("read " + std::to_string(r) + ": region and cell range disagree");
+    for (uint32_t i = 0; i < nb; i++) {
+        const uint64_t n_var = var_off[i + 1] - var_off[i];
+        for (uint64_t r = read_off[i]; r < read_off[i + 1]; r++)
+            if (rend[r] < rstart[r] || rend[r] > n_var || cell_off[r + 1] < cell_off[r] || cell_off[r + 1] - cell_off[r] != (uint64_t)(rend[r] - rstart[r]))
+                return fail("read " + std::to_string(r) + ": region outside its block, or region and cell range disagree");
+    }
     const uint64_t nc = cell_off[nr];
     if (!find("alleles", 1, nc, true, &al) || !find("quals", 1, nc, true, &ql) || !find("ignored", 1, nv, true, &ig) || !find("is_snv", 1, nv, true, &sn)) return fail("cell / variant sections");
     if (!find("var_pos", 8, nv, false, &vp)) return fail("var_pos section");

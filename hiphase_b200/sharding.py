@@ -46,14 +46,19 @@ def gather_block_records(local_ids, local_records, n_total, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     local_ids = np.asarray(local_ids, np.int64)
-    local_records = np.asarray(local_records).reshape(len(local_ids), -1).astype(np.int64)
-    stride = local_records.shape[1] if local_records.ndim == 2 and local_records.shape[1] else 1
+    local_records = np.asarray(local_records)
+    # a rank without blocks does not know the record width: the ranks agree on (rows, stride) first
+    my_stride = int(local_records.size // len(local_ids)) if len(local_ids) else 0
+    local_records = local_records.reshape(len(local_ids), my_stride).astype(np.int64)
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    k = torch.tensor([len(local_ids)], dtype=torch.int64, device=dev)
-    ks = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    k = torch.tensor([len(local_ids), my_stride], dtype=torch.int64, device=dev)
+    ks = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(ks, k, group=group)
-    kmax = int(max(int(x.item()) for x in ks))
+    sizes = torch.stack(ks).cpu().numpy()
+    kmax, stride = int(sizes[:, 0].max()), int(sizes[:, 1].max())
+    if (sizes[:, 1][sizes[:, 0] > 0] != stride).any():
+        raise ValueError("ranks disagree on the record width")
     pad = torch.full((kmax, stride + 1), -1, dtype=torch.int64, device=dev)
     if len(local_ids):
         pad[:len(local_ids), 0] = torch.from_numpy(local_ids).to(dev)

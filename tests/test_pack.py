@@ -121,3 +121,29 @@ def test_runner_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([lib.RUNNER_PATH, path, str(tmp_path / "run"), "0"], capture_output=True, text=True)
     assert r.returncode != 0 and "error" in r.stderr.lower()
     assert not os.path.exists(str(tmp_path / "run.stats.tsv"))
+
+
+def test_corrupt_counts_are_rejected_not_followed(tmp_path):
+    """A section count that makes elem_size * count wrap, or a read region outside its block, is an invalid file."""
+    import struct
+    from hiphase_b200 import synth
+    batch = synth.config_c3_stream(2, first_block=3)
+    path = os.path.join(tmp_path, "ok.hpb")
+    lib.pack_write_blocks(path, batch)
+    raw = bytearray(open(path, "rb").read())
+    n_sections = struct.unpack_from("<I", raw, 12)[0]
+    for i in range(n_sections):                     # read_start: count 2^62 (4 * count wraps to 0)
+        name = bytes(raw[24 + 40 * i: 24 + 40 * i + 16]).rstrip(b"\0")
+        if name == b"read_start":
+            bad = bytearray(raw)
+            struct.pack_into("<Q", bad, 24 + 40 * i + 24, 1 << 62)
+            p2 = os.path.join(tmp_path, "wrap.hpb"); open(p2, "wb").write(bytes(bad))
+            with pytest.raises(lib.HiPhaseB200Error):
+                lib.pack_read_blocks(p2)
+        if name == b"read_end":                     # first read ends beyond its block's variants
+            off = struct.unpack_from("<Q", raw, 24 + 40 * i + 32)[0]
+            bad = bytearray(raw)
+            struct.pack_into("<I", bad, off, 1 << 30)
+            p3 = os.path.join(tmp_path, "region.hpb"); open(p3, "wb").write(bytes(bad))
+            with pytest.raises(lib.HiPhaseB200Error):
+                lib.pack_read_blocks(p3)

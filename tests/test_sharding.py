@@ -47,6 +47,35 @@ def _worker(rank, world, port, n_total, q):
         dist.destroy_process_group()
 
 
+def _worker_empty_rank(rank, world, port, q):
+    """Rank 1 owns no block at all (world > n_blocks, or an LPT deal that leaves a shard empty)."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = np.arange(3) if rank == 0 else np.zeros(0, np.int64)
+        rec = np.stack([mine + 10, mine * 2], axis=1) if rank == 0 else np.zeros((0, 0), np.int64)
+        got = sharding.gather_block_records(mine, rec, 3)
+        q.put((rank, bool(np.array_equal(got, np.stack([np.arange(3) + 10, np.arange(3) * 2], axis=1)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_with_an_empty_rank_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_worker_empty_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_gather_world2_gloo():
     import torch.multiprocessing as mp
     s = socket.socket()
