@@ -726,6 +726,9 @@ __device__ uint2 sub_solve_fast(const AstarArgs& a, const BlkMeta& m, WarpCtx& w
                                 uint32_t blk) {
     const uint32_t lane = w.lane;
     const uint32_t N = m.n_var;
+    const uint32_t* const hring = w.hring;                 // H[] ring and speculation floor in registers for the whole sub-solve
+    const uint32_t h_floor = w.h_floor;
+    auto Hq = [&](uint32_t idx) { return hring[max(idx, h_floor) & 63u]; };
     const uint32_t* aoff = a.act_off + m.var_base + blk;
     const uint32_t* aidx = a.act_idx + m.cell_base;
     const uint32_t* col = a.col + m.cell_base;
@@ -754,7 +757,7 @@ restart:
     uint64_t ckey = ~0ull, qmin = ~0ull;
     uint32_t cpos = 0, cnt = 0;
     // current top (root, :325)
-    uint32_t cur_total = w.H(v + 1), cur_lo = 63u << 26;
+    uint32_t cur_total = Hq(v + 1), cur_lo = 63u << 26;
     uint64_t cur_h1 = 0, cur_h2 = 0;
     int cur_src = SRC_ROOT;
     uint32_t cur_x1 = 0, cur_x2 = 0;
@@ -764,7 +767,7 @@ restart:
     uint32_t cache_first = 0xffffffffu, cache_present = 0;
     // column records of the current column p (slot = lane + 32k) and the offsets of p and p+1
     // column records two columns ahead are always in flight (the small L1 next to 196 KB of shared memory misses often)
-    uint32_t o_p = __ldg(aoff + v), o_p1 = __ldg(aoff + v + 1), o_p2 = (v + 2 <= N) ? __ldg(aoff + v + 2) : o_p1;
+    uint32_t o_p = __ldg(aoff + v), o_p1 = __ldg(aoff + v + 1), o_p2 = __ldg(aoff + min(v + 2, N));      // aoff[N] = all cells: empty columns beyond N
     uint32_t colc[K], coln[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -773,6 +776,7 @@ restart:
         coln[k] = (v + 1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
     uint32_t next_idx = 1, next_expected = 0, max_cost = 0, visits = 0, rr = 0;
+    uint64_t lbit = 1ull;                           // 1 << length of cur: shifted along the dive, re-seated after a real pop
     const uint32_t max_visits = a.min_queue_size / 10 + a.queue_increment * clip;    // :266, :333
 
     long long tq = 0;
@@ -832,6 +836,7 @@ restart:
             // re-seat the column state on this node's position
             const uint32_t Lp = cur_lo & 63u;
             const uint32_t pp = v + Lp;
+            lbit = 1ull << Lp;
             const uint32_t d = ((cur_lo >> 6) & 0xfffffu) - cache_first;
             if (Lp == 0u) cur_src = SRC_ROOT;
             else if (d < (uint32_t)__popc(cache_present)) {
@@ -839,9 +844,9 @@ restart:
                 const uint32_t cs = slot_of_ordinal(cache_present, d);
                 cur_src = SRC_CACHE; cur_x1 = cs & 1u; cur_x2 = (0x9u >> cs) & 1u;
             } else cur_src = SRC_PLANES;
-            heur_p = w.H(Lp == 0u ? v + 1 : pp);
+            heur_p = Hq(Lp == 0u ? v + 1 : pp);
             if (pp < N) {
-                o_p = __ldg(aoff + pp); o_p1 = __ldg(aoff + pp + 1); o_p2 = (pp + 2 <= N) ? __ldg(aoff + pp + 2) : o_p1;
+                o_p = __ldg(aoff + pp); o_p1 = __ldg(aoff + pp + 1); o_p2 = __ldg(aoff + min(pp + 2, N));
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
@@ -864,12 +869,13 @@ restart:
         const uint32_t p = v + L;
         const uint32_t a_cur = o_p1 - o_p;
         // ---- prefetch the next column's records (addresses are known; validity is masked once o_p2 arrives) ----
-        const uint32_t o_p3 = (p + 3 <= N) ? __ldg(aoff + p + 3) : o_p2;
+        const uint32_t o_p3 = __ldg(aoff + min(p + 3, N));
+        // (records read past the block's last column are masked by the empty column's size; the array has 130 entries of slack)
         uint32_t colnn[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) colnn[k] = (p + 2 < N) ? __ldg(col_lane + o_p2 + 32u * k) : kEmpty;
-        const uint32_t heur = w.H(p + 1);
-        const bool bad_col = (badwin >> L) & 1ull;
+        for (int k = 0; k < K; k++) colnn[k] = __ldg(col_lane + o_p2 + 32u * k);
+        const uint32_t heur = Hq(p + 1);
+        const bool bad_col = (badwin & lbit) != 0ull;
         const bool ident = (cur_h1 == cur_h2);
 
         // ---- this node's (s1, s2) per slot ----
@@ -917,22 +923,31 @@ restart:
         }
         const uint32_t r0 = wsum(pk0), r1 = wsum(pk1);
 
-        const uint32_t present = present_mask(bad_col, ident);
-        const uint32_t nchild = bad_col ? 1u : (ident ? 3u : 4u);
+        // the common expansion (a heterozygous choice was made earlier, the column is not ignored) has all four children:
+        // a warp-uniform branch keeps its key arithmetic free of the selects of the special cases
+        const bool plain = !bad_col && !ident;
+        const uint32_t present = plain ? 0xfu : present_mask(bad_col, ident);
+        const uint32_t nchild = plain ? 4u : (bad_col ? 1u : 3u);
         if (kCount) { const long long t1 = clock64(); w.ts_score += t1 - tq; tq = t1; w.ns_exp++; if (cur_src == SRC_PLANES) w.ns_planes++; }
         if (kCount) { w.pops++; w.evals += nchild; w.sum_lp += (uint64_t)nchild * L; w.cells += cells * nchild; }
 
         // candidate totals / keys; low words are ordered lo0 < lo1 < lo2 < lo3, so the first minimum wins ties
         const uint32_t tb = cur_total - heur_p + heur;
-        const uint32_t t0 = bad_col ? 0xffffffffu : tb + (r0 & 0xffffu);
-        const uint32_t t1 = (bad_col || ident) ? 0xffffffffu : tb + (r0 >> 16);
-        const uint32_t t2 = tb + (r1 & 0xffffu);
-        const uint32_t t3 = bad_col ? 0xffffffffu : tb + (r1 >> 16);
-        if (bad_col && t2 != cur_total) { w.status = HP_BLOCK_ASSERT; break; }             // :360
         const uint32_t lo_base = (cur_lo & 0xfc000000u) | (next_idx << 6) | (L + 1);
         // lo of candidate c = (c < 2 ? lo0 : lo2) + ((c & 1) << 6)
         const uint32_t lo0 = lo_base - (1u << 26);
-        const uint32_t lo2 = lo_base + (bad_col ? 0u : (ident ? 64u : 128u));
+        uint32_t t0, t1, t2, t3, lo2;
+        if (plain) {
+            t0 = tb + (r0 & 0xffffu); t1 = tb + (r0 >> 16); t2 = tb + (r1 & 0xffffu); t3 = tb + (r1 >> 16);
+            lo2 = lo_base + 128u;
+        } else {
+            t0 = bad_col ? 0xffffffffu : tb + (r0 & 0xffffu);
+            t1 = 0xffffffffu;                                            // (1|0) only exists next to a different (0|1)
+            t2 = tb + (r1 & 0xffffu);
+            t3 = bad_col ? 0xffffffffu : tb + (r1 >> 16);
+            if (bad_col && t2 != cur_total) { w.status = HP_BLOCK_ASSERT; break; }             // :360
+            lo2 = lo_base + (bad_col ? 0u : 64u);
+        }
         const uint32_t tmin = min(min(t0, t1), min(t2, t3));
         const uint32_t best = (t0 == tmin) ? 0u : (t1 == tmin) ? 1u : (t2 == tmin) ? 2u : 3u;
 
@@ -1004,6 +1019,7 @@ restart:
                         }
                     }
                 }
+                if (w.status != HP_BLOCK_OK) break;
             }
             rr += 4;
         }
@@ -1024,14 +1040,14 @@ restart:
         cur_lo = ((best & 2u) ? lo2 : lo0) + ((best & 1u) << 6);
         cur_x1 = best & 1u; cur_x2 = (0x9u >> best) & 1u;
         if (!bad_col) {
-            cur_h1 |= (uint64_t)cur_x1 << L;
-            cur_h2 |= (uint64_t)cur_x2 << L;
+            cur_h1 |= cur_x1 ? lbit : 0ull;
+            cur_h2 |= cur_x2 ? lbit : 0ull;
         }
+        lbit <<= 1;
         cur_src = SRC_CACHE;
         heur_p = heur;
         __syncwarp();
         if (kCount) w.ts_rest += clock64() - tq;
-        if (w.status != HP_BLOCK_OK) break;
     }
     return make_uint2(max_cost, next_expected - 1);
 }
