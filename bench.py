@@ -522,7 +522,8 @@ def main():
                                      "reference's u8 rescoring traffic (6 B/cell + node clones), counted by the kernel and equal to "
                                      "the oracle's counters; the working set is L1/L2/SMEM resident so DRAM traffic is far lower by "
                                      "design" % n_chunks},
-                "clocks": sampler.summary(), "result_checksum": checksum}
+                "clocks": sampler.summary(), "result_checksum": checksum,
+                "build": (lib.lib().hp_build_info() or b"").decode()}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_oracle(wl, wl.sample_ids(1000, 32), threads)

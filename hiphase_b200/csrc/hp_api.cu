@@ -254,6 +254,13 @@ extern "C" {
 
 int hp_abi_version(void) { return HP_ABI_VERSION; }
 
+#define HP_STR2(x) #x
+#define HP_STR(x) HP_STR2(x)
+const char* hp_build_info(void) {
+    return "hiphase_b200 ABI " HP_STR(HP_ABI_VERSION) "; nvcc " HP_STR(__CUDACC_VER_MAJOR__) "." HP_STR(__CUDACC_VER_MINOR__) "." HP_STR(__CUDACC_VER_BUILD__)
+           "; -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo; compiled " __DATE__ " " __TIME__;
+}
+
 void hp_default_params(hp_params* p) {
     p->min_queue_size = 1000; p->queue_increment = 3; p->wfa_prune_distance = 500; p->wfa_max_edit_distance = 500;
 }

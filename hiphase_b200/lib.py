@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 # HP_B200_LIB: kernel-development override (A/B builds of the same ABI); the product path is the in-tree .so
 LIB_PATH = os.environ.get("HP_B200_LIB") or os.path.join(CSRC, "libhiphase_b200.so")
 
-EXPORTS = ("hp_abi_version", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
+EXPORTS = ("hp_abi_version", "hp_build_info", "hp_default_params", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
            "hp_astar_solve_batch", "hp_astar_solve_device", "hp_astar_solve_one", "hp_launch_count",
            "hp_last_kernel_ms", "hp_wfa_align_batch", "hp_wfa_graph_align", "hp_post_solve_batch",
            "hp_local_realign_batch", "hp_edit_distance_batch", "hp_assemble_blocks", "hp_pack_write_blocks", "hp_pack_open",
@@ -50,6 +50,7 @@ def lib():
         L.hp_ctx_create.argtypes = [C.POINTER(A.hp_params), C.c_int, C.POINTER(C.c_void_p)]
         L.hp_ctx_destroy.argtypes = [C.c_void_p]
         L.hp_last_error.restype = C.c_char_p
+        L.hp_build_info.restype = C.c_char_p
         L.hp_last_error.argtypes = [C.c_void_p]
         L.hp_astar_solve_batch.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.POINTER(A.hp_astar_out)]
         L.hp_astar_solve_device.argtypes = [C.c_void_p, C.POINTER(A.hp_block_batch), C.c_uint64, C.c_uint64, C.c_uint64,

@@ -93,6 +93,8 @@ void hp_default_params(hp_params* p);
 typedef struct hp_ctx hp_ctx;
 
 int  hp_abi_version(void);
+/* How this binary was built: ABI version, nvcc release, target architecture, compile date (bench.py records it). */
+const char* hp_build_info(void);
 /* device < 0 selects the current CUDA device. */
 int  hp_ctx_create(const hp_params* params, int device, hp_ctx** out_ctx);
 void hp_ctx_destroy(hp_ctx* ctx);

@@ -19,3 +19,26 @@ lb = synth.config_local(1, full_rows=True, n_reads=12)
 lo = ctx.local_realign_batch(lb); lr = O.local_realign(lb)
 assert np.array_equal(lo.alleles, lr.alleles) and np.array_equal(lo.quals, lr.quals)
 print("sanitizer workload ok")
+# round 2: streaming lanes + shared slab pool, bulk-async prep on the C3 stream (incl. a block whose cells end the arrays), the
+# realignment pipeline, the CIGAR projection, 4-word node masks, the block service
+from hiphase_b200 import _abi as A
+ctx.set_lanes(3)
+bs = [synth.config_c3_stream(10, first_block=10 * i) for i in range(4)]
+hs = [ctx.astar_submit(x) for x in bs[:3]]
+for h, x in zip(hs, bs[:3]):
+    o = ctx.astar_wait(h); r = O.astar_solve(x, threads=4, want_heuristic=False, want_counters=False)
+    assert np.array_equal(o.h1, r.h1) and np.array_equal(o.stats, r.stats)
+d, vt = synth.config_realign(1, 0, window=6000, n_var=10, n_hom=4, n_reads=16, read_lo=800, read_hi=2000, sv_max=200, err=0.004)
+rb = A.RealignBatch(global_failure_minimum=2, global_failure_ratio=0.2, **d)
+c2 = lib.Context(A.hp_params(1000, 3, 500, 6), device=0)
+ro = c2.realign_block_batch(rb); rr = O.realign_block_batch(rb, A.hp_params(1000, 3, 500, 6))
+assert np.array_equal(ro.map_mode, rr.map_mode) and np.array_equal(ro.alleles[: int(rr.as_struct().assembled.n_cells)], rr.alleles[: int(rr.as_struct().assembled.n_cells)])
+c2.close()
+import importlib.util
+spec = importlib.util.spec_from_file_location("t", os.path.join(R, "tests", "test_gpu_wfa.py")); t = importlib.util.module_from_spec(spec); spec.loader.exec_module(t)
+big = t._dense_snv_batch(360, 2, seed=1)
+assert (ctx.wfa_align_batch(big, trav_words=32).status == 0).all()
+svc = lib.BlockService(device=0)
+h1, h2, st = svc.solve_one(bs[3], 2)
+svc.close()
+print("round-2 sanitizer workload ok")
