@@ -83,6 +83,9 @@ constexpr uint32_t kWfaMaxNodes = 4096;          // node activity mask: MW 32-bi
 constexpr uint32_t kNil = 0xffffffffu;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr int kWfaWarps = 8;
+#ifndef HP_WFA_CTAS_PER_SM
+#define HP_WFA_CTAS_PER_SM 2
+#endif
 
 __host__ __device__ inline uint32_t wfa_slot_stride(uint32_t set_words) { return 32u + 16u * set_words; }
 
@@ -257,7 +260,7 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
 }
 
 template <int MW>
-__global__ void __launch_bounds__(kWfaWarps * 32) wfa_align_kernel(WfaArgs a) {
+__global__ void __launch_bounds__(kWfaWarps * 32, HP_WFA_CTAS_PER_SM) wfa_align_kernel(WfaArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gwarp = blockIdx.x * kWfaWarps + (threadIdx.x >> 5);
     WfaCtx c;
@@ -889,7 +892,7 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     }
     a.prune_distance = prune; a.max_edit_distance = max_ed;
 
-    int n_ctas = std::min<int>((nj + kWfaWarps - 1) / kWfaWarps, ctx->sm_count * 2);
+    int n_ctas = std::min<int>((nj + kWfaWarps - 1) / kWfaWarps, ctx->sm_count * HP_WFA_CTAS_PER_SM);
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     a.table_cap = table_cap; a.set_words_max = sw_max;
     a.slab_bytes = wfa_slab_bytes(table_cap, sw_max);
