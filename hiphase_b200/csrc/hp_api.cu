@@ -338,7 +338,7 @@ int hp_ctx_set_lanes(hp_ctx* ctx, int lanes) {
 // Not part of the public header: per-block phase cycles of the last counting run (profiling aid for bench/profiles).
 int hp_debug_set_team(hp_ctx* ctx, int team) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->force_team = team; return HP_OK; }
 // bit 0: build the WFA graphs on the host (A/B aid); bit 1: no workspace hint (exercises the regrow path)
-int hp_debug_wfa_build_mode(hp_ctx* ctx, int mode) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->wfa_host_build = (mode & 1) != 0; ctx->wfa_no_hint = (mode & 2) != 0; return HP_OK; }
+int hp_debug_wfa_build_mode(hp_ctx* ctx, int mode) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->wfa_host_build = (mode & 1) != 0; ctx->wfa_no_hint = (mode & 2) != 0; ctx->wfa_dbg_times = (mode & 4) != 0; return HP_OK; }
 // Test aid (not in the public header): scores every read of block 0 of the batch last solved on this context with the device's
 // bit-plane scorer (score_planes) against haplotypes h1 / h2 (bit j = allele at haplotype position j) over
 // [offset, offset + len): the device counterpart of ReadSegment::score_partial_haplotype (read_segments.rs:177-206).
@@ -360,6 +360,9 @@ int hp_debug_score_partial(hp_ctx* ctx, uint64_t h1, uint64_t h2, uint32_t offse
     HP_CUDA(ctx, cudaStreamSynchronize(L->stream));
     return HP_OK;
 }
+// Piece filter of the graph-WFA kernel: switch (test / A-B aid) and the number of reads it answered in the last batch call.
+int hp_debug_wfa_filter(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->wfa_no_filter = on == 0; return HP_OK; }
+uint32_t hp_debug_wfa_filtered(const hp_ctx* ctx) { return ctx ? ctx->wfa_filtered : 0; }
 int hp_debug_enable_block_cycles(hp_ctx* ctx, int on) { if (!ctx) return HP_ERR_INVALID_INPUT; ctx->want_dbg = on != 0; return HP_OK; }
 int hp_debug_read_block_cycles(hp_ctx* ctx, uint64_t* out, uint32_t n_blocks) {
     if (!ctx || !out || n_blocks > ctx->dbg_blocks) return HP_ERR_INVALID_INPUT;

@@ -96,6 +96,10 @@ struct hp_ctx {
     hp::DevBuf ticket, stage_in, stage_out;
     // WFA workspaces
     hp::DevBuf wfa_ws, wfa_in, wfa_out, wfa_graph;
+    bool wfa_no_filter = false;             // test aid: never short-circuit hopeless reads (piece filter off)
+    uint32_t wfa_filtered = 0;              // reads the piece filter answered in the last hp_wfa_align_batch call
+    uint32_t wfa_filtered_now = 0;          // ... of the run in flight
+    bool wfa_dbg_times = false;             // profiling aid: the counting variant reports per-job start / end times instead of set_ops / n_nodes
     bool wfa_no_hint = false;               // test aid: start with an unsized graph workspace (exercises the regrow path)
     bool wfa_host_build = false;            // debug / A-B aid: build the graphs on the host instead of on the device
     uint64_t wfa_layout[4] = {0, 0, 0, 0};  // {workspace pointer, slab bytes, table cap, warps} the hash keys were last zeroed for

@@ -68,6 +68,7 @@ struct WfaArgs {
     uint32_t set_words_max;        // set words the slab layout was sized for
     uint32_t* ticket;
     uint32_t* epochs;              // [warps of the launch] job counter of each warp's table (persists across launches)
+    const uint32_t* noise;         // optional [n_jobs]: probe estimate of each job (jobs at or above kNoisyProbe try the piece filter)
     // outputs
     int32_t*  out_status;
     uint32_t* out_score;
@@ -77,23 +78,37 @@ struct WfaArgs {
     uint64_t* out_traversed;       // optional
     uint32_t  trav_words;
     uint64_t* out_counters;        // optional [n_jobs * 4]
+    int dbg_times;                 // profiling aid: counters 2 and 3 carry the job's start / end time (ns) and the filter stays on
 };
 
 constexpr uint32_t kWfaMaxNodes = 4096;          // node activity mask: MW 32-bit words per lane (kernel variants MW = 1, 4)
 constexpr uint32_t kNil = 0xffffffffu;
+constexpr uint32_t kNoisyProbe = 12;   // probe estimate (edits per 512 bases, over the start of the read) from which a job is scheduled first
+constexpr uint32_t kPiece = 10;                              // piece filter: bases per read piece (2 bits each -> 2^20 codes)
+constexpr uint64_t kPieceBitmapBytes = (1ull << (2 * kPiece)) / 8;
 constexpr uint64_t kEmptyKey = ~0ull;
-constexpr int kWfaWarps = 8;
+// One warp per CTA: a warp that is stuck with a long job (a read that runs to MaxEditDistance takes ~25 ms) then holds on to its own
+// registers only, and the CTAs of the next launch (another context's chunk, the A* of this one) move in beside it.  With 8 warps
+// per CTA one straggler kept the other 7 warps' share of the SM idle until it was done.
+#ifndef HP_WFA_WARPS
+#define HP_WFA_WARPS 1
+#endif
+constexpr int kWfaWarps = HP_WFA_WARPS;
+#ifndef HP_WFA_PRIVATE_STEPS
+#define HP_WFA_PRIVATE_STEPS 2
+#endif
+constexpr int kPrivateSteps = HP_WFA_PRIVATE_STEPS;   // 8-base extension steps a lane takes alone before the warp finishes its run
 #ifndef HP_WFA_CTAS_PER_SM
-#define HP_WFA_CTAS_PER_SM 2
+#define HP_WFA_CTAS_PER_SM (16 / HP_WFA_WARPS)
 #endif
 
 __host__ __device__ inline uint32_t wfa_slot_stride(uint32_t set_words) { return 32u + 16u * set_words; }
 
 // slab layout: keys[cap] u64 | slots[cap * stride] | items[2][cap] u32 | seg_start[2][1024] | seg_len[2][1024] |
-//              late_head[1024] | chunks[cap/8 * 34] u32 | rowtmp[4096] u32
+//              late_head[1024] | chunks[cap/8 * 34] u32 | rowtmp[4096] u32 | kmer_bits[2^20 bits]
 __host__ __device__ inline uint64_t wfa_slab_bytes(uint32_t cap, uint32_t set_words) {
     uint64_t b = (uint64_t)cap * 8 + (uint64_t)cap * wfa_slot_stride(set_words) + 2ull * cap * 4 + 5ull * kWfaMaxNodes * 4 +
-                 (uint64_t)(cap / 8) * 34 * 4 + 4096ull * 4;
+                 (uint64_t)(cap / 8) * 34 * 4 + 4096ull * 4 + kPieceBitmapBytes;
     return (b + 255) & ~255ull;
 }
 
@@ -106,6 +121,7 @@ struct WfaSlab {
     uint32_t* late_head;
     uint32_t* chunks;      // chunk c: [next, count, 32 items]
     uint32_t* rowtmp;
+    uint32_t* kmer_bits;   // piece filter: one bit per 10-mer code
 };
 
 __device__ __forceinline__ WfaSlab wfa_carve(uint8_t* p, uint32_t cap, uint32_t set_words) {
@@ -120,7 +136,8 @@ __device__ __forceinline__ WfaSlab wfa_carve(uint8_t* p, uint32_t cap, uint32_t 
     s.seg_len[1] = (uint32_t*)p; p += kWfaMaxNodes * 4;
     s.late_head = (uint32_t*)p; p += kWfaMaxNodes * 4;
     s.chunks = (uint32_t*)p; p += (uint64_t)(cap / 8) * 34 * 4;
-    s.rowtmp = (uint32_t*)p;
+    s.rowtmp = (uint32_t*)p; p += 4096ull * 4;
+    s.kmer_bits = (uint32_t*)p;
     return s;
 }
 
@@ -195,42 +212,87 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
                                          uint32_t& slot_out) {
     first = false; slot_out = kNil;
     uint32_t n_created = 0;
+    // ---- extend (wfa_graph.rs:454-459) ----
+    // Eight bases per step (unaligned 64-bit windows assembled from aligned loads; every byte pool is followed by at least
+    // 16 readable bytes of staging slack).  Two private steps per lane settle the waves that stop at once (nearly all of them
+    // on a wrong diagonal); a wave that is still running after 16 bases is on a matching diagonal and is finished by the whole
+    // warp, 256 bases per step.  n_cmp counts the byte compares of the reference: the matches plus the mismatch that stops
+    // the run.
+    uint32_t off = offset;
+    uint32_t pos = (uint32_t)(diag + (int32_t)offset);
+    uint32_t node_len = 0;
+    const uint8_t* seq = nullptr;
+    bool running = false;
     if (act) {
-        // ---- extend (wfa_graph.rs:454-459) ----
         const WfaNode nd = c.nodes[node];
-        const uint8_t* seq = node_seq(*c.a, nd);
-        uint32_t off = offset;
-        uint32_t pos = (uint32_t)(diag + (int32_t)off);
-        // eight bases per step (unaligned 64-bit windows assembled from aligned loads; every byte pool is followed by
-        // at least 16 readable bytes of staging slack); n_cmp counts the byte compares of the reference: the matches plus
-        // the mismatch that stops the run
-        while (off < nd.len && pos < c.read_len) {
-            const uint32_t rem = min(nd.len - off, c.read_len - pos);
+        seq = node_seq(*c.a, nd);
+        node_len = nd.len;
+        running = off < node_len && pos < c.read_len;
+#pragma unroll 1
+        for (int step = 0; step < kPrivateSteps && running; step++) {
+            const uint32_t rem = min(node_len - off, c.read_len - pos);
             uint64_t x = ld64_unaligned(seq + off) ^ ld64_unaligned(c.read + pos);
             if (rem < 8u) x &= (1ull << (8u * rem)) - 1ull;
             if (x) {
                 const uint32_t adv = (uint32_t)(__ffsll((long long)x) - 1) >> 3;
                 off += adv; pos += adv; c.n_cmp += adv + 1;
+                running = false;
+            } else {
+                const uint32_t adv = min(rem, 8u);
+                off += adv; pos += adv; c.n_cmp += adv;
+                running = off < node_len && pos < c.read_len;
+            }
+        }
+    }
+    for (uint32_t rm = __ballot_sync(HP_FULL_MASK, running); rm; rm &= rm - 1) {
+        const uint32_t src = __ffs(rm) - 1;
+        const uint8_t* sq = (const uint8_t*)__shfl_sync(HP_FULL_MASK, (unsigned long long)(uintptr_t)(seq + off), src);
+        const uint8_t* rd = c.read + __shfl_sync(HP_FULL_MASK, pos, src);
+        uint32_t rem = __shfl_sync(HP_FULL_MASK, min(node_len - off, c.read_len - pos), src);
+        uint32_t total = 0, stopped = 0;
+        while (rem) {
+            const uint32_t my0 = c.lane * 8u;
+            uint64_t x = 0;
+            if (my0 < rem) {
+                x = ld64_unaligned(sq + my0) ^ ld64_unaligned(rd + my0);
+                if (rem - my0 < 8u) x &= (1ull << (8u * (rem - my0))) - 1ull;
+            }
+            const uint32_t bm = __ballot_sync(HP_FULL_MASK, x != 0);
+            if (bm) {
+                const uint32_t adv = my0 + ((uint32_t)(__ffsll((long long)x) - 1) >> 3);
+                total += __shfl_sync(HP_FULL_MASK, adv, __ffs(bm) - 1);
+                stopped = 1;
                 break;
             }
-            const uint32_t adv = min(rem, 8u);
-            off += adv; pos += adv; c.n_cmp += adv;
+            const uint32_t step = min(rem, 256u);
+            total += step; rem -= step; sq += step; rd += step;
         }
-        // ---- find or insert the slot ----
-        const uint64_t key = wfa_key(c.epoch, node, diag);
-        uint32_t h = wfa_hash(node, diag) & (c.cap - 1);
-        uint32_t slot = kNil;
-        bool created = false;
-        for (uint32_t probe = 0; probe < c.cap; probe++) {
-            unsigned long long k = c.s.keys[h];
-            if ((uint32_t)(k >> kEpochShift) != c.epoch) {                   // empty: never used, or left by an earlier job
-                const unsigned long long seen = k;
-                k = atomicCAS(&c.s.keys[h], seen, (unsigned long long)key);
-                if (k == seen) { slot = h; created = true; break; }
-            }
-            if (k == key) { slot = h; break; }
-            h = (h + 1) & (c.cap - 1);
+        if (c.lane == src) { off += total; pos += total; c.n_cmp += total + stopped; }
+    }
+    // ---- find or insert the slot ----
+    // The table belongs to this warp alone, so no atomic is needed (an atomicCAS is a round trip to the L2 for every new slot):
+    // lanes that meet the same empty entry are told apart by __match_any_sync, the lowest of them takes the entry with a plain
+    // store and the others look at it again.
+    const uint64_t key = wfa_key(c.epoch, node, diag);
+    uint32_t h = wfa_hash(node, diag) & (c.cap - 1);
+    uint32_t slot = kNil;
+    bool created = false;
+    bool need = act;
+    for (uint32_t probe = 0; probe < 2u * c.cap && __any_sync(HP_FULL_MASK, need); probe++) {
+        bool empty = false;
+        if (need) {
+            const unsigned long long k = c.s.keys[h];
+            empty = (uint32_t)(k >> kEpochShift) != c.epoch;                 // never used, or left by an earlier job
+            if (!empty) { if (k == key) { slot = h; need = false; } else h = (h + 1) & (c.cap - 1); }
         }
+        const uint32_t em = __ballot_sync(HP_FULL_MASK, empty);
+        if (empty) {
+            const uint32_t peers = __match_any_sync(em, h);
+            if (c.lane == (uint32_t)(__ffs(peers) - 1)) { c.s.keys[h] = key; slot = h; created = true; need = false; }
+        }
+        __syncwarp();
+    }
+    if (act) {
         if (slot != kNil) {
             SlotRef sr{c.s.slots + (uint64_t)slot * c.stride, c.sw};
             if (created) { sr.record() = 0; sr.tag(0) = kNil; sr.tag(1) = kNil; sr.diag() = diag; sr.node() = node; }
@@ -259,6 +321,105 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
     if (c.used > c.cap / 2) c.overflow = true;
 }
 
+// ---- piece filter: an exact proof that a read cannot align within max_edit_distance -------------------------------------
+// Cut the read into disjoint pieces of kPiece bases.  An alignment of the read to ANY path of the graph with k unit-cost edits
+// leaves all but at most k pieces untouched, and an untouched piece occurs verbatim in that path.  So the number of pieces that
+// occur in NO path of the graph is a lower bound of the edit distance the reference computes (wfa_graph.rs:350-650, global in
+// the read and in the graph; pruning can only make its result larger).  If the bound exceeds max_edit_distance the reference
+// returns MaxEditDistance (:645-648) and so do we, without walking 500 edit-distance levels (~20 ms of one warp per read).
+// The kPiece-mers of all paths are collected in a bitmap: those inside a node by all lanes side by side, those that start in the
+// last kPiece - 1 bases of a node by a bounded depth-first walk through its descendants, one (node, start) pair per lane.  A
+// piece is looked up by a code that is a function of its bytes alone (two bits of each byte), so a piece that does occur always
+// finds its bit; bytes outside ACGT only make codes collide, which can hide a missing piece but never invent one.  A graph
+// whose walk exceeds its budget gives no verdict (the alignment runs as usual).  Only reads whose probe estimate, scaled to the
+// read, is clearly beyond max_edit_distance try it.
+__device__ __forceinline__ uint32_t base2(uint32_t b) { return (b >> 1) & 3u; }
+__device__ __forceinline__ uint32_t pack8(uint64_t w) {          // base i of the 8 bytes -> bits [2i, 2i + 2)
+    uint64_t x = (w >> 1) & 0x0303030303030303ull;
+    x = (x | (x >> 6)) & 0x000F000F000F000Full;
+    x = (x | (x >> 12)) & 0x000000FF000000FFull;
+    x = (x | (x >> 24)) & 0xFFFFull;
+    return (uint32_t)x;
+}
+static_assert(kPiece == 10, "piece_code packs 8 + 2 bases");
+__device__ __forceinline__ uint32_t piece_code(const uint8_t* p) {   // code of p[0 .. 10): reads up to p + 16 (staging slack)
+    const uint64_t hi = ld64_unaligned(p + 8);
+    return pack8(ld64_unaligned(p)) | (base2((uint32_t)hi) << 16) | (base2((uint32_t)(hi >> 8)) << 18);
+}
+
+__device__ bool wfa_piece_filter(WfaCtx& c, const WfaArgs& a, const uint32_t* child_off, uint32_t n_nodes) {
+    const uint32_t lane = c.lane;
+    const uint32_t pieces = c.read_len / kPiece;
+    if (pieces <= a.max_edit_distance) return false;
+    uint32_t* bits = c.s.kmer_bits;
+    for (uint32_t i = lane; i < (uint32_t)(kPieceBitmapBytes / 16); i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    // pieces inside a node
+    for (uint32_t u0 = 0; u0 < n_nodes; u0 += 32) {
+        WfaNode mine{0, 0, 0};
+        if (u0 + lane < n_nodes) mine = c.nodes[u0 + lane];
+        const uint8_t* my_seq = node_seq(a, mine);
+        const uint32_t cnt = min(32u, n_nodes - u0);
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t len = __shfl_sync(HP_FULL_MASK, mine.len, k);
+            const uint8_t* seq = (const uint8_t*)__shfl_sync(HP_FULL_MASK, (unsigned long long)(uintptr_t)my_seq, k);
+            if (len < kPiece) continue;
+            for (uint32_t i = lane; i + kPiece <= len; i += 32) {
+                const uint32_t code = piece_code(seq + i);
+                atomicOr(&bits[code >> 5], 1u << (code & 31u));
+            }
+        }
+    }
+    // pieces that start in the last kPiece - 1 bases of a node and continue into its descendants
+    constexpr int kMaxDepth = 12;
+    constexpr uint32_t kWalkBudget = 256;
+    bool giveup = false;
+    const uint32_t n_starts = n_nodes * (kPiece - 1);
+    for (uint32_t s0 = 0; s0 < n_starts; s0 += 32) {
+        const uint32_t s = s0 + lane;
+        if (s < n_starts) {
+            const uint32_t u = s / (kPiece - 1), back = s % (kPiece - 1) + 1;      // the piece starts `back` bases before the node's end
+            const WfaNode nd = c.nodes[u];
+            if (back <= nd.len) {
+                const uint8_t* seq = node_seq(a, nd) + (nd.len - back);
+                uint32_t code = 0;
+                for (uint32_t k = 0; k < back; k++) code |= base2(seq[k]) << (2 * k);
+                uint32_t st_node[kMaxDepth], st_edge[kMaxDepth], st_code[kMaxDepth], st_have[kMaxDepth];
+                int depth = 0;
+                uint32_t walked = 0;
+                st_node[0] = u; st_edge[0] = child_off[u]; st_code[0] = code; st_have[0] = back;
+                while (depth >= 0) {
+                    const uint32_t n = st_node[depth];
+                    if (st_edge[depth] == child_off[n + 1]) { depth--; continue; }
+                    const uint32_t ch = a.child_idx[st_edge[depth]++];
+                    if (++walked > kWalkBudget) { giveup = true; break; }
+                    const WfaNode cn = c.nodes[ch];
+                    const uint8_t* cs = node_seq(a, cn);
+                    uint32_t cc = st_code[depth], have = st_have[depth];
+                    const uint32_t t = min(kPiece - have, cn.len);
+                    for (uint32_t k = 0; k < t; k++) cc |= base2(cs[k]) << (2 * (have + k));
+                    have += t;
+                    if (have == kPiece) { atomicOr(&bits[cc >> 5], 1u << (cc & 31u)); continue; }
+                    if (depth + 1 >= kMaxDepth) { giveup = true; break; }
+                    depth++;
+                    st_node[depth] = ch; st_edge[depth] = child_off[ch]; st_code[depth] = cc; st_have[depth] = have;
+                }
+            }
+        }
+        giveup = __any_sync(HP_FULL_MASK, giveup);
+        if (giveup) return false;
+    }
+    __threadfence_block();
+    __syncwarp();
+    uint32_t missing = 0;
+    for (uint32_t t = lane; t < pieces; t += 32) {
+        const uint32_t code = piece_code(c.read + (uint64_t)t * kPiece);
+        if (!((__ldcg(&bits[code >> 5]) >> (code & 31u)) & 1u)) missing++;
+    }
+    missing = __reduce_add_sync(HP_FULL_MASK, missing);
+    return missing > a.max_edit_distance;
+}
+
 template <int MW>
 __global__ void __launch_bounds__(kWfaWarps * 32, HP_WFA_CTAS_PER_SM) wfa_align_kernel(WfaArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -274,6 +435,8 @@ __global__ void __launch_bounds__(kWfaWarps * 32, HP_WFA_CTAS_PER_SM) wfa_align_
         if (j >= a.n_jobs) break;
         j = a.order[j];
         const WfaJob job = a.jobs[j];
+        unsigned long long t_start = 0;
+        if (a.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         int status = job.status;
         uint32_t score = 0;
         c.n_cmp = c.n_waves = c.n_setops = 0;
@@ -297,6 +460,16 @@ __global__ void __launch_bounds__(kWfaWarps * 32, HP_WFA_CTAS_PER_SM) wfa_align_
             const uint32_t sink = n_nodes - 1;
             const uint32_t max_chunks = c.cap / 8;
 
+            // reads whose probe estimate, scaled to the read, reaches 0.9 max_edit_distance (a try costs ~1 ms, a proof saves ~25):
+            // try to prove MaxEditDistance without aligning (never in the counting variant, whose work counters are the
+            // reference's)
+            if (a.noise && (!a.out_counters || a.dbg_times) && a.noise[j] >= kNoisyProbe &&
+                (uint64_t)a.noise[j] * c.read_len * 10ull >= (uint64_t)a.max_edit_distance * 512ull * 9ull &&
+                wfa_piece_filter(c, a, child_off, n_nodes)) {
+                status = HP_WFA_MAX_EDIT_DISTANCE; score = a.max_edit_distance;
+                if (lane == 0) atomicAdd(a.ticket + 1, 1u);
+            }
+          if (status == HP_WFA_OK) {
             // a fresh epoch instead of a table clear (the clear only happens when the 20-bit counter wraps)
             {
                 uint32_t e = 0;
@@ -493,6 +666,7 @@ __global__ void __launch_bounds__(kWfaWarps * 32, HP_WFA_CTAS_PER_SM) wfa_align_
                 if (ed > a.max_edit_distance) { status = HP_WFA_MAX_EDIT_DISTANCE; score = a.max_edit_distance; break; }
                 if (__ballot_sync(HP_FULL_MASK, any_next != 0) == 0) { status = HP_WFA_WORKSPACE_OVERFLOW; break; }   // cannot happen
             }
+          }
         }
         if (lane == 0) {
             a.out_status[j] = status;
@@ -506,6 +680,7 @@ __global__ void __launch_bounds__(kWfaWarps * 32, HP_WFA_CTAS_PER_SM) wfa_align_
             if (lane == 0) {
                 uint64_t* o = a.out_counters + (uint64_t)j * 4;
                 o[0] = cmp; o[1] = wv; o[2] = so; o[3] = n_nodes;
+                if (a.dbg_times) { unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end)); o[2] = t_start; o[3] = t_end; }
             }
         }
         __syncwarp();
@@ -554,7 +729,6 @@ struct BuildArgs {
     uint32_t* e_child;
 };
 
-constexpr uint32_t kNoisyProbe = 6;    // probe estimate (edit distance over the first 256 bases) from which a job is scheduled first
 constexpr int kBuildCap = 64;      // open ALT branches / parents of one node / pending allele-0 tags
 constexpr uint32_t kBuildOk = 0, kBuildInvalid = 1, kBuildOverflow = 2;
 
@@ -682,7 +856,10 @@ struct ProbeArgs {
     uint32_t* noise;               // [n_sel]
 };
 
-__device__ __forceinline__ uint32_t probe_ed64(const uint8_t* pat, const uint8_t* txt) {
+// Edit distance of the 64-byte pattern to its best-matching infix of txt[0, n_txt) (Myers' bit-vector search: the first row of the
+// matrix is free, the minimum over all end positions is kept).  A pattern that sits a few bases off its expected place -- an
+// indel earlier in the read -- still scores its own errors only.
+__device__ __forceinline__ uint32_t probe_ed64(const uint8_t* pat, const uint8_t* txt, uint32_t n_txt) {
     uint64_t pA = 0, pC = 0, pG = 0, pT = 0;
     for (uint32_t j = 0; j < 64; j++) {
         const uint8_t c = pat[j];
@@ -690,8 +867,8 @@ __device__ __forceinline__ uint32_t probe_ed64(const uint8_t* pat, const uint8_t
         if (c == 'A') pA |= bit; else if (c == 'C') pC |= bit; else if (c == 'G') pG |= bit; else if (c == 'T') pT |= bit;
     }
     uint64_t Pv = ~0ull, Mv = 0;
-    uint32_t score = 64;
-    for (uint32_t i = 0; i < 64; i++) {
+    uint32_t score = 64, best = 64;
+    for (uint32_t i = 0; i < n_txt; i++) {
         const uint8_t c = txt[i];
         const uint64_t Eq = c == 'A' ? pA : c == 'C' ? pC : c == 'G' ? pG : c == 'T' ? pT : 0ull;
         const uint64_t Xv = Eq | Mv;
@@ -699,12 +876,16 @@ __device__ __forceinline__ uint32_t probe_ed64(const uint8_t* pat, const uint8_t
         uint64_t Ph = Mv | ~(Xh | Pv);
         uint64_t Mh = Pv & Xh;
         if (Ph >> 63) score++; else if (Mh >> 63) score--;
-        Ph = (Ph << 1) | 1ull; Mh <<= 1;
+        Ph <<= 1; Mh <<= 1;
         Pv = Mh | ~(Xv | Ph); Mv = Ph & Xv;
+        best = min(best, score);
     }
-    return score;
+    return best;
 }
 
+// Scheduling estimate of a job: the first 512 read bases in eight blocks of 64, each matched against the reference window around
+// its own offset (32 bases of play on either side), as edits per 512 bases.  ~0 for a clean read (plus the variants it carries),
+// ~25 for a read at 5 % error.  Scheduling and the piece-filter gate only: results never depend on it.
 __global__ void __launch_bounds__(128) wfa_noise_probe_kernel(ProbeArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.n_sel) return;
@@ -712,10 +893,15 @@ __global__ void __launch_bounds__(128) wfa_noise_probe_kernel(ProbeArgs a) {
     const uint64_t rlen = a.read_off[j + 1] - a.read_off[j], wlen = a.ref_end[j] - a.ref_start[j];
     const uint8_t* rd = a.read_bytes + a.read_off[j];
     const uint8_t* rf = a.reference + a.ref_start[j];
-    uint32_t est = 0;
-    for (uint32_t k = 0; k < 4; k++)
-        if ((k + 1) * 64ull <= rlen && (k + 1) * 64ull <= wlen) est += probe_ed64(rd + 64 * k, rf + 64 * k);
-    a.noise[slot] = est;
+    uint32_t est = 0, blocks = 0;
+    for (uint32_t k = 0; k < 8; k++) {
+        if ((k + 1) * 64ull > rlen) break;
+        const uint64_t t0 = k ? 64ull * k - 32 : 0, t1 = min(wlen, (uint64_t)(64ull * k + 96));
+        if (t1 <= t0) break;
+        est += probe_ed64(rd + 64 * k, rf + t0, (uint32_t)(t1 - t0));
+        blocks++;
+    }
+    a.noise[slot] = blocks ? est * 8u / blocks : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -828,6 +1014,7 @@ struct DevBuilt {
     const WfaNode* nodes = nullptr;
     const uint32_t *child_off = nullptr, *child_idx = nullptr, *amap_off = nullptr, *amap = nullptr;
     const uint8_t *reference = nullptr, *allele_bytes = nullptr, *read_bytes = nullptr, *vtype = nullptr;
+    const uint32_t* noise = nullptr;       // probe estimates, one per job of the run
 };
 
 struct WfaHostInputs {
@@ -869,6 +1056,10 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
         const bool nx = fg.jobs[x].pad >= kNoisyProbe, ny = fg.jobs[y].pad >= kNoisyProbe;
         if (nx != ny) return nx;
+        if (nx) {      // among the noisy: the ones the piece filter is least likely to answer first (they run the longest)
+            const uint64_t ex = (uint64_t)fg.jobs[x].pad * fg.jobs[x].read_len, ey = (uint64_t)fg.jobs[y].pad * fg.jobs[y].read_len;
+            if (ex != ey) return ex < ey;
+        }
         return fg.jobs[x].read_len > fg.jobs[y].read_len;
     });
     if (dev) {
@@ -876,7 +1067,9 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
         a.amap_off = dev->amap_off; a.amap = dev->amap;
         a.reference = dev->reference; a.allele_bytes = dev->allele_bytes; a.seq_pool = nullptr; a.read_bytes = dev->read_bytes; a.vtype = dev->vtype;
         a.order = (const uint32_t*)up(order.data(), 4ull * nj);
+        a.noise = ctx->wfa_no_filter ? nullptr : dev->noise;
     } else {
+        a.noise = nullptr;
         a.jobs = (const WfaJob*)up(fg.jobs.data(), sizeof(WfaJob) * nj);
         a.order = (const uint32_t*)up(order.data(), 4ull * nj);
         a.nodes = (const WfaNode*)up(fg.nodes.data(), sizeof(WfaNode) * fg.nodes.size());
@@ -924,6 +1117,7 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     a.out_alleles = carve(n_rows); a.out_quals = carve(n_rows);
     a.out_traversed = tw ? (uint64_t*)carve(8ull * nj * tw) : nullptr; a.trav_words = tw;
     a.out_counters = out->counters ? (uint64_t*)carve(32ull * nj) : nullptr;
+    a.dbg_times = ctx->wfa_dbg_times ? 1 : 0;
 
     WFA_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     // node masks: one word per lane up to 1024 nodes, four words (4096 nodes) for batches with a larger graph
@@ -933,6 +1127,7 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     WFA_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->launches++; ctx->timing_pending = true;
 
+    WFA_CUDA(ctx, cudaMemcpyAsync(&ctx->wfa_filtered_now, a.ticket + 1, 4, cudaMemcpyDeviceToHost, st));
     // download into temporaries, then scatter (the caller's arrays may be indexed by original job ids)
     ctx->wfa_h_status.resize(nj); ctx->wfa_h_score.resize(nj); ctx->wfa_h_nodes.resize(nj);
     ctx->wfa_h_alleles.resize(n_rows); ctx->wfa_h_quals.resize(n_rows);
@@ -947,6 +1142,7 @@ static int wfa_run(hp_ctx* ctx, const FlatGraphs& fg, const WfaHostInputs& in, u
     if (tw) WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_trav.data(), a.out_traversed, 8ull * nj * tw, cudaMemcpyDeviceToHost, st));
     if (out->counters) WFA_CUDA(ctx, cudaMemcpyAsync(ctx->wfa_h_ctr.data(), a.out_counters, 32ull * nj, cudaMemcpyDeviceToHost, st));
     WFA_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->wfa_filtered += ctx->wfa_filtered_now;
     return HP_OK;
 }
 
@@ -1086,6 +1282,7 @@ static int wfa_build_on_device(hp_ctx* ctx, const hp_wfa_batch* b, const std::ve
     WFA_CUDA(ctx, cudaStreamSynchronize(st));
     for (uint32_t k = 0; k < ns; k++) fg.jobs[k].pad = noise[k];
     dev = di.pools;
+    dev.noise = d_counts;
     dev.jobs = d_jobs; dev.nodes = a.nodes; dev.child_off = a.child_off; dev.child_idx = a.child_idx; dev.amap_off = a.amap_off; dev.amap = a.amap;
     return HP_OK;
 }
@@ -1119,6 +1316,7 @@ int hp_wfa_align_batch(hp_ctx* ctx, const hp_wfa_batch* b, hp_wfa_out* out) {
     if (!ctx || !b || !out || !out->status || !out->score || !out->alleles || !out->quals) return HP_ERR_INVALID_INPUT;
     if (b->n_jobs == 0) return HP_OK;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return wfa_fail(ctx, HP_ERR_CUDA, "cudaSetDevice failed");
+    ctx->wfa_filtered = 0;
     const hp_variant_table& vt = b->variants;
     for (uint32_t j = 0; j < b->n_jobs; j++) {
         if (b->het_hi[j] < b->het_lo[j] || b->hom_hi[j] < b->hom_lo[j] || b->het_hi[j] > vt.n_variants || b->hom_hi[j] > vt.n_variants ||

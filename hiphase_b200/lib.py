@@ -241,6 +241,15 @@ class Context:
         """Test / A-B aid: bit 0 = build the WFA graphs on the host, bit 1 = start without a workspace hint."""
         self.check(lib().hp_debug_wfa_build_mode(self._h, int(mode)))
 
+    def set_wfa_filter(self, on):
+        """Test / A-B aid: the piece filter that proves MaxEditDistance for hopeless reads without aligning them."""
+        self.check(lib().hp_debug_wfa_filter(self._h, int(bool(on))))
+
+    def wfa_filtered(self):
+        """Reads the piece filter answered in the last wfa_align_batch call."""
+        lib().hp_debug_wfa_filtered.restype = C.c_uint32
+        return int(lib().hp_debug_wfa_filtered(self._h))
+
     def launch_count(self):
         return int(lib().hp_launch_count(self._h))
 

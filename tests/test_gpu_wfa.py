@@ -194,3 +194,53 @@ def test_device_builder_overflow_falls_back_to_the_host_builder(ctx):
     ref_out = O.wfa_align(batch, threads=2, trav_words=4)
     out = ctx.wfa_align_batch(batch, trav_words=4)
     _assert_wfa_parity(out, ref_out)
+
+
+def test_piece_filter_is_exact():
+    """The piece filter answers MaxEditDistance for reads whose number of 10-base pieces that occur in no path of the graph
+    exceeds max_edit_distance (a lower bound of the edit distance of wfa_graph.rs:350-650).  Filter on, filter off and the
+    oracle agree on every output; the filter fires on the hopeless reads and on nothing else."""
+    batch, jb, meta = synth.config_c4(2, window=20000, n_het=30, n_hom=30, n_reads=24, read_lo=2500, read_hi=6000, sv_max=300,
+                                      err=0.01, p_noisy=0.35, err_noisy=0.3)
+    # reads at the limit: edit distance close to max_edit_distance on either side (errors every ~18 bases over the whole read)
+    for max_ed in (100, 200):
+        params = A.hp_params(1000, 3, 500, max_ed)
+        ref = O.wfa_align(batch, params, threads=8, trav_words=4)
+        n_max = int((ref.status == A.HP_WFA_MAX_EDIT_DISTANCE).sum())
+        assert n_max > 3 and (ref.status == A.HP_WFA_OK).sum() > 3
+        outs = []
+        for on in (1, 0):
+            c = lib.Context(params, device=0)
+            c.set_wfa_filter(on)
+            out = c.wfa_align_batch(batch, trav_words=4)
+            _assert_wfa_parity(out, ref)
+            outs.append(c.wfa_filtered())
+            c.close()
+        assert outs[1] == 0 and 0 < outs[0] <= n_max, (outs, n_max)
+
+
+def test_piece_filter_keeps_reads_near_the_limit():
+    """Reads with one substitution in (almost) every piece are within max_edit_distance although most of their pieces are
+    absent from the graph: the bound counts pieces, not bases, and must not fire below the limit."""
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    L = 3300                                              # 330 pieces > max_edit_distance 300: the filter is tried
+    ref = rng.integers(0, 4, L)
+    hets = [{"type": "snv", "pos": p, "ref_len": 1, "a0": bytes([acgt[ref[p]]]), "a1": bytes([acgt[(ref[p] + 1) % 4]])} for p in range(100, L - 100, 211)]
+    reads = []
+    for n_err in (280, 295, 300, 301, 305, 320):         # max_edit_distance 300: three on each side
+        seq = ref.copy()
+        pos = rng.choice(L // 10, n_err - 20, replace=False) * 10 + rng.integers(0, 10, n_err - 20)   # one per piece ...
+        seq[pos] = (seq[pos] + 2) % 4
+        extra = rng.choice(L, 20, replace=False)                                                  # ... and a few anywhere
+        seq[extra] = (seq[extra] + 1) % 4
+        reads.append(bytes(acgt[seq]))
+    batch = wfa_batch_single(bytes(acgt[ref]), hets, [], 0, L, reads)
+    params = A.hp_params(1000, 3, 500, 300)
+    ref_out = O.wfa_align(batch, params, threads=6, trav_words=1)
+    assert set(ref_out.status.tolist()) == {A.HP_WFA_OK, A.HP_WFA_MAX_EDIT_DISTANCE}
+    c = lib.Context(params, device=0)
+    out = c.wfa_align_batch(batch, trav_words=1)
+    _assert_wfa_parity(out, ref_out)
+    assert c.wfa_filtered() <= int((ref_out.status == A.HP_WFA_MAX_EDIT_DISTANCE).sum())
+    c.close()
