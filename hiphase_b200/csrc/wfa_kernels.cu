@@ -85,7 +85,8 @@ constexpr uint32_t kWfaMaxNodes = 4096;          // node activity mask: MW 32-bi
 constexpr uint32_t kNil = 0xffffffffu;
 constexpr uint32_t kNoisyProbe = 12;   // probe estimate (edits per 512 bases, over the start of the read) from which a job is scheduled first
 constexpr uint32_t kPiece = 10;                              // piece filter: bases per read piece (2 bits each -> 2^20 codes)
-constexpr uint64_t kPieceBitmapBytes = (1ull << (2 * kPiece)) / 8;
+constexpr uint32_t kPieceSlots = 4096;                       // ... hash set of the read's pieces (u32 entries, at most half full)
+constexpr uint64_t kPieceTableBytes = 4ull * kPieceSlots;
 constexpr uint64_t kEmptyKey = ~0ull;
 // One warp per CTA: a warp that is stuck with a long job (a read that runs to MaxEditDistance takes ~25 ms) then holds on to its own
 // registers only, and the CTAs of the next launch (another context's chunk, the A* of this one) move in beside it.  With 8 warps
@@ -105,10 +106,10 @@ constexpr int kPrivateSteps = HP_WFA_PRIVATE_STEPS;   // 8-base extension steps 
 __host__ __device__ inline uint32_t wfa_slot_stride(uint32_t set_words) { return 32u + 16u * set_words; }
 
 // slab layout: keys[cap] u64 | slots[cap * stride] | items[2][cap] u32 | seg_start[2][1024] | seg_len[2][1024] |
-//              late_head[1024] | chunks[cap/8 * 34] u32 | rowtmp[4096] u32 | kmer_bits[2^20 bits]
+//              late_head[1024] | chunks[cap/8 * 34] u32 | rowtmp[4096] u32 | piece_tbl[4096] u32
 __host__ __device__ inline uint64_t wfa_slab_bytes(uint32_t cap, uint32_t set_words) {
     uint64_t b = (uint64_t)cap * 8 + (uint64_t)cap * wfa_slot_stride(set_words) + 2ull * cap * 4 + 5ull * kWfaMaxNodes * 4 +
-                 (uint64_t)(cap / 8) * 34 * 4 + 4096ull * 4 + kPieceBitmapBytes;
+                 (uint64_t)(cap / 8) * 34 * 4 + 4096ull * 4 + kPieceTableBytes;
     return (b + 255) & ~255ull;
 }
 
@@ -121,7 +122,7 @@ struct WfaSlab {
     uint32_t* late_head;
     uint32_t* chunks;      // chunk c: [next, count, 32 items]
     uint32_t* rowtmp;
-    uint32_t* kmer_bits;   // piece filter: one bit per 10-mer code
+    uint32_t* piece_tbl;   // piece filter: hash set of the read's pieces
 };
 
 __device__ __forceinline__ WfaSlab wfa_carve(uint8_t* p, uint32_t cap, uint32_t set_words) {
@@ -137,7 +138,7 @@ __device__ __forceinline__ WfaSlab wfa_carve(uint8_t* p, uint32_t cap, uint32_t 
     s.late_head = (uint32_t*)p; p += kWfaMaxNodes * 4;
     s.chunks = (uint32_t*)p; p += (uint64_t)(cap / 8) * 34 * 4;
     s.rowtmp = (uint32_t*)p; p += 4096ull * 4;
-    s.kmer_bits = (uint32_t*)p;
+    s.piece_tbl = (uint32_t*)p;
     return s;
 }
 
@@ -326,13 +327,17 @@ __device__ __forceinline__ void wfa_push(WfaCtx& c, bool act, uint32_t node, int
 // leaves all but at most k pieces untouched, and an untouched piece occurs verbatim in that path.  So the number of pieces that
 // occur in NO path of the graph is a lower bound of the edit distance the reference computes (wfa_graph.rs:350-650, global in
 // the read and in the graph; pruning can only make its result larger).  If the bound exceeds max_edit_distance the reference
-// returns MaxEditDistance (:645-648) and so do we, without walking 500 edit-distance levels (~20 ms of one warp per read).
-// The kPiece-mers of all paths are collected in a bitmap: those inside a node by all lanes side by side, those that start in the
-// last kPiece - 1 bases of a node by a bounded depth-first walk through its descendants, one (node, start) pair per lane.  A
-// piece is looked up by a code that is a function of its bytes alone (two bits of each byte), so a piece that does occur always
-// finds its bit; bytes outside ACGT only make codes collide, which can hide a missing piece but never invent one.  A graph
-// whose walk exceeds its budget gives no verdict (the alignment runs as usual).  Only reads whose probe estimate, scaled to the
-// read, is clearly beyond max_edit_distance try it.
+// returns MaxEditDistance (:645-648) and so do we, without walking 500 edit-distance levels (~25 ms of one warp per read).
+// The read's pieces (the first 2048 of them: a subset still gives a lower bound) go into a small hash set with their
+// multiplicity (16 KB per warp, L2-resident); then every kPiece-mer of every path of the graph is looked up and its entry marked:
+// those inside a node by all lanes side by side, those that start in the last kPiece - 1 bases of a node by a bounded
+// depth-first walk through its descendants, one (node, start) pair per lane.  What stays unmarked is missing.  A piece is
+// identified by a code that is a function of its bytes alone (two bits of each byte), so a piece that does occur always finds
+// its entry; bytes outside ACGT only make codes collide, which can hide a missing piece but never invent one.  A graph whose
+// walk exceeds its budget gives no verdict (the alignment runs as usual).  Only reads whose probe estimate, scaled to the read,
+// reaches max_edit_distance try it.
+// entry: bits 0-20 code + 1 (0 = empty) | bits 21-30 multiplicity | bit 31 seen in the graph.  A multiplicity that overflows
+// runs into the "seen" bit and beyond: the entry then counts for less than it should, never for more.
 __device__ __forceinline__ uint32_t base2(uint32_t b) { return (b >> 1) & 3u; }
 __device__ __forceinline__ uint32_t pack8(uint64_t w) {          // base i of the 8 bytes -> bits [2i, 2i + 2)
     uint64_t x = (w >> 1) & 0x0303030303030303ull;
@@ -346,13 +351,38 @@ __device__ __forceinline__ uint32_t piece_code(const uint8_t* p) {   // code of 
     const uint64_t hi = ld64_unaligned(p + 8);
     return pack8(ld64_unaligned(p)) | (base2((uint32_t)hi) << 16) | (base2((uint32_t)(hi >> 8)) << 18);
 }
+__device__ __forceinline__ uint32_t piece_hash(uint32_t code) { return (code * 0x9E3779B1u) >> 20; }   // 12 bits
+static_assert(kPieceSlots == 4096, "piece_hash returns 12 bits");
+constexpr uint32_t kPieceKeyMask = 0x1FFFFFu, kPieceOne = 1u << 21, kPieceSeen = 1u << 31;
+
+// marks the entry of `code`, if the read has such a piece (the table is read at the L2: it was filled with atomics)
+__device__ __forceinline__ void piece_mark(uint32_t* tbl, uint32_t code) {
+    const uint32_t key = code + 1u;
+    for (uint32_t h = piece_hash(code);; h = (h + 1u) & (kPieceSlots - 1u)) {
+        const uint32_t v = __ldcg(&tbl[h]);
+        if (v == 0u) return;
+        if ((v & kPieceKeyMask) == key) { if (!(v & kPieceSeen)) atomicOr(&tbl[h], kPieceSeen); return; }
+    }
+}
 
 __device__ bool wfa_piece_filter(WfaCtx& c, const WfaArgs& a, const uint32_t* child_off, uint32_t n_nodes) {
     const uint32_t lane = c.lane;
-    const uint32_t pieces = c.read_len / kPiece;
+    const uint32_t pieces = min(c.read_len / kPiece, kPieceSlots / 2u);
     if (pieces <= a.max_edit_distance) return false;
-    uint32_t* bits = c.s.kmer_bits;
-    for (uint32_t i = lane; i < (uint32_t)(kPieceBitmapBytes / 16); i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
+    uint32_t* tbl = c.s.piece_tbl;
+    for (uint32_t i = lane; i < kPieceSlots / 4u; i += 32) __stcg(reinterpret_cast<uint4*>(tbl) + i, make_uint4(0, 0, 0, 0));
+    __threadfence_block();
+    __syncwarp();
+    // the read's pieces, with multiplicity
+    for (uint32_t t = lane; t < pieces; t += 32) {
+        const uint32_t code = piece_code(c.read + (uint64_t)t * kPiece), key = code + 1u;
+        for (uint32_t h = piece_hash(code);; h = (h + 1u) & (kPieceSlots - 1u)) {
+            const uint32_t old = atomicCAS(&tbl[h], 0u, key | kPieceOne);
+            if (old == 0u) break;
+            if ((old & kPieceKeyMask) == key) { atomicAdd(&tbl[h], kPieceOne); break; }
+        }
+    }
+    __threadfence_block();
     __syncwarp();
     // pieces inside a node
     for (uint32_t u0 = 0; u0 < n_nodes; u0 += 32) {
@@ -364,10 +394,7 @@ __device__ bool wfa_piece_filter(WfaCtx& c, const WfaArgs& a, const uint32_t* ch
             const uint32_t len = __shfl_sync(HP_FULL_MASK, mine.len, k);
             const uint8_t* seq = (const uint8_t*)__shfl_sync(HP_FULL_MASK, (unsigned long long)(uintptr_t)my_seq, k);
             if (len < kPiece) continue;
-            for (uint32_t i = lane; i + kPiece <= len; i += 32) {
-                const uint32_t code = piece_code(seq + i);
-                atomicOr(&bits[code >> 5], 1u << (code & 31u));
-            }
+            for (uint32_t i = lane; i + kPiece <= len; i += 32) piece_mark(tbl, piece_code(seq + i));
         }
     }
     // pieces that start in the last kPiece - 1 bases of a node and continue into its descendants
@@ -399,7 +426,7 @@ __device__ bool wfa_piece_filter(WfaCtx& c, const WfaArgs& a, const uint32_t* ch
                     const uint32_t t = min(kPiece - have, cn.len);
                     for (uint32_t k = 0; k < t; k++) cc |= base2(cs[k]) << (2 * (have + k));
                     have += t;
-                    if (have == kPiece) { atomicOr(&bits[cc >> 5], 1u << (cc & 31u)); continue; }
+                    if (have == kPiece) { piece_mark(tbl, cc); continue; }
                     if (depth + 1 >= kMaxDepth) { giveup = true; break; }
                     depth++;
                     st_node[depth] = ch; st_edge[depth] = child_off[ch]; st_code[depth] = cc; st_have[depth] = have;
@@ -412,9 +439,9 @@ __device__ bool wfa_piece_filter(WfaCtx& c, const WfaArgs& a, const uint32_t* ch
     __threadfence_block();
     __syncwarp();
     uint32_t missing = 0;
-    for (uint32_t t = lane; t < pieces; t += 32) {
-        const uint32_t code = piece_code(c.read + (uint64_t)t * kPiece);
-        if (!((__ldcg(&bits[code >> 5]) >> (code & 31u)) & 1u)) missing++;
+    for (uint32_t i = lane; i < kPieceSlots; i += 32) {
+        const uint32_t v = __ldcg(&tbl[i]);
+        if (v != 0u && !(v & kPieceSeen)) missing += (v >> 21) & 0x3FFu;
     }
     missing = __reduce_add_sync(HP_FULL_MASK, missing);
     return missing > a.max_edit_distance;
