@@ -321,6 +321,7 @@ void hp_ctx_destroy(hp_ctx* ctx) {
                       &ctx->wfa_out, &ctx->wfa_graph, &ctx->comm_send, &ctx->comm_recv})
         b->release();
     ctx->pin_send.release(); ctx->pin_recv.release();
+    ctx->realign_rb.release(); ctx->realign_rq.release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

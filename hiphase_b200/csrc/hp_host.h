@@ -113,6 +113,9 @@ struct hp_ctx {
     int comm_rank = 0, comm_world = 1;
     hp::DevBuf comm_send, comm_recv;
     hp::HostPin pin_send, pin_recv;
+    // hp_realign_block_batch: pinned scratch for the bases / qualities of the reads gathered for local realignment (grow-only:
+    // fresh pageable vectors cost ~10 ms of page faults per call and a staged copy)
+    hp::HostPin realign_rb, realign_rq;
 };
 
 namespace hp {

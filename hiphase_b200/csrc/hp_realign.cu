@@ -79,7 +79,9 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         uint64_t n_seg = 0, n_rd = 0;
         for (size_t k = 0; k < ns; k++) { const uint32_t j = sel[k]; n_seg += L.seg_off[j + 1] - L.seg_off[j]; n_rd += L.read_off[j + 1] - L.read_off[j]; }
         c_sr.reserve(n_seg); c_sd.reserve(n_seg); c_sl.reserve(n_seg);
-        std::vector<uint8_t> c_rb(n_rd + 1), c_rq(n_rd + 1);
+        if (!ctx->realign_rb.reserve(n_rd + 1) || !ctx->realign_rq.reserve(n_rd + 1)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "pinned scratch for local realignment");
+        uint8_t* c_rb = (uint8_t*)ctx->realign_rb.ptr;
+        uint8_t* c_rq = (uint8_t*)ctx->realign_rq.ptr;
         for (size_t k = 0; k < ns; k++) {
             const uint32_t j = sel[k];
             c_lo[k] = L.var_lo[j]; c_hi[k] = L.var_hi[j]; c_pos[k] = L.read_pos[j];
@@ -95,7 +97,7 @@ extern "C" int hp_realign_block_batch(hp_ctx* ctx, const hp_realign_batch* in, h
         cb.n_jobs = (uint32_t)ns;
         cb.var_lo = c_lo.data(); cb.var_hi = c_hi.data(); cb.read_pos = c_pos.data(); cb.seg_off = c_seg_off.data();
         cb.seg_ref_start = c_sr.data(); cb.seg_read_start = c_sd.data(); cb.seg_len = c_sl.data();
-        cb.read_bytes = c_rb.data(); cb.read_quals = c_rq.data(); cb.read_off = c_read_off.data(); cb.row_off = c_row_off.data();
+        cb.read_bytes = c_rb; cb.read_quals = c_rq; cb.read_off = c_read_off.data(); cb.row_off = c_row_off.data();
         std::vector<uint8_t> o_al(c_row_off[ns] + 1), o_q(c_row_off[ns] + 1);
         std::vector<int32_t> o_st(ns, -1);
         hp_local_out co{};
