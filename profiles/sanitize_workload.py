@@ -42,3 +42,13 @@ svc = lib.BlockService(device=0)
 h1, h2, st = svc.solve_one(bs[3], 2)
 svc.close()
 print("round-2 sanitizer workload ok")
+# second half of round 2: the piece filter (hash set of read pieces, bounded depth-first walk), the warp-wide extension and the
+# atomic-free slot insertion, on noisy reads around max_edit_distance
+wb2, _, _ = synth.config_c4(1, window=8000, n_het=14, n_hom=14, n_reads=10, read_lo=2200, read_hi=3500, sv_max=200, err=0.01, p_noisy=0.5, err_noisy=0.3)
+p2 = A.hp_params(1000, 3, 500, 100)
+c3 = lib.Context(p2, device=0)
+wo2 = c3.wfa_align_batch(wb2, trav_words=2); wr2 = O.wfa_align(wb2, p2, threads=4, trav_words=2)
+assert np.array_equal(wo2.status, wr2.status) and np.array_equal(wo2.score, wr2.score) and np.array_equal(wo2.alleles, wr2.alleles)
+assert c3.wfa_filtered() > 0 and (wr2.status == 0).any()
+c3.close()
+print("round-2 piece-filter workload ok")

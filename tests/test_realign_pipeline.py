@@ -90,6 +90,39 @@ def test_gpu_pipeline_trips_at_fifty_failures():
     ctx.close()
 
 
+@pytest.mark.gpu
+def test_contexts_on_several_threads_agree_with_the_oracle():
+    """The reference calls the loop from its pool workers (main.rs:385-408); here a worker owns a context.  Four threads run
+    different batches side by side, several times over, with A* behind each: every result equals the oracle's."""
+    import threading
+    params = A.hp_params(1000, 3, 500, 8)
+    work = [_batch(2, 30 + 5 * k, 5, 0.3, err=0.004, **SMALL) for k in range(4)]
+    refs = [O.realign_block_batch(b, params) for b, _ in work]
+    assert all(r.rc == 0 for r in refs)
+    errors = []
+
+    def worker(k):
+        try:
+            ctx = lib.Context(params, device=0)
+            b, vtypes = work[k]
+            is_snv = np.concatenate([(np.array(v) == 0).astype(np.uint8) for v in vtypes])
+            exp = O.astar_solve(refs[k].block_batch(is_snv=is_snv), params, want_heuristic=False, want_counters=False)
+            for _ in range(3):
+                out = ctx.realign_block_batch(b)
+                _same(out, refs[k])
+                got = ctx.astar_solve_batch(out.block_batch(is_snv=is_snv))
+                assert np.array_equal(got.h1, exp.h1) and np.array_equal(got.h2, exp.h2) and np.array_equal(got.stats, exp.stats)
+            ctx.close()
+        except BaseException as e:      # noqa: BLE001 -- reported by the main thread
+            errors.append((k, repr(e)))
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 # ---- CIGAR projection (the pre-WFA half of global_realignment, read_parsing.rs:672-742) --------------------------------
 def _plan_inputs(n_blocks, seed0, **kw):
     map_block, seg_off, sr, sd, sl, het_first, het_pos, hom_first, hom_pos, reads = [], [0], [], [], [], [0], [], [0], [], []
