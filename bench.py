@@ -423,9 +423,12 @@ def main():
     class _Local:        # what hp_comm_gather_results needs of the local batch: its variant offsets
         var_off = local_var_off
 
-    def e2e_steps(k_steps):
+    def e2e_steps(k_steps, src=None, dst=None):
         """Chunk jobs go to the lanes as they free up (at most n_lanes in flight, oldest waited first); a step is complete when
-        its last chunk has landed: its results are handed to rank 0 in block order."""
+        its last chunk has landed: its results are handed to rank 0 in block order.  src / dst: the host batches and output
+        sets to use (default: the pinned ones)."""
+        src = chunks if src is None else src
+        dst = host_outs if dst is None else dst
         flight = []
 
         def retire():
@@ -439,7 +442,7 @@ def main():
             for c in range(n_chunks):
                 if len(flight) == n_lanes:
                     retire()
-                flight.append((ctx.astar_submit(chunks[c], out=host_outs[k % steps_in_flight][c]), k, c))
+                flight.append((ctx.astar_submit(src[c], out=dst[k % steps_in_flight][c]), k, c))
         while flight:
             retire()
 
@@ -469,14 +472,15 @@ def main():
                 setattr(p, k, np.array(getattr(b, k), copy=True))
             p.n_blocks = b.n_blocks
             pg.append(p)
-        ksteps = max(2, min(5, args.steps))
+        pg_outs = [[A.AstarOut.sized(b.n_vars, b.n_blocks) for b in chunks] for _ in range(steps_in_flight)]
+        ksteps = max(2, min(10, args.steps))
+        e2e_steps(max(2, (n_lanes + n_chunks - 1) // n_chunks + 1), pg, pg_outs)      # every lane gets its pinned staging first
         sync_all()
         t0 = time.perf_counter()
-        for _ in range(ksteps):
-            jobs = [ctx.astar_submit(p) for p in pg]
-            for j in jobs:
-                ctx.astar_wait(j)
+        e2e_steps(ksteps, pg, pg_outs)        # the same pipelined loop as above, inputs and outputs in ordinary numpy arrays
+        torch.cuda.synchronize()
         e2e_pageable = wl.n_total / ((time.perf_counter() - t0) / ksteps)
+        del pg_outs
         del pg
 
     if rank == 0:

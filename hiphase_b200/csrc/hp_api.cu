@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 #include <cuda_runtime.h>
 
@@ -105,6 +107,7 @@ static void lane_destroy(AstarLane* l) {
     for (DevBuf* b : {&l->meta, &l->rmeta, &l->planes, &l->act_off, &l->act_cur, &l->act_idx, &l->col, &l->order, &l->heur,
                       &l->ticket, &l->stage_in, &l->stage_out, &l->dbg})
         b->release();
+    l->pin_in.release(); l->pin_out.release();
     for (cudaEvent_t e : {l->ev0, l->ev1, l->ev_fork, l->ev_join[0], l->ev_join[1], l->ev_done, l->ev_in}) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {l->stream, l->aux[0], l->aux[1]}) if (st) cudaStreamDestroy(st);
     delete l;
@@ -240,6 +243,41 @@ int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_
 }
 
 // Marks the end of everything enqueued for this lane on `stream` (kernels and result copies).
+// true when the driver would have to stage copies to / from this host pointer (ordinary malloc / Vec memory)
+bool host_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// Copies the segments {dst, src, bytes} with a few threads (a single memcpy stream is ~10 GB/s; the H2D engine takes 50).
+void parallel_copy(const std::vector<CopySeg>& segs) {
+    constexpr size_t kPiece = 4u << 20;
+    std::vector<CopySeg> pieces;
+    size_t total = 0;
+    for (const CopySeg& s : segs)
+        for (size_t o = 0; o < s.bytes; o += kPiece) { pieces.push_back({s.dst + o, s.src + o, std::min(kPiece, s.bytes - o)}); total += pieces.back().bytes; }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min<size_t>(8, hw), std::max<size_t>(1, total / (8u << 20)));
+    std::atomic<size_t> next{0};
+    auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < pieces.size();) memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes); };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (std::thread& t : th) t.join();
+}
+
+// Host -> device copy of a large array: pageable sources go through `pin` (filled by parallel_copy) so the copy engine runs
+// at its own speed; pinned sources and small arrays are copied directly.  `pin` must stay untouched until the stream is synchronised.
+bool upload_large(HostPin& pin, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return true;
+    if (bytes < (4u << 20) || !host_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!pin.reserve(bytes)) return false;
+    parallel_copy({CopySeg{(uint8_t*)pin.ptr, (const uint8_t*)src, bytes}});
+    return cudaMemcpyAsync(dst, pin.ptr, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+}
+
 static int lane_mark_done(hp_ctx* ctx, AstarLane* L, cudaStream_t stream) {
     HP_CUDA(ctx, cudaEventRecord(L->ev_done, stream));
     L->used = true;
@@ -322,6 +360,7 @@ void hp_ctx_destroy(hp_ctx* ctx) {
         b->release();
     ctx->pin_send.release(); ctx->pin_recv.release();
     ctx->realign_rb.release(); ctx->realign_rq.release();
+    ctx->pin_reads.release(); ctx->pin_ref.release(); ctx->pin_quals.release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -470,7 +509,8 @@ static int validate_host_batch(hp_ctx* ctx, const hp_block_batch* b, uint32_t* m
 // Carves `bytes` (256-aligned) out of a staging buffer.
 static uint8_t* carve(uint8_t*& p, size_t bytes) { uint8_t* r = p; p += (bytes + 255) & ~(size_t)255; return r; }
 
-// H2D + kernels + D2H of one host batch, all asynchronous on the lane's stream (no synchronisation).
+// H2D + kernels + D2H of one host batch, all asynchronous on the lane's stream (no synchronisation).  The lane's previous
+// job has been waited for (hp_astar_wait / the retry's own synchronisation), so its pinned staging is free.
 static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, hp_astar_out* out, uint32_t max_n, int max_ctas, int busy_lanes) {
     const uint32_t nb = b->n_blocks;
     const uint64_t n_vars = b->var_off[nb], n_reads = b->read_off[nb], n_cells = b->cell_off[n_reads];
@@ -481,12 +521,19 @@ static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b
     const size_t in_bytes = 256 * 12 + 8 * (nb + 1) * 2 + 4 * n_reads * 2 + 8 * (n_reads + 1) + n_cells * 2 + n_vars * 2;
     if (in_bytes > L->stage_in.cap && L->used) HP_CUDA(ctx, cudaEventSynchronize(L->ev_done));   // re-allocation frees the old buffer
     if (!L->stage_in.reserve(in_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "input staging allocation failed");
+    const bool stage_inputs = host_pageable(n_cells ? (const void*)b->alleles : (const void*)b->var_off);
+    if (stage_inputs && !L->pin_in.reserve(in_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "pinned input staging allocation failed");
     uint8_t* p = (uint8_t*)L->stage_in.ptr;
+    uint8_t* const p0 = p;
+    std::vector<CopySeg> segs;
     hp_block_batch d = *b;
 #define HP_UP(field, type, count)                                                                                  \
     do {                                                                                                           \
         uint8_t* dst = carve(p, sizeof(type) * (size_t)(count));                                                   \
-        if ((count) > 0) HP_CUDA(ctx, cudaMemcpyAsync(dst, b->field, sizeof(type) * (size_t)(count), cudaMemcpyHostToDevice, st)); \
+        if ((count) > 0) {                                                                                         \
+            if (stage_inputs) segs.push_back({(uint8_t*)L->pin_in.ptr + (dst - p0), (const uint8_t*)b->field, sizeof(type) * (size_t)(count)}); \
+            else HP_CUDA(ctx, cudaMemcpyAsync(dst, b->field, sizeof(type) * (size_t)(count), cudaMemcpyHostToDevice, st)); \
+        }                                                                                                          \
         d.field = (const type*)dst;                                                                                \
     } while (0)
     HP_UP(var_off, uint64_t, nb + 1); HP_UP(read_off, uint64_t, nb + 1);
@@ -494,12 +541,17 @@ static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b
     HP_UP(alleles, uint8_t, n_cells); HP_UP(quals, uint8_t, n_cells);
     HP_UP(ignored, uint8_t, n_vars); HP_UP(is_snv, uint8_t, n_vars);
 #undef HP_UP
+    if (stage_inputs) {
+        parallel_copy(segs);
+        HP_CUDA(ctx, cudaMemcpyAsync(p0, L->pin_in.ptr, (size_t)(p - p0), cudaMemcpyHostToDevice, st));
+    }
     // ---- device outputs ----
     const size_t out_bytes = 256 * 8 + n_vars * 2 + sizeof(hp_phase_stats) * (size_t)nb + 4ull * nb +
                              (out->heuristic ? 8 * (n_vars + nb) : 0) + (out->counters ? sizeof(hp_astar_counters) * (size_t)nb : 0);
     if (out_bytes > L->stage_out.cap && L->used) HP_CUDA(ctx, cudaEventSynchronize(L->ev_done));
     if (!L->stage_out.reserve(out_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "output staging allocation failed");
     uint8_t* q = (uint8_t*)L->stage_out.ptr;
+    uint8_t* const q0 = q;
     hp_astar_out dout;
     dout.h1 = carve(q, n_vars); dout.h2 = carve(q, n_vars);
     dout.stats = (hp_phase_stats*)carve(q, sizeof(hp_phase_stats) * (size_t)nb);
@@ -510,6 +562,16 @@ static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b
     int rc = astar_device(ctx, L, &d, n_vars, n_reads, n_cells, max_n, &dout, st, max_ctas, busy_lanes);
     if (rc != HP_OK) return rc;
     // ---- D2H ----
+    L->out_staged = host_pageable(out->h1);
+    if (L->out_staged) {
+        if (!L->pin_out.reserve(out_bytes)) return fail(ctx, HP_ERR_OUT_OF_MEMORY, "pinned output staging allocation failed");
+        L->out_off[0] = (size_t)((uint8_t*)dout.h1 - q0); L->out_off[1] = (size_t)((uint8_t*)dout.h2 - q0);
+        L->out_off[2] = (size_t)((uint8_t*)dout.stats - q0); L->out_off[3] = (size_t)((uint8_t*)dout.status - q0);
+        L->out_off[4] = dout.heuristic ? (size_t)((uint8_t*)dout.heuristic - q0) : 0;
+        L->out_off[5] = dout.counters ? (size_t)((uint8_t*)dout.counters - q0) : 0;
+        HP_CUDA(ctx, cudaMemcpyAsync(L->pin_out.ptr, q0, (size_t)(q - q0), cudaMemcpyDeviceToHost, st));
+        return lane_mark_done(ctx, L, st);
+    }
     HP_CUDA(ctx, cudaMemcpyAsync(out->h1, dout.h1, n_vars, cudaMemcpyDeviceToHost, st));
     HP_CUDA(ctx, cudaMemcpyAsync(out->h2, dout.h2, n_vars, cudaMemcpyDeviceToHost, st));
     HP_CUDA(ctx, cudaMemcpyAsync(out->stats, dout.stats, sizeof(hp_phase_stats) * (size_t)nb, cudaMemcpyDeviceToHost, st));
@@ -517,6 +579,23 @@ static int astar_host_enqueue(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b
     if (out->heuristic) HP_CUDA(ctx, cudaMemcpyAsync(out->heuristic, dout.heuristic, 8 * (n_vars + nb), cudaMemcpyDeviceToHost, st));
     if (out->counters) HP_CUDA(ctx, cudaMemcpyAsync(out->counters, dout.counters, sizeof(hp_astar_counters) * (size_t)nb, cudaMemcpyDeviceToHost, st));
     return lane_mark_done(ctx, L, st);
+}
+
+// After the lane's stream has been synchronised: results that landed in the pinned staging go to the caller's arrays.
+static void astar_host_deliver(AstarLane* L, const hp_block_batch* b, hp_astar_out* out) {
+    if (!L->out_staged) return;
+    L->out_staged = false;
+    const uint32_t nb = b->n_blocks;
+    const uint64_t n_vars = b->var_off[nb];
+    const uint8_t* s = (const uint8_t*)L->pin_out.ptr;
+    std::vector<CopySeg> segs;
+    segs.push_back({out->h1, s + L->out_off[0], (size_t)n_vars});
+    segs.push_back({out->h2, s + L->out_off[1], (size_t)n_vars});
+    segs.push_back({(uint8_t*)out->stats, s + L->out_off[2], sizeof(hp_phase_stats) * (size_t)nb});
+    segs.push_back({(uint8_t*)out->status, s + L->out_off[3], 4ull * nb});
+    if (out->heuristic) segs.push_back({(uint8_t*)out->heuristic, s + L->out_off[4], 8 * (size_t)(n_vars + nb)});
+    if (out->counters) segs.push_back({(uint8_t*)out->counters, s + L->out_off[5], sizeof(hp_astar_counters) * (size_t)nb});
+    parallel_copy(segs);
 }
 
 // Blocks whose main queue outgrew its slab are re-run (synchronously, on the same lane) with a 4x larger slab and
@@ -566,7 +645,8 @@ static int astar_host_retry(hp_ctx* ctx, AstarLane* L, const hp_block_batch* b, 
         int max_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>(ctx->sm_count, (24ull << 30) / std::max<uint64_t>(slab, 1)));
         int rc = astar_host_enqueue(ctx, L, &sb, &so, sub_max, max_ctas, 0);
         if (rc == HP_OK && cudaStreamSynchronize(L->stream) != cudaSuccess) { cudaGetLastError(); rc = fail(ctx, HP_ERR_CUDA, "retry pass failed on the device"); }
-        if (rc != HP_OK) { ctx->qcap = qcap0; return rc; }
+        if (rc != HP_OK) { ctx->qcap = qcap0; L->out_staged = false; return rc; }
+        astar_host_deliver(L, &sb, &so);
         for (size_t k = 0; k < redo.size(); k++) {
             const uint32_t i = redo[k];
             const uint64_t v0 = b->var_off[i], n = b->var_off[i + 1] - v0;
@@ -623,9 +703,11 @@ int hp_astar_wait(hp_ctx* ctx, hp_astar_job* job) {
     if (job->batch.n_blocks != 0) {
         if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(L->stream) != cudaSuccess) {
             cudaGetLastError();
+            L->out_staged = false;
             rc = fail(ctx, HP_ERR_CUDA, "device work of the job failed");
         } else {
             ctx->last_lane = job->lane;
+            astar_host_deliver(L, &job->batch, &job->out);
             rc = astar_host_retry(ctx, L, &job->batch, &job->out);
         }
     }

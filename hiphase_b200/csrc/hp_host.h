@@ -36,6 +36,12 @@ struct HostPin {
     void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
 };
 
+// pageable host memory (hp_api.cu)
+struct CopySeg { uint8_t* dst; const uint8_t* src; size_t bytes; };
+bool host_pageable(const void* p);
+void parallel_copy(const std::vector<CopySeg>& segs);
+bool upload_large(HostPin& pin, void* dst, const void* src, size_t bytes, cudaStream_t st);
+
 // kernel launchers (astar_kernels.cu)
 size_t astar_smem_bytes(uint32_t sub_capl, int team);
 int astar_max_team();
@@ -56,6 +62,13 @@ struct AstarLane {
     bool used = false;                       // ev_done has been recorded at least once
     bool timing_pending = false;
     hp::DevBuf meta, rmeta, planes, act_off, act_cur, act_idx, col, order, heur, ticket, stage_in, stage_out, dbg;
+    // Pageable caller buffers (an ordinary Vec): inputs are gathered into pin_in by a few host threads and go to the device in
+    // one copy; results land in pin_out and are handed to the caller's arrays by hp_astar_wait.  (A cudaMemcpyAsync to or from
+    // pageable memory is staged by the driver and blocks the calling thread until the stream gets there, which would make
+    // hp_astar_submit wait for the kernels.)
+    hp::HostPin pin_in, pin_out;
+    bool out_staged = false;                 // the batch in flight writes its results to pin_out
+    size_t out_off[6] = {0, 0, 0, 0, 0, 0};  // h1, h2, stats, status, heuristic, counters inside pin_out
     struct hp_astar_job* job = nullptr;      // job in flight on this lane (streaming entry)
 };
 
@@ -116,6 +129,8 @@ struct hp_ctx {
     // hp_realign_block_batch: pinned scratch for the bases / qualities of the reads gathered for local realignment (grow-only:
     // fresh pageable vectors cost ~10 ms of page faults per call and a staged copy)
     hp::HostPin realign_rb, realign_rq;
+    // pinned staging for large pageable inputs of the synchronous entries (read bases, reference, base qualities)
+    hp::HostPin pin_reads, pin_ref, pin_quals;
 };
 
 namespace hp {

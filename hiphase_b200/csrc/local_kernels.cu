@@ -573,7 +573,9 @@ extern "C" int hp_local_realign_batch(hp_ctx* ctx, const hp_local_batch* b, hp_l
     a.seg_ref = (const int64_t*)up(b->seg_ref_start, 8 * n_segs);
     a.seg_read = (const uint32_t*)up(b->seg_read_start, 4 * n_segs);
     a.seg_len = (const uint32_t*)up(b->seg_len, 4 * n_segs);
-    a.read_bytes = up(b->read_bytes, n_read); a.read_quals = up(b->read_quals, n_read);
+    // bulk arrays: pageable sources go through pinned staging (hp::upload_large)
+    { uint8_t* d = p; p += al256(n_read); ok &= hp::upload_large(ctx->pin_reads, d, b->read_bytes, n_read, st); a.read_bytes = d; }
+    { uint8_t* d = p; p += al256(n_read); ok &= hp::upload_large(ctx->pin_quals, d, b->read_quals, n_read, st); a.read_quals = d; }
     a.read_off = (const uint64_t*)up(b->read_off, 8 * ((size_t)nj + 1));
     a.row_off = (const uint64_t*)up(b->row_off, 8 * ((size_t)nj + 1));
     uint8_t* q = (uint8_t*)ctx->stage_out.ptr;

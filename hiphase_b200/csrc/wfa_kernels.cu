@@ -1203,8 +1203,9 @@ static int wfa_upload_batch(hp_ctx* ctx, const hp_wfa_batch* b, DevInputs& di, s
     a.index_allele0 = up(vt.index_allele0, nv); a.ignored = up(vt.ignored, nv);
     di.pools.vtype = up(vt.vtype, nv);
     di.pools.allele_bytes = up(vt.allele_bytes, vt.n_allele_bytes);
-    di.pools.reference = up(b->reference, b->n_reference);
-    di.pools.read_bytes = up(b->read_bytes, n_read);
+    // the two bulk arrays: pageable sources go through pinned staging (hp::upload_large)
+    { uint8_t* d = p; p += al(b->n_reference); ok &= upload_large(ctx->pin_ref, d, b->reference, b->n_reference, st); di.pools.reference = d; }
+    { uint8_t* d = p; p += al(n_read); ok &= upload_large(ctx->pin_reads, d, b->read_bytes, n_read, st); di.pools.read_bytes = d; }
     a.ref_start = (const uint64_t*)up(b->ref_start, 8ull * nj); a.ref_end = (const uint64_t*)up(b->ref_end, 8ull * nj);
     a.het_lo = (const uint32_t*)up(b->het_lo, 4ull * nj); a.het_hi = (const uint32_t*)up(b->het_hi, 4ull * nj);
     a.hom_lo = (const uint32_t*)up(b->hom_lo, 4ull * nj); a.hom_hi = (const uint32_t*)up(b->hom_hi, 4ull * nj);

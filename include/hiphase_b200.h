@@ -198,8 +198,13 @@ void hp_service_destroy(hp_service* svc);
  * hp_astar_submit enqueues H2D + kernels + D2H of one batch on one of the context's lanes (own stream and workspaces;
  * hp_ctx_set_lanes, default 4) and returns without waiting; batches in flight on different lanes share the GPU, so the
  * long serial chain of one noisy block overlaps the next batches instead of idling the device.  The caller's buffers
- * (*batch arrays and *out arrays) must stay valid and untouched until hp_astar_wait returns; they should be pinned
- * (hp_host_alloc / hp_host_register) -- pageable buffers work but make the copies synchronous.
+ * (*batch arrays and *out arrays) must stay valid and untouched until hp_astar_wait returns.  Pinned buffers
+ * (hp_host_alloc / hp_host_register) are copied from and to directly.  Pageable buffers (an ordinary Vec) are staged by the
+ * library: submit gathers the inputs into the lane's pinned staging with a few host threads (it may then be reused at
+ * once, though the contract above does not promise it), the results land in pinned staging and hp_astar_wait copies them
+ * into *out -- so the results of a pageable job are in *out only after hp_astar_wait, not when hp_astar_poll reports done.
+ * C3 end to end: 115 k blocks/s pinned, 93 k pageable (37 k before the staging: a cudaMemcpyAsync to pageable memory
+ * blocks the caller until the stream gets there).
  * hp_astar_wait blocks until the results are in *out (overflowed blocks are re-run there, as in hp_astar_solve_batch)
  * and releases the job.  Submitting more jobs than lanes waits for the oldest job's device work first.
  * HP_OK from wait / solve_batch means the call ran: each block's own outcome is in out->status[] (HP_BLOCK_*).
