@@ -476,6 +476,12 @@ __host__ __device__ inline uint64_t sub_spill_bytes(uint32_t capl, uint32_t capl
     return ((aos > pay ? aos : pay) + 255) & ~255ull;
 }
 constexpr uint32_t kFreeStack = 192;   // free main-queue record slots kept in shared memory
+// Sub-solver score vectors as packed u16x2 (a read's cost against h1 in the low half, against h2 in the high half: a window of
+// <= 63 variants of quality <= 255 stays below 2^16), so the per-slot child arithmetic runs on the packed-halfword min
+// (VIMNMX.U16x2, the DPX family of sm_90+ / sm_100) and PRMT, and the carry into the next column moves two words, not four.
+#ifndef HP_SUB_PACKED
+#define HP_SUB_PACKED 1
+#endif
 
 struct WarpCtx {
     SubEntry* sq;           // this warp's sub-solver queue: first capl_s entries of every stripe, in shared memory
@@ -763,7 +769,11 @@ restart:
     uint32_t cur_x1 = 0, cur_x2 = 0;
     uint32_t heur_p = cur_total;                    // heuristic term inside cur_total (root quirk: H[v+1])
     // children of the last expansion, already in the slot order of the column after it
+#if HP_SUB_PACKED
+    uint32_t nX[K], nY[K], nW[K];                   // X = A0 | B0 << 16, Y = A1 | B1 << 16
+#else
     uint32_t nA0[K], nA1[K], nB0[K], nB1[K], nW[K];
+#endif
     uint32_t cache_first = 0xffffffffu, cache_present = 0;
     // column records of the current column p (slot = lane + 32k) and the offsets of p and p+1
     // column records two columns ahead are always in flight (the small L1 next to 196 KB of shared memory misses often)
@@ -771,7 +781,11 @@ restart:
     uint32_t colc[K], coln[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
+#if HP_SUB_PACKED
+        nX[k] = nY[k] = nW[k] = 0;
+#else
         nA0[k] = nA1[k] = nB0[k] = nB1[k] = nW[k] = 0;
+#endif
         colc[k] = (lane + 32u * k < o_p1 - o_p) ? __ldg(col + o_p + lane + 32u * k) : kEmpty;
         coln[k] = (v + 1 < N) ? __ldg(col_lane + o_p1 + 32u * k) : kEmpty;
     }
@@ -878,6 +892,56 @@ restart:
         const bool bad_col = (badwin & lbit) != 0ull;
         const bool ident = (cur_h1 == cur_h2);
 
+#if HP_SUB_PACKED
+        // ---- this node's (s1 | s2 << 16) per slot ----
+        uint32_t s12[K], wv[K];
+        if (cur_src == SRC_CACHE) {
+            // low half from X (A0) or Y (A1) by the node's h1 allele, high half from X (B0) or Y (B1) by its h2 allele
+            const uint32_t sel = (cur_x1 ? 0x54u : 0x10u) | (cur_x2 ? 0x7600u : 0x3200u);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                // slots beyond the column's coverage hold nothing (warp-uniform test): their work is skipped below as well
+                if (k == 0 || a_cur > 32u * k) { s12[k] = __byte_perm(nX[k], nY[k], sel); wv[k] = nW[k]; }
+                else { s12[k] = 0; wv[k] = 0; }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) { s12[k] = 0; wv[k] = 0; }
+            if (cur_src == SRC_PLANES) {
+                auto hap = [&](int which, int i0) { return shift_signed(which ? cur_h2 : cur_h1, i0); };
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const uint32_t j = lane + 32u * k;
+                    if (j < a_cur) {
+                        const ReadMeta rm = rmeta[__ldg(aidx + o_p + j)];
+                        uint32_t s1, s2;
+                        score_planes(a, m, rm, (int)v - (int)rm.start, (int)L, hap, s1, s2);
+                        s12[k] = s1 | (s2 << 16);
+                        wv[k] = p - (uint32_t)max((int)rm.start, (int)v);
+                    }
+                }
+            }
+        }
+        // ---- children: X = (A0 | B0 << 16) = s12 + q0, Y = (A1 | B1 << 16) = s12 + q1; deltas against base, two per word ----
+        uint32_t X[K], Y[K];
+        uint32_t pk0 = 0, pk1 = 0;
+        uint64_t cells = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (k > 0 && a_cur <= 32u * k) { X[k] = Y[k] = 0; continue; }                       // empty slot: contributes nothing
+            const uint32_t c = colc[k];
+            const uint32_t qq = bad_col ? 0u : (c & 0xffu) * 0x10001u;                          // quality in both halves
+            const uint32_t al = c & 0x300u;
+            X[k] = s12[k] + ((al != 0u) ? qq : 0u);
+            Y[k] = s12[k] + ((al != 0x100u) ? qq : 0u);
+            const uint32_t base2 = __vminu2(s12[k], __byte_perm(s12[k], 0, 0x1032));            // min(s1, s2) in both halves
+            const uint32_t m01 = __vminu2(X[k], __byte_perm(Y[k], 0, 0x1032));                  // min(A0, B1) | min(B0, A1) << 16
+            const uint32_t m00 = __vminu2(__byte_perm(X[k], Y[k], 0x5410), __byte_perm(X[k], Y[k], 0x7632));   // min(A0, B0) | min(A1, B1) << 16
+            pk0 += m01 - base2;
+            pk1 += m00 - base2;
+            if (kCount) { wv[k] += 1; if (lane + 32u * k < a_cur) cells += wv[k]; }
+        }
+#else
         // ---- this node's (s1, s2) per slot ----
         uint32_t s1[K], s2[K], wv[K];
         if (cur_src == SRC_CACHE) {
@@ -921,6 +985,7 @@ restart:
             pk1 += (c00 - base) | ((c11 - base) << 16);
             if (kCount) { wv[k] += 1; if (lane + 32u * k < a_cur) cells += wv[k]; }
         }
+#endif
         const uint32_t r0 = wsum(pk0), r1 = wsum(pk1);
 
         // the common expansion (a heterozygous choice was made earlier, the column is not ignored) has all four children:
@@ -953,6 +1018,34 @@ restart:
 
         // ---- children vectors into the next column's slot order (off the critical path) ----
         {
+#if HP_SUB_PACKED
+            const uint32_t a_next = o_p2 - o_p1;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (k > 0 && a_next <= 32u * k) {                        // the next column has no read in this slot
+                    nX[k] = nY[k] = nW[k] = 0;
+                    colc[k] = kEmpty;
+                    coln[k] = colnn[k];
+                    continue;
+                }
+                const uint32_t cn = (lane + 32u * k < a_next) ? coln[k] : kEmpty;
+                const uint32_t carry = cn >> 16, sl = carry & 31u;
+                uint32_t g0 = __shfl_sync(HP_FULL_MASK, X[0], sl), g1 = __shfl_sync(HP_FULL_MASK, Y[0], sl);
+                uint32_t gw = kCount ? __shfl_sync(HP_FULL_MASK, wv[0], sl) : 0u;
+#pragma unroll
+                for (int kk = 1; kk < K; kk++) {
+                    if (a_cur <= 32u * kk) continue;                     // nothing to carry out of an empty slot
+                    const uint32_t u0 = __shfl_sync(HP_FULL_MASK, X[kk], sl), u1 = __shfl_sync(HP_FULL_MASK, Y[kk], sl);
+                    const uint32_t uw = kCount ? __shfl_sync(HP_FULL_MASK, wv[kk], sl) : 0u;
+                    if ((carry >> 5) == (uint32_t)kk) { g0 = u0; g1 = u1; gw = uw; }
+                }
+                const bool has = carry != 0xffffu;
+                nX[k] = has ? g0 : 0u; nY[k] = has ? g1 : 0u;
+                nW[k] = has ? gw : 0u;
+                colc[k] = cn;
+                coln[k] = colnn[k];
+            }
+#else
             const uint32_t a_next = o_p2 - o_p1;
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -981,6 +1074,7 @@ restart:
                 colc[k] = cn;
                 coln[k] = colnn[k];
             }
+#endif
             o_p = o_p1; o_p1 = o_p2; o_p2 = o_p3;
         }
         cache_first = next_idx; cache_present = present;
