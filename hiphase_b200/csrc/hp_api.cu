@@ -356,7 +356,7 @@ void hp_ctx_destroy(hp_ctx* ctx) {
         if (l) { if (l->used) cudaEventSynchronize(l->ev_done); delete l->job; lane_destroy(l); }
     }
     for (DevBuf* b : {&ctx->ticket, &ctx->slabs, &ctx->slab_busy, &ctx->stage_in, &ctx->stage_out, &ctx->wfa_ws, &ctx->wfa_in,
-                      &ctx->wfa_out, &ctx->wfa_graph, &ctx->comm_send, &ctx->comm_recv})
+                      &ctx->wfa_out, &ctx->wfa_graph, &ctx->comm_send, &ctx->comm_recv, &ctx->ed_scratch})
         b->release();
     ctx->pin_send.release(); ctx->pin_recv.release();
     ctx->realign_rb.release(); ctx->realign_rq.release();

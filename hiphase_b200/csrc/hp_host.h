@@ -107,6 +107,7 @@ struct hp_ctx {
     uint32_t dbg_blocks = 0;
     // staging / scratch of the other entry points (WFA, local realignment, assembly, post-solve)
     hp::DevBuf ticket, stage_in, stage_out;
+    hp::DevBuf ed_scratch;                  // local realignment / edit distance: per-warp delta rows of multi-panel comparisons
     // WFA workspaces
     hp::DevBuf wfa_ws, wfa_in, wfa_out, wfa_graph;
     bool wfa_no_filter = false;             // test aid: never short-circuit hopeless reads (piece filter off)

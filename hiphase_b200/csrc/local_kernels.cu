@@ -59,11 +59,13 @@ struct LocalArgs {
     uint32_t* t_clip2;
     int64_t* del_end;      // SV deletion called ALT: first_end_coordinate
     uint32_t* ticket;
+    int8_t* ed_scratch;    // per-warp row of horizontal deltas for patterns beyond one panel (nullptr: none needed)
+    uint64_t ed_stride;
 };
 
 constexpr uint32_t kPending = 4u, kUnhandled = 8u, kBadSlice = 16u, kTooLong = 32u, kSvDelAlt = 64u;
 constexpr int kLocalWarps = 4;
-constexpr int kCoopK = 8;                    // 64-base blocks per lane in the systolic path: m <= 32*8*64 = 16384
+constexpr int kCoopK = 8;                    // 64-base blocks per lane in the systolic path: 32*8*64 = 16384 pattern rows per panel
 constexpr uint32_t kEdTooLong = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t base_code(uint8_t c) {
@@ -145,12 +147,20 @@ __device__ uint32_t ed_small(const uint8_t* pat, uint32_t m, const uint8_t* txt,
 // Warp-systolic multi-word version: lane b owns the 64-base pattern blocks [b*K, b*K+K); at step t it processes text
 // character t-b, taking the horizontal carry of its first block from lane b-1's last block of the previous step.
 // peq: shared memory, [(k*4 + letter)*32 + lane].  Every lane returns the distance.  m > 64 (else use ed_small).
-__device__ uint32_t ed_coop(const uint8_t* pat, uint32_t m, const uint8_t* txt, uint32_t n, uint64_t* peq, uint32_t lane) {
+// Patterns beyond one panel (kPanelRows = 32 lanes x kCoopK blocks x 64 rows) are processed panel after panel: the horizontal
+// deltas leaving a panel's last row (one per text character, in hbuf[0..n)) enter the next panel's first row where the first
+// panel takes the constant +1 of the global distance.  hbuf == nullptr: no scratch, such a pattern returns kEdTooLong.
+constexpr uint32_t kPanelRows = 32u * kCoopK * 64u;
+
+// One panel: pattern rows pat[0..m), m <= kPanelRows.  kFirst: the horizontal delta entering row 0 is the constant +1, else
+// hbuf[j]; kLast: the distance is tracked at the panel's last row (score), else the deltas leaving it go to hbuf[j].
+template <bool kFirst, bool kLast>
+__device__ __forceinline__ int ed_panel(const uint8_t* pat, uint32_t m, const uint8_t* txt, uint32_t n, uint64_t* peq, uint32_t lane,
+                                        volatile int8_t* hbuf, int score, uint32_t& last_lane) {
     const uint32_t nblk = (m + 63) >> 6;
     const uint32_t K = (nblk + 31) >> 5;
-    if (K > (uint32_t)kCoopK) return kEdTooLong;
     const uint32_t b0 = lane * K;                                  // first block of this lane
-    const uint32_t last_lane = (nblk - 1) / K;
+    last_lane = (nblk - 1) / K;
     // pattern masks
     for (uint32_t k = 0; k < K; k++) {
         uint64_t pA = 0, pC = 0, pG = 0, pT = 0;
@@ -170,16 +180,15 @@ __device__ uint32_t ed_coop(const uint8_t* pat, uint32_t m, const uint8_t* txt, 
     uint64_t Pv[kCoopK], Mv[kCoopK];
 #pragma unroll
     for (int k = 0; k < kCoopK; k++) { Pv[k] = ~0ull; Mv[k] = 0; }
-    int score = (int)m;
     const uint32_t top_bit = (m - 1) & 63u;
     int hout_prev = 0;
     const uint32_t steps = n + last_lane;
     uint8_t ch_next = (lane == 0 && n > 0) ? txt[0] : 0;
     for (uint32_t t = 0; t < steps; t++) {
         int hin = __shfl_up_sync(HP_FULL_MASK, hout_prev, 1);
-        if (lane == 0) hin = 1;
         const int64_t j = (int64_t)t - (int64_t)lane;
         const bool active = j >= 0 && j < (int64_t)n && lane <= last_lane;
+        if (lane == 0) hin = (kFirst || !active) ? 1 : (int)hbuf[j];
         const uint8_t ch = ch_next;
         // the next step's character: t + 1 - lane
         {
@@ -205,7 +214,7 @@ __device__ uint32_t ed_coop(const uint8_t* pat, uint32_t m, const uint8_t* txt, 
                     uint64_t Ph = Mv[k] | ~(Xh | Pv[k]);
                     uint64_t Mh = Pv[k] & Xh;
                     int hout = 0;
-                    if (g == nblk - 1) {                            // the distance is tracked at the pattern's last row
+                    if (kLast && g == nblk - 1) {                   // the distance is tracked at the pattern's last row
                         if ((Ph >> top_bit) & 1ull) score++; else if ((Mh >> top_bit) & 1ull) score--;
                     }
                     if (Ph >> 63) hout = 1; else if (Mh >> 63) hout = -1;
@@ -217,9 +226,32 @@ __device__ uint32_t ed_coop(const uint8_t* pat, uint32_t m, const uint8_t* txt, 
                 }
             }
             hout_prev = hin;
+            // a panel that is not the last one is full and ends on a block boundary: the delta leaving its last row feeds the
+            // next panel (lane 0 read hbuf[j] of this panel last_lane steps ago, so the row is reused in place)
+            if (!kLast && lane == last_lane) hbuf[j] = (int8_t)hin;
         }
     }
     __syncwarp();
+    return score;
+}
+
+// patterns of several panels (rare: an SV allele and a read slice both beyond 16384 bases)
+__device__ __noinline__ uint32_t ed_coop_long(const uint8_t* pat, uint32_t m, const uint8_t* txt, uint32_t n, uint64_t* peq,
+                                              uint32_t lane, volatile int8_t* hbuf) {
+    uint32_t last_lane = 0;
+    int score = ed_panel<true, false>(pat, kPanelRows, txt, n, peq, lane, hbuf, (int)m, last_lane);
+    uint32_t p0 = kPanelRows;
+    for (; m - p0 > kPanelRows; p0 += kPanelRows)
+        score = ed_panel<false, false>(pat + p0, kPanelRows, txt, n, peq, lane, hbuf, score, last_lane);
+    score = ed_panel<false, true>(pat + p0, m - p0, txt, n, peq, lane, hbuf, score, last_lane);
+    return (uint32_t)__shfl_sync(HP_FULL_MASK, score, last_lane);
+}
+
+__device__ __forceinline__ uint32_t ed_coop(const uint8_t* pat, uint32_t m, const uint8_t* txt, uint32_t n, uint64_t* peq, uint32_t lane,
+                                            volatile int8_t* hbuf = nullptr) {
+    if (m > kPanelRows) return hbuf ? ed_coop_long(pat, m, txt, n, peq, lane, hbuf) : kEdTooLong;
+    uint32_t last_lane = 0;
+    const int score = ed_panel<true, true>(pat, m, txt, n, peq, lane, nullptr, (int)m, last_lane);
     return (uint32_t)__shfl_sync(HP_FULL_MASK, score, last_lane);
 }
 
@@ -247,6 +279,7 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_realign_kernel(LocalAr
     __shared__ uint32_t job_s[kLocalWarps];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint64_t* peq = peq_s[warp];
+    volatile int8_t* hbuf = a.ed_scratch ? a.ed_scratch + (uint64_t)(blockIdx.x * kLocalWarps + warp) * a.ed_stride : nullptr;
     for (;;) {
         if (lane == 0) job_s[warp] = atomicAdd(a.ticket, 1u);
         __syncwarp();
@@ -422,7 +455,7 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_realign_kernel(LocalAr
                     const uint8_t* xb = (const uint8_t*)__shfl_sync(HP_FULL_MASK, (unsigned long long)(which ? c1 : c0), src);
                     const uint32_t la = __shfl_sync(HP_FULL_MASK, n, src), lb = __shfl_sync(HP_FULL_MASK, which ? l1 : l0, src);
                     const bool a_short = la <= lb;
-                    const uint32_t d = ed_coop(a_short ? xa : xb, a_short ? la : lb, a_short ? xb : xa, a_short ? lb : la, peq, lane);
+                    const uint32_t d = ed_coop(a_short ? xa : xb, a_short ? la : lb, a_short ? xb : xa, a_short ? lb : la, peq, lane, hbuf);
                     if ((int)lane == src) { if (which) d1 = d; else d0 = d; }
                 }
             }
@@ -487,6 +520,8 @@ struct EdArgs {
     const uint64_t* b_off;
     const uint32_t* b_len;
     uint32_t* dist;
+    int8_t* ed_scratch;
+    uint64_t ed_stride;
 };
 
 __global__ void __launch_bounds__(kLocalWarps * 32) edit_distance_kernel(EdArgs a) {
@@ -503,7 +538,7 @@ __global__ void __launch_bounds__(kLocalWarps * 32) edit_distance_kernel(EdArgs 
         const uint32_t m = x_short ? lx : ly, n = x_short ? ly : lx;
         uint32_t d;
         if (m <= 64u) { d = 0; if (lane == 0) d = ed_small(pat, m, txt, n); d = __shfl_sync(HP_FULL_MASK, d, 0); }
-        else d = ed_coop(pat, m, txt, n, peq_s[warp], lane);
+        else d = ed_coop(pat, m, txt, n, peq_s[warp], lane, a.ed_scratch ? a.ed_scratch + (uint64_t)gw * a.ed_stride : nullptr);
         if (lane == 0) a.dist[p] = d;
         __syncwarp();
     }
@@ -588,7 +623,21 @@ extern "C" int hp_local_realign_batch(hp_ctx* ctx, const hp_local_batch* b, hp_l
     a.del_end = (int64_t*)carve(8 * n_cells);
     a.ticket = (uint32_t*)ctx->ticket.ptr;
     ok &= cudaMemsetAsync(a.ticket, 0, 4, st) == cudaSuccess;
-    const int grid = (int)std::min<uint64_t>(((uint64_t)nj + kLocalWarps - 1) / kLocalWarps, (uint64_t)ctx->sm_count * 8);
+    int grid = (int)std::min<uint64_t>(((uint64_t)nj + kLocalWarps - 1) / kLocalWarps, (uint64_t)ctx->sm_count * 8);
+    // comparisons with more than one panel of pattern rows (both the read slice and an allele beyond 16384 bases) carry a row of
+    // horizontal deltas per warp from panel to panel
+    a.ed_scratch = nullptr; a.ed_stride = 0;
+    {
+        uint64_t max_allele = 0, max_read = 0;
+        for (uint32_t k = 0; k < nvt; k++) max_allele = std::max<uint64_t>(max_allele, std::max(t.allele0_len[k], t.allele1_len[k]));
+        for (uint32_t j = 0; j < nj; j++) max_read = std::max<uint64_t>(max_read, b->read_off[j + 1] - b->read_off[j]);
+        if (max_allele > kPanelRows && max_read > kPanelRows) {
+            grid = std::min(grid, ctx->sm_count * 2);
+            a.ed_stride = al256(std::max(max_allele, max_read));
+            if (!ctx->ed_scratch.reserve((size_t)grid * kLocalWarps * a.ed_stride)) return fail(HP_ERR_OUT_OF_MEMORY, "edit distance scratch allocation failed");
+            a.ed_scratch = (int8_t*)ctx->ed_scratch.ptr;
+        }
+    }
     if (ctx->ev0) { cudaEventRecord(ctx->ev0, st); }
     local_realign_kernel<<<grid, kLocalWarps * 32, 0, st>>>(a);
     if (ctx->ev1) { cudaEventRecord(ctx->ev1, st); ctx->timing_pending = true; }
@@ -626,7 +675,19 @@ extern "C" int hp_edit_distance_batch(hp_ctx* ctx, uint32_t n_pairs, const uint8
     a.a_off = (const uint64_t*)up(a_off, 8 * (size_t)n_pairs); a.a_len = (const uint32_t*)up(a_len, 4 * (size_t)n_pairs);
     a.b_off = (const uint64_t*)up(b_off, 8 * (size_t)n_pairs); a.b_len = (const uint32_t*)up(b_len, 4 * (size_t)n_pairs);
     a.dist = (uint32_t*)ctx->stage_out.ptr;
-    const int grid = (int)std::min<uint64_t>(((uint64_t)n_pairs + kLocalWarps - 1) / kLocalWarps, (uint64_t)ctx->sm_count * 8);
+    int grid = (int)std::min<uint64_t>(((uint64_t)n_pairs + kLocalWarps - 1) / kLocalWarps, (uint64_t)ctx->sm_count * 8);
+    a.ed_scratch = nullptr; a.ed_stride = 0;
+    {
+        uint64_t longest = 0;                                            // text length of the pairs whose pattern spans several panels
+        for (uint32_t i = 0; i < n_pairs; i++)
+            if (std::min(a_len[i], b_len[i]) > kPanelRows) longest = std::max<uint64_t>(longest, std::max(a_len[i], b_len[i]));
+        if (longest) {
+            grid = std::min(grid, ctx->sm_count * 2);
+            a.ed_stride = al256(longest);
+            if (!ctx->ed_scratch.reserve((size_t)grid * kLocalWarps * a.ed_stride)) return fail(HP_ERR_OUT_OF_MEMORY, "edit distance scratch allocation failed");
+            a.ed_scratch = (int8_t*)ctx->ed_scratch.ptr;
+        }
+    }
     edit_distance_kernel<<<grid, kLocalWarps * 32, 0, st>>>(a);
     ok &= cudaGetLastError() == cudaSuccess;
     ctx->launches++;

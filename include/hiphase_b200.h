@@ -365,8 +365,8 @@ int hp_wfa_graph_align(hp_ctx* ctx, uint32_t n_nodes, const uint8_t* seq, const 
 #define HP_LOCAL_UNHANDLED_TYPE    1   /* a reachable variant is SvDuplication / SvInversion / SvBreakend / Unknown:  */
                                        /* the reference panics (read_parsing.rs:320-322, 452-454)                   */
 #define HP_LOCAL_BAD_SLICE         2   /* start index after end index in the read: the reference panics on the slice */
-#define HP_LOCAL_ALLELE_TOO_LONG   3   /* an inexact comparison with BOTH sequences longer than 16384 bases: outside  */
-                                       /* the kernel's range                                                        */
+#define HP_LOCAL_ALLELE_TOO_LONG   3   /* reserved: no longer reported (comparisons of two sequences beyond 16384     */
+                                       /* bases run panel by panel; the reference's grid has no length limit either) */
 
 /* bits of hp_local_out.match_class (the per-variant inputs of ReadStats, read_parsing.rs:457-477) */
 #define HP_LOCAL_OVERLAPS  1           /* overlaps_allele                                                           */
@@ -412,7 +412,7 @@ typedef struct hp_local_out {
 int hp_local_realign_batch(hp_ctx* ctx, const hp_local_batch* batch, hp_local_out* out);
 
 /* sequence_alignment::edit_distance for n_pairs pairs: a = bytes[a_off[i] .. +a_len[i]), b likewise.  Host buffers.
- * dist[i] = UINT32_MAX when both sequences are longer than 16384 bases (outside the kernel's range). */
+ * Any lengths: pairs whose shorter side exceeds 16384 bases are processed in panels of 16384 pattern rows. */
 int hp_edit_distance_batch(hp_ctx* ctx, uint32_t n_pairs, const uint8_t* bytes, uint64_t n_bytes,
                            const uint64_t* a_off, const uint32_t* a_len, const uint64_t* b_off, const uint32_t* b_len,
                            uint32_t* dist);

@@ -145,3 +145,36 @@ def test_block_service_packs_concurrent_one_block_calls():
     h1, h2, st = svc.solve_one(batch, 3)
     assert np.array_equal(h1, ref.h1[int(batch.var_off[3]):int(batch.var_off[4])])
     svc.close()
+
+
+def test_full_c3_one_batch_equals_chunks_in_flight():
+    """BASELINE.json configs[2] at full size (the 10 000 blocks bench.py times): solved as one batch and as four interleaved
+    chunks in flight on the lanes, the results are the same bytes block for block (a block's result does not depend on what it
+    was batched with, nor on the team size / device share its launch got), and the size-independent invariants hold."""
+    ctx = lib.Context(device=0)
+    ctx.set_lanes(4)
+    ids = np.arange(10000, dtype=np.uint64)
+    whole = synth.stream_blocks(ids)
+    out = ctx.astar_solve_batch(whole)
+    assert (out.status == 0).all(), np.bincount(out.status)
+    st = out.stats
+    n = np.diff(whole.var_off.astype(np.int64))
+    assert (st["actual_cost"] >= st["estimated_cost"]).all()                                   # phase_stats.rs:163
+    assert ((st["phased_variants"] + st["homozygous_variants"] + st["skipped_variants"]) == n).all()
+    ign = whole.ignored.astype(bool)
+    assert (out.h1[ign] == 2).all() and (out.h2[ign] == 2).all() and (out.h1[~ign] < 2).all() and (out.h2[~ign] < 2).all()
+    assert (st["pruned_solutions"] > 0).sum() >= 50                                            # the noisy 2 % prune
+    parts = [ids[k::4] for k in range(4)]
+    batches = [synth.stream_blocks(p) for p in parts]
+    handles = [ctx.astar_submit(b) for b in batches]
+    for p, b, h in zip(parts, batches, handles):
+        o = ctx.astar_wait(h)
+        assert (o.status == 0).all()
+        assert np.array_equal(o.stats, st[p.astype(np.int64)])
+        for k in range(0, len(p), 97):                                                         # haplotype bytes of every 97th block
+            v0, v1 = int(whole.var_off[int(p[k])]), int(whole.var_off[int(p[k]) + 1])
+            c0 = int(b.var_off[k])
+            assert np.array_equal(o.h1[c0:c0 + v1 - v0], out.h1[v0:v1]) and np.array_equal(o.h2[c0:c0 + v1 - v0], out.h2[v0:v1])
+    again = ctx.astar_solve_batch(whole)                                                       # idempotence
+    assert np.array_equal(again.h1, out.h1) and np.array_equal(again.h2, out.h2) and np.array_equal(again.stats, st)
+    ctx.close()

@@ -182,10 +182,52 @@ def test_gpu_edit_distance_random(ctx):
         assert int(x) == O.edit_distance(a, b), (len(a), len(b))
 
 
+def _mutated(rng, a, p_sub=0.01, p_del=0.003, p_ins=0.003):
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    b = a.copy()
+    idx = rng.random(len(b)) < p_sub
+    b[idx] = letters[rng.integers(0, 4, int(idx.sum()))]
+    b = np.delete(b, np.flatnonzero(rng.random(len(b)) < p_del))
+    for pos in sorted(rng.integers(0, len(b), int(len(b) * p_ins)), reverse=True):
+        b = np.insert(b, pos, letters[rng.integers(0, 4)])
+    return b
+
+
 @pytest.mark.gpu
-def test_gpu_edit_distance_out_of_range(ctx):
-    a = np.full(16385 + 64, ord("A"), np.uint8)
-    assert int(ctx.edit_distance_batch([(a, a)])[0]) == 0xFFFFFFFF      # both sides above 16384 bases: reported, never wrong
+def test_gpu_edit_distance_beyond_one_panel(ctx):
+    """Both sequences longer than one panel of the bit-vector kernel (16384 pattern rows): two and three panels, a pattern that
+    ends exactly on a panel boundary, identical sequences.  The reference's full grid has no length limit
+    (sequence_alignment.rs:6-38)."""
+    rng = np.random.default_rng(99)
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    a1 = letters[rng.integers(0, 4, 16385 + 64)]
+    a2 = letters[rng.integers(0, 4, 20000)]
+    a3 = letters[rng.integers(0, 4, 33100)]
+    a4 = letters[rng.integers(0, 4, 2 * 16384)]
+    pairs = [(a1, a1), (a2, _mutated(rng, a2)), (_mutated(rng, a3), a3), (a4, np.concatenate([_mutated(rng, a4), a2[:300]])),
+             (a2, letters[rng.integers(0, 4, 17000)])]
+    d = ctx.edit_distance_batch(pairs)
+    assert int(d[0]) == 0
+    for (a, b), x in zip(pairs[1:], d[1:]):
+        assert int(x) == O.edit_distance(a, b), (len(a), len(b))
+
+
+@pytest.mark.gpu
+def test_gpu_local_realign_sv_insertion_beyond_one_panel(ctx):
+    """A 17 kb SV insertion inside a read that carries a noisy copy of it: closest_allele_clip compares two sequences that are
+    both longer than one panel (variants.rs:598-641)."""
+    rng = np.random.default_rng(17)
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    ref = letters[rng.integers(0, 4, 240)].tobytes()
+    ins = letters[rng.integers(0, 4, 17000)]
+    sv = Variant(0, 4, 100, 1, ref[100:101], ref[100:101] + ins.tobytes())
+    snv = Variant(0, 0, 180, 1, ref[180:181], b"A" if ref[180:181] != b"A" else b"C")
+    got = _mutated(rng, ins).tobytes()
+    read = ref[:101] + got + ref[101:]
+    job = _single_job([sv, snv], 0, [(0, 0, 101), (101, 101 + len(got), len(ref) - 101)], read, [30] * len(read))
+    ref_out = O.local_realign(job)
+    assert int(ref_out.alleles[0]) == 1 and 0 < int(ref_out.edit_distance.reshape(-1, 2)[0, 1]) < 2000
+    _same(ctx.local_realign_batch(job), ref_out)
 
 
 @pytest.mark.gpu
