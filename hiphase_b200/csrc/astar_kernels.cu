@@ -2203,6 +2203,14 @@ constexpr int kMaxTeam = HP_MAX_TEAM;
 #ifndef HP_CTAS_PER_SM
 #define HP_CTAS_PER_SM (16 / HP_MAX_TEAM)
 #endif
+// The "dense" build of the production kernels: 20 warps per SM in 96 registers.  The sub-solver's dive stays in registers (the
+// packed score vectors made room), the main loop and the real-pop path spill, so a block's chain is ~25 % slower -- but with
+// batches in flight (throughput regime: more blocks than warps) five warps per scheduler cover the dive's dependent chain
+// better than four: +10 % blocks/s on the C3 stream (profiles/r2l_warps_per_sm.txt).  A launch alone on the device, and any
+// launch with fewer blocks than warps, keeps the 128-register build (its length is its slowest block's chain).
+#ifndef HP_CTAS_PER_SM_DENSE
+#define HP_CTAS_PER_SM_DENSE (20 / HP_MAX_TEAM)
+#endif
 #ifndef HP_SPEC_FAIL_ROUNDS
 #define HP_SPEC_FAIL_ROUNDS 6
 #endif
@@ -2362,8 +2370,8 @@ constexpr int kSubCaplShared = HP_SUB_CAPL_S;    // sub-solver queue entries per
 
 // One kernel per score-vector class K (1: <= 32 reads per column, 2: <= 64, 0: any) keeps the register footprint of the
 // common class small.  Class c owns order[class_start[c] .. +class_count[c]) and ticket[c].
-template <int K, bool kCount>
-__global__ void __launch_bounds__(kMaxTeam * 32, HP_CTAS_PER_SM) astar_solve_kernel(AstarArgs a) {
+template <int K, bool kCount, bool kDense>
+__global__ void __launch_bounds__(kMaxTeam * 32, kDense ? HP_CTAS_PER_SM_DENSE : HP_CTAS_PER_SM) astar_solve_kernel(AstarArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ TeamShared ts;
     constexpr int cls = (K == 1) ? 0 : (K == 2 ? 1 : 2);
@@ -2486,7 +2494,7 @@ size_t astar_smem_bytes(uint32_t sub_capl, int team) {
     return (size_t)team * capl_s * 32 * sizeof(SubEntry);
 }
 int astar_max_team() { return kMaxTeam; }
-int astar_warps_per_sm() { return HP_CTAS_PER_SM * kMaxTeam; }
+int astar_warps_per_sm(bool dense) { return (dense ? HP_CTAS_PER_SM_DENSE : HP_CTAS_PER_SM) * kMaxTeam; }
 uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl) {
     const uint32_t capl_s = std::min<uint32_t>(sub_capl, kSubCaplShared);
     const uint64_t spill = (uint64_t)kMaxTeam * sub_spill_bytes(sub_capl, capl_s);
@@ -2504,19 +2512,24 @@ cudaError_t launch_astar_prep(PrepArgs pa, uint32_t max_block_vars, cudaStream_t
     return cudaGetLastError();
 }
 
-template <int K, bool kCount>
+template <int K, bool kCount, bool kDense = false>
 static cudaError_t launch_one(const AstarArgs& a, int n_ctas, int team, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(astar_solve_kernel<K, kCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(astar_solve_kernel<K, kCount, kDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    astar_solve_kernel<K, kCount><<<n_ctas, team * 32, smem, stream>>>(a);
+    astar_solve_kernel<K, kCount, kDense><<<n_ctas, team * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
 // Three launches (one per score-vector class, each on its own stream so they run side by side); a class without blocks
 // exits at once.
-cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t* streams) {
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t* streams, bool dense) {
     const size_t smem = astar_smem_bytes(a.sub_capl, team);
     cudaError_t e;
+    if (dense && !a.out_counters) {        // the two register-vector classes have a dense build; the generic class is rare
+        if ((e = launch_one<1, false, true>(a, n_ctas, team, smem, streams[0])) != cudaSuccess) return e;
+        if ((e = launch_one<2, false, true>(a, n_ctas, team, smem, streams[1])) != cudaSuccess) return e;
+        return launch_one<0, false>(a, n_ctas, team, smem, streams[2]);
+    }
     if (a.out_counters) {
         if ((e = launch_one<1, true>(a, n_ctas, team, smem, streams[0])) != cudaSuccess) return e;
         if ((e = launch_one<2, true>(a, n_ctas, team, smem, streams[1])) != cudaSuccess) return e;
@@ -2537,8 +2550,9 @@ int astar_max_ctas_per_sm(uint32_t sub_capl) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem) == cudaSuccess) best = std::max(best, nb);
         else cudaGetLastError();
     };
-    probe(astar_solve_kernel<1, false>); probe(astar_solve_kernel<2, false>); probe(astar_solve_kernel<0, false>);
-    probe(astar_solve_kernel<1, true>); probe(astar_solve_kernel<2, true>); probe(astar_solve_kernel<0, true>);
+    probe(astar_solve_kernel<1, false, false>); probe(astar_solve_kernel<2, false, false>); probe(astar_solve_kernel<0, false, false>);
+    probe(astar_solve_kernel<1, true, false>); probe(astar_solve_kernel<2, true, false>); probe(astar_solve_kernel<0, true, false>);
+    probe(astar_solve_kernel<1, false, true>); probe(astar_solve_kernel<2, false, true>);
     return best > 0 ? best : 32;
 }
 

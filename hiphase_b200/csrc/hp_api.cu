@@ -162,20 +162,35 @@ int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_
     // batches in flight each launch takes capacity x over / (busy lanes + 1) warps, so the launches are co-resident and the
     // serial chain of one launch's slowest block runs beside the bulk of the others (a launch that holds the whole grid
     // would keep the next launch's CTAs queued behind it until its bulk has drained).
-    int warps_per_sm = astar_warps_per_sm();
-    if (const char* e = getenv("HP_DBG_WARPS_PER_SM")) warps_per_sm = std::max(1, std::min(warps_per_sm, atoi(e)));   // occupancy experiments
-    const int resident_warps = ctx->sm_count * warps_per_sm;
-    int share_warps = resident_warps;
-    if (busy_lanes > 0) {
-        double over = 1.5;              // measured on C3 (profiles/r2c_sweep.txt): 1.0-1.5 equal within noise, 2.0 slower
-        if (const char* e = getenv("HP_DBG_OVERSUB")) over = std::max(0.25, atof(e));
-        share_warps = (int)std::min<double>(resident_warps, std::max(1.0, resident_warps * over / (busy_lanes + 1)));
+    // Throughput regime (other batches in flight and at least four blocks per warp of this launch's share): the dense build of
+    // the kernels, 20 warps per SM; a launch whose length is its slowest block's chain keeps the 128-register build (C2 steps
+    // of 1000 short blocks over 555 warps lose 20 % with the dense build, C3 steps of 10 000 blocks gain 6 %:
+    // profiles/r2m_dense_ab.txt).
+    bool dense = busy_lanes > 0 && !out->counters;
+    bool force_dense = false;
+    if (const char* e = getenv("HP_DBG_DENSE")) {                        // A/B and profiling aid: 0 = never, 2 = also for a launch alone
+        dense = dense && atoi(e) != 0;
+        if (atoi(e) == 2 && !out->counters) dense = force_dense = true;
     }
-    // team size: use otherwise idle warps for speculative sub-solves (exact, see astar_kernels.cu)
-    int team = 1;
-    // (up to 2x oversubscription of the share still pays: measured on C2, 1000 blocks alone -> team 4)
-    while (team * 2 <= astar_max_team() && (uint64_t)nb * team * 2 <= 2ull * (uint64_t)share_warps) team *= 2;
-    if (ctx->force_team > 0) team = std::min(ctx->force_team, astar_max_team());
+    int share_warps = 0, team = 1;
+    for (;;) {
+        int warps_per_sm = astar_warps_per_sm(dense);
+        if (const char* e = getenv("HP_DBG_WARPS_PER_SM")) warps_per_sm = std::max(1, std::min(warps_per_sm, atoi(e)));   // occupancy experiments
+        const int resident_warps = ctx->sm_count * warps_per_sm;
+        share_warps = resident_warps;
+        if (busy_lanes > 0) {
+            double over = 1.5;              // measured on C3 (profiles/r2c_sweep.txt): 1.0-1.5 equal within noise, 2.0 slower
+            if (const char* e = getenv("HP_DBG_OVERSUB")) over = std::max(0.25, atof(e));
+            share_warps = (int)std::min<double>(resident_warps, std::max(1.0, resident_warps * over / (busy_lanes + 1)));
+        }
+        // team size: use otherwise idle warps for speculative sub-solves (exact, see astar_kernels.cu)
+        team = 1;
+        // (up to 2x oversubscription of the share still pays: measured on C2, 1000 blocks alone -> team 4)
+        while (team * 2 <= astar_max_team() && (uint64_t)nb * team * 2 <= 2ull * (uint64_t)share_warps) team *= 2;
+        if (ctx->force_team > 0) team = std::min(ctx->force_team, astar_max_team());
+        if (dense && !force_dense && (team > 1 || (uint64_t)nb < 4ull * (uint64_t)share_warps)) { dense = false; continue; }   // latency regime after all
+        break;
+    }
     int n_ctas = (int)std::min<uint64_t>(nb, (uint64_t)std::max(1, share_warps / team));
     if (max_ctas > 0) n_ctas = std::min(n_ctas, max_ctas);
     const uint32_t hap_words = (max_block_vars + 63) / 64;
@@ -231,7 +246,7 @@ int astar_device(hp_ctx* ctx, AstarLane* L, const hp_block_batch* batch, uint64_
     HP_CUDA(ctx, cudaEventRecord(L->ev_fork, stream));
     cudaStream_t cls_stream[3] = {stream, L->aux[0], L->aux[1]};
     for (int c = 1; c < 3; c++) HP_CUDA(ctx, cudaStreamWaitEvent(cls_stream[c], L->ev_fork, 0));
-    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, team, cls_stream));
+    HP_CUDA(ctx, launch_astar_solve(a, n_ctas, team, cls_stream, dense));
     for (int c = 1; c < 3; c++) {
         HP_CUDA(ctx, cudaEventRecord(L->ev_join[c - 1], cls_stream[c]));
         HP_CUDA(ctx, cudaStreamWaitEvent(stream, L->ev_join[c - 1], 0));

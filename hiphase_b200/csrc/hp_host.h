@@ -45,10 +45,10 @@ bool upload_large(HostPin& pin, void* dst, const void* src, size_t bytes, cudaSt
 // kernel launchers (astar_kernels.cu)
 size_t astar_smem_bytes(uint32_t sub_capl, int team);
 int astar_max_team();
-int astar_warps_per_sm();
+int astar_warps_per_sm(bool dense = false);
 uint64_t astar_slab_bytes(uint32_t qcap, uint32_t hap_words, uint32_t sub_capl);
 cudaError_t launch_astar_prep(PrepArgs pa, uint32_t max_block_vars, cudaStream_t stream);
-cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t* streams /* [3]: one per class */);
+cudaError_t launch_astar_solve(const AstarArgs& a, int n_ctas, int team, cudaStream_t* streams /* [3]: one per class */, bool dense = false);
 int astar_max_ctas_per_sm(uint32_t sub_capl);
 cudaError_t launch_score_planes_debug(const AstarArgs& a, uint64_t h1, uint64_t h2, int offset, int L, uint32_t* s1, uint32_t* s2,
                                       cudaStream_t stream);
