@@ -11,6 +11,7 @@
 #include <numeric>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <dlfcn.h>
@@ -229,15 +230,19 @@ int hp_comm_gather_results(hp_ctx* ctx, uint64_t n_local, const uint64_t* local_
         send_rec[i].index = local_ids[i]; send_rec[i].status = lo->status[i]; send_rec[i].stats = lo->stats[i];
     }
     for (uint64_t i = n_local; i < max_n; i++) { send_rec[i].index = ~0ull; send_rec[i].status = -1; memset(&send_rec[i].stats, 0, sizeof(hp_phase_stats)); }
-    if (nv_local) { memcpy(send_h, lo->h1, nv_local); memcpy(send_h + hv, lo->h2, nv_local); }
+    if (nv_local) parallel_copy({CopySeg{send_h, lo->h1, (size_t)nv_local}, CopySeg{send_h + hv, lo->h2, (size_t)nv_local}});
     HP_CUDA_S(ctx, cudaMemcpyAsync(ctx->comm_send.ptr, ctx->pin_send.ptr, msg, cudaMemcpyHostToDevice, ctx->stream));
     rc = allgather_dev(ctx, ctx->comm_send.ptr, ctx->comm_recv.ptr, msg);
     if (rc != HP_OK) return rc;
     if (receive) HP_CUDA_S(ctx, cudaMemcpyAsync(ctx->pin_recv.ptr, ctx->comm_recv.ptr, msg * W, cudaMemcpyDeviceToHost, ctx->stream));
     HP_CUDA_S(ctx, cudaStreamSynchronize(ctx->stream));
     if (!receive) return HP_OK;
-    // 3. re-order by global block index
+    // 3. re-order by global block index: a serial pass checks every record and finds where its haplotype bytes start, then a
+    //    few host threads copy the blocks into place (200 000 blocks = three small copies each: ~40 ms on one thread)
     std::vector<uint8_t> seen(n_total, 0);
+    struct Src { const GatherRecord* rec; const uint8_t* h1; const uint8_t* h2; };
+    std::vector<Src> src;
+    src.reserve(n_total);
     for (uint64_t r = 0; r < W; r++) {
         uint64_t v = 0;
         const uint8_t* base = (const uint8_t*)ctx->pin_recv.ptr + r * msg;
@@ -250,11 +255,23 @@ int hp_comm_gather_results(hp_ctx* ctx, uint64_t n_local, const uint64_t* local_
             seen[g.index] = 1;
             const uint64_t n = all_var_off[g.index + 1] - all_var_off[g.index];
             if (v + n > sizes[2 * r + 1]) return fail(ctx, HP_ERR_INVALID_INPUT, "gathered haplotype bytes do not match the variant offsets");
-            memcpy(ao->h1 + all_var_off[g.index], h1 + v, n); memcpy(ao->h2 + all_var_off[g.index], h2 + v, n);
-            ao->stats[g.index] = g.stats; ao->status[g.index] = (int32_t)g.status;
+            src.push_back({&g, h1 + v, h2 + v});
             v += n;
         }
     }
+    auto place = [&](size_t lo_i, size_t hi_i) {
+        for (size_t k = lo_i; k < hi_i; k++) {
+            const GatherRecord& g = *src[k].rec;
+            const uint64_t o = all_var_off[g.index], n = all_var_off[g.index + 1] - o;
+            memcpy(ao->h1 + o, src[k].h1, n); memcpy(ao->h2 + o, src[k].h2, n);
+            ao->stats[g.index] = g.stats; ao->status[g.index] = (int32_t)g.status;
+        }
+    };
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())), src.size() / 8192));
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; t++) th.emplace_back(place, src.size() * t / nt, src.size() * (t + 1) / nt);
+    place(0, src.size() / nt);
+    for (std::thread& t : th) t.join();
     return HP_OK;
 }
 
