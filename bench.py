@@ -535,6 +535,11 @@ def main():
             ref, sb, dt = cpu_oracle(wl, ids, threads)
             line["cpu_baseline"] = {"value": len(ids) / dt, "unit": "blocks/s", "cores": threads, "kind": "port",
                                     "sample": wl.sample_text() + "; %.1f s wall" % dt}
+            if args.config in ("auto", "c3") and world == 1:      # the CPU figure at one thread next to all threads
+                ids1 = wl.sample_ids(0, 50)
+                _, _, dt1 = cpu_oracle(wl, ids1, 1)
+                line["cpu_baseline"]["one_thread"] = {"value": len(ids1) / dt1, "unit": "blocks/s", "cores": 1,
+                                                      "sample": wl.sample_text(50) + "; %.1f s wall" % dt1}
             # parity of the GPU's end-to-end results with the oracle on that sample
             ok = True
             for i, g in enumerate(ids.astype(np.int64)):
