@@ -203,8 +203,11 @@ void hp_service_destroy(hp_service* svc);
  * library: submit gathers the inputs into the lane's pinned staging with a few host threads (it may then be reused at
  * once, though the contract above does not promise it), the results land in pinned staging and hp_astar_wait copies them
  * into *out -- so the results of a pageable job are in *out only after hp_astar_wait, not when hp_astar_poll reports done.
- * C3 end to end: 115 k blocks/s pinned, 93 k pageable (37 k before the staging: a cudaMemcpyAsync to pageable memory
+ * C3 end to end: 116 k blocks/s pinned, 104 k pageable (37 k before the staging: a cudaMemcpyAsync to pageable memory
  * blocks the caller until the stream gets there).
+ * Which build of the solver kernels a batch gets is decided per launch: with other batches in flight and at least four
+ * blocks per warp of the launch's share of the device it is the 20-warps-per-SM build (throughput), else the 16-warp one
+ * (shortest chain per block).  Results do not depend on it.
  * hp_astar_wait blocks until the results are in *out (overflowed blocks are re-run there, as in hp_astar_solve_batch)
  * and releases the job.  Submitting more jobs than lanes waits for the oldest job's device work first.
  * HP_OK from wait / solve_batch means the call ran: each block's own outcome is in out->status[] (HP_BLOCK_*).
