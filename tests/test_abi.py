@@ -48,3 +48,74 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "hp_oracle" not in txt and "oracle_lib" not in txt and "libhp_oracle" not in txt, f
+
+
+def _c_compile_and_run(tmp_path, source, link=False):
+    import subprocess
+    src = tmp_path / "probe.c"
+    exe = tmp_path / "probe"
+    src.write_text(source)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)]
+    if link:
+        cmd += ["-L", lib.CSRC, "-lhiphase_b200", "-Wl,-rpath," + lib.CSRC]
+    subprocess.run(cmd, check=True)
+    return subprocess.run([str(exe)], capture_output=True, text=True)
+
+
+def test_header_is_plain_c_and_the_ctypes_mirrors_match_it(tmp_path):
+    """include/hiphase_b200.h compiles as C99 (-pedantic -Werror), and every struct mirrored in _abi.py has the size and the
+    field offsets the C compiler gives it (same field names, same order)."""
+    structs = [(n, getattr(A, n)) for n in dir(A) if n.startswith("hp_") and isinstance(getattr(A, n), type)
+               and issubclass(getattr(A, n), C.Structure)]
+    assert len(structs) >= 18
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hiphase_b200.h"', 'int main(void) {']
+    for name, cls in structs:
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f[0], name, f[0]))
+    lines += ['  return 0;', '}']
+    r = _c_compile_and_run(tmp_path, "\n".join(lines))
+    assert r.returncode == 0, r.stderr
+    got = dict(l.split() for l in r.stdout.strip().splitlines())
+    for name, cls in structs:
+        assert int(got[name]) == C.sizeof(cls), name
+        for f in cls._fields_:
+            assert int(got["%s.%s" % (name, f[0])]) == getattr(cls, f[0]).offset, (name, f[0])
+
+
+def test_c_program_links_the_library_and_gets_the_no_device_error(tmp_path):
+    """A C99 caller (what a cc + bindgen build of HiPhase would link): host-only entries work, hp_ctx_create reports
+    HP_ERR_NO_DEVICE without a GPU instead of falling back to anything."""
+    import torch
+    lib.build()
+    src = r'''
+#include <stdio.h>
+#include <string.h>
+#include "hiphase_b200.h"
+int main(void) {
+    hp_params p;
+    uint32_t n_var[5] = {2000, 20, 300, 40, 1000};
+    uint64_t n_cells[5] = {60000, 600, 9000, 1200, 30000};
+    uint64_t cost[5];
+    uint32_t shard[5];
+    hp_ctx* ctx = NULL;
+    int rc;
+    hp_default_params(&p);
+    if (hp_abi_version() != HP_ABI_VERSION) return 10;
+    if (p.min_queue_size != 1000 || p.queue_increment != 3) return 11;
+    if (hp_block_costs(5, n_var, n_cells, cost) != HP_OK) return 12;
+    if (hp_lpt_partition(cost, 5, 2, shard) != HP_OK) return 13;
+    if (shard[0] == shard[4]) return 14;                 /* the two heaviest blocks go to different shards */
+    rc = hp_ctx_create(&p, 0, &ctx);
+    printf("%d %s\n", rc, hp_last_error(NULL));
+    if (rc == HP_OK) hp_ctx_destroy(ctx);
+    return 0;
+}
+'''
+    r = _c_compile_and_run(tmp_path, src, link=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    rc = int(r.stdout.split()[0])
+    if torch.cuda.is_available():
+        assert rc == A.HP_OK
+    else:
+        assert rc == A.HP_ERR_NO_DEVICE and "no CPU fallback" in r.stdout
