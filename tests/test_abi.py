@@ -119,3 +119,56 @@ int main(void) {
         assert rc == A.HP_OK
     else:
         assert rc == A.HP_ERR_NO_DEVICE and "no CPU fallback" in r.stdout
+
+
+def _check_rust_structs(text, at_least):
+    found = re.findall(r"#\[repr\(C\)\]\s*(?:#\[derive\([^)]*\)\]\s*)?pub struct (\w+)\s*\{(.*?)\}", text, flags=re.S)
+    found = [(n, b) for n, b in found if "_private" not in b]
+    assert len(found) >= at_least, [n for n, _ in found]
+    prim = {"u8": 1, "i8": 1, "u16": 2, "u32": 4, "i32": 4, "c_int": 4, "f32": 4, "u64": 8, "i64": 8, "usize": 8, "f64": 8}
+
+    def size_align(ty):
+        ty = ty.strip()
+        if ty.startswith("*"):
+            return 8, 8
+        if ty in prim:
+            return prim[ty], prim[ty]
+        cls = getattr(A, ty)                       # a nested struct of the header
+        return C.sizeof(cls), C.alignment(cls)
+    for name, body in found:
+        cls = getattr(A, name)
+        fields = re.findall(r"pub (\w+)\s*:\s*([^,]+?)\s*(?:,|$)", body.strip(), flags=re.S)
+        assert [f for f, _ in fields] == [f[0] for f in cls._fields_], name
+        off = 0
+        for fname, ty in fields:
+            sz, al = size_align(ty)
+            off = (off + al - 1) // al * al
+            assert off == getattr(cls, fname).offset, (name, fname, ty)
+            assert sz == getattr(cls, fname).size, (name, fname, ty)
+            off += sz
+    return [n for n, _ in found]
+
+
+def test_rust_structs_of_the_integration_guide_match_the_header():
+    """The Rust shim in INTEGRATION.md cannot be compiled here (no cargo), so its #[repr(C)] structs are at least held against the
+    header: same field names in the same order, and the offsets repr(C) gives those Rust types equal the C compiler's (through
+    the ctypes mirrors, which the test above pins to the header)."""
+    _check_rust_structs(open(os.path.join(ROOT, "INTEGRATION.md")).read(), 6)
+
+
+def test_generated_rust_bindings_are_current_and_complete():
+    """bindings/rust/b200_ffi.rs (tools/gen_rust_ffi.py: what bindgen would emit from the header) is up to date, declares every
+    exported function and every struct of the header, and its struct layouts equal the C compiler's."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(ROOT, "bindings", "rust", "b200_ffi.rs")).read()
+    assert text == gen.generate(open(gen.HEADER).read()), "run python tools/gen_rust_ffi.py"
+    assert set(re.findall(r"pub fn (hp_\w+)\(", text)) == set(lib.EXPORTS)
+    names = _check_rust_structs(text, 18)
+    mirrored = {n for n in dir(A) if n.startswith("hp_") and isinstance(getattr(A, n), type) and issubclass(getattr(A, n), C.Structure)}
+    assert set(names) == mirrored
+    for n, v in re.findall(r"pub const (HP_\w+): \w+ = (-?\d+);", text):
+        if hasattr(A, n):
+            assert getattr(A, n) == int(v), n
