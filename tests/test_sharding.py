@@ -133,3 +133,36 @@ def test_stream_generator_is_shard_independent():
             c0, c1 = int(a.cell_off[r]), int(a.cell_off[r + 1])
             assert a.alleles[c0] < 2 and a.alleles[c1 - 1] < 2 and (a.alleles[c0:c1] < 2).sum() >= 2
     assert 25 < a.n_cells / a.n_vars < 35
+
+
+def test_bench_workloads_deal_every_block_exactly_once():
+    """bench.py's sharding of the named configurations (host logic of the N-GPU runs): every block of C5 goes to exactly one
+    rank, a rank's chunks partition its shard, the shards' estimated costs are balanced, and both arms sample the same blocks."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world in (1, 2, 8):
+        wl = bench.Workload("c5", world)
+        assert wl.n_total == 200000 and wl.scaling == "strong"
+        seen = np.zeros(wl.n_total, np.int32)
+        costs = []
+        for rank in range(world):
+            ids = wl.rank_ids(rank)
+            seen[ids.astype(np.int64)] += 1
+            costs.append(int(wl.cost[ids.astype(np.int64)].sum()))
+            chunks = wl.chunk_ids(rank, 8)
+            assert sum(len(c) for c in chunks) == len(ids)
+            assert np.array_equal(np.sort(np.concatenate(chunks)), np.sort(ids))
+            # chunks are miniatures of the shard: their costs agree within a few per cent
+            cc = [int(wl.cost[c.astype(np.int64)].sum()) for c in chunks]
+            assert max(cc) <= 1.05 * min(cc)
+        assert (seen == 1).all()
+        assert max(costs) <= 1.001 * min(costs)
+    wl = bench.Workload("c3", 1)
+    assert wl.n_total == 10000 and "configs[2]" in wl.label
+    a, b = wl.sample_ids(3), wl.sample_ids(3)
+    assert np.array_equal(a, b) and len(np.unique(a)) == bench.CPU_SAMPLE_BLOCKS and a.max() < wl.n_total
+    assert not np.array_equal(wl.sample_ids(3), wl.sample_ids(4))
